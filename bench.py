@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — training samples/s (forward + backward + update) of the LeNet-style CNN, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--real f32|f64]
+
+A "step" is one mini-batch of Net::learn (Net.inl:226-317): forward, cost derivative, backward, (all-reduce), update.
+
+N = 1   workload = BASELINE.json configs[1]: LeNet (C 5x5x20 ReLU -> P max 2x2 -> N 100 ReLU -> N 10 softmax), B = 256.
+N > 1   workload = configs[4]: the same net, global mini-batch 8192 sharded over the ranks, per-step NCCL all-reduce of
+        the flat gradient (strong scaling: total work per step is fixed).
+
+`value`     device-timed (CUDA events on the library's stream) over K steps with the data set resident in HBM
+            (65 536 items = 205 MB of inputs, larger than the 126 MB L2; each step gathers a fresh slice of the epoch
+            permutation), max over ranks.
+`e2e`       the same metric through the host-buffer entry point dlb_net_step_host: per step the batch is copied from
+            pinned host memory, and the batch cost is read back (8 bytes) - copies inside the timed region.
+`roofline`  the kernel with the largest share of the step, timed per launch with CUDA events in a separate
+            instrumented pass; algorithmic bytes per launch as defined in DESIGN.md; peak = MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline` / `--impl reference`  the reference's own Net<CpuDC>::learn (oracle/_ref, all host threads) on a bounded
+            sample of the same workload.  oracle/ is used here as the baseline being timed, never by the GPU arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ITEMS = 65536
+LR, LAMBDA = 0.01, 0.1
+CROSS_ENTROPY = 2
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def synthetic_data(n, in_n, out_n, dtype, seed=7):
+    """MNIST-shaped synthetic items: inputs U[0,1), one-hot labels i mod 10."""
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, in_n), dtype=np.float32).astype(dtype)
+    y = np.zeros((n, out_n), dtype)
+    y[np.arange(n), np.arange(n) % out_n] = 1
+    return x, y
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        self.windows = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.flush(); self.f.seek(0)
+        rows = []
+        for line in self.f.read().splitlines():
+            p = [t.strip() for t in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                ts = time.mktime(time.strptime(p[0].split(".")[0], "%Y/%m/%d %H:%M:%S")) + float("0." + p[0].split(".")[1])
+                rows.append((ts, float(p[2]), float(p[3]), float(p[4]), p[5:9]))
+            except (ValueError, IndexError):
+                continue
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        inside = [r for r in rows if any(t0 - 0.05 <= r[0] <= t1 + 0.05 for t0, t1 in self.windows)] or rows
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in inside for i in range(4) if r[4][i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside),
+                "power_w_max": max(r[3] for r in inside), "samples": len(inside), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# algorithmic bytes per launch of each operator tag (DESIGN.md "Roofline accounting")
+# ------------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(net, key: str, batch: int, sz: int) -> float | None:
+    layer_s, tag, kernel = key.split(":")
+    l = int(layer_s)
+    L = net.layers_count()
+    P = net.param_count
+    if tag == "sgd_update":
+        return 3.0 * P * sz
+    if tag == "cost_grad":
+        return 3.0 * batch * net.layer_out_size(L - 1) * sz
+    if l < 0 or l >= L:
+        return None
+    in_n, out_n = net.layer_in_size(l), net.layer_out_size(l)
+    n_par = (net.layer_param_offset(l + 1) if l + 1 < L else P) - net.layer_param_offset(l)
+    spec = net._specs[l]
+    bias_n = out_n if spec.type != 3 else 0
+    weight_n = n_par - bias_n
+    if kernel == "gemm_finalize_kernel":
+        return None          # partial-sum traffic is overhead of the split, not algorithmic
+    if tag in ("conv_fwd", "full_fwd"):
+        return batch * (in_n + 2 * out_n) * sz + n_par * sz
+    if tag == "softmax_fwd":
+        return batch * 3 * out_n * sz
+    if tag == "pool_fwd":
+        return batch * (in_n * sz + out_n * sz + out_n * 4)
+    if tag == "pool_bwd":
+        return batch * (out_n * sz + out_n * 4 + in_n * sz)
+    if tag == "act_grad_bias":
+        return batch * 3 * out_n * sz + bias_n * sz
+    if tag in ("full_dW", "conv_dK"):
+        return batch * (out_n + in_n) * sz + weight_n * sz
+    if tag in ("full_dX", "conv_dX"):
+        return batch * (out_n + in_n) * sz + weight_n * sz
+    return None
+
+
+def step_bytes_per_sample(net, batch: int, sz: int) -> float:
+    """SURVEY.md §8(d) accounting for the whole step: activations once per write and once per read across one fused
+    kernel per layer per direction, index maps 4 B, parameters 6 P per step."""
+    L = net.layers_count()
+    act = 0
+    for l in range(L):
+        in_n, out_n = net.layer_in_size(l), net.layer_out_size(l)
+        aux = out_n                                   # derivatives / index map written forward, read backward
+        fwd = in_n + out_n + aux
+        bwd = out_n + aux + (in_n if l > 0 else 0)    # delta in, aux in, input gradient out (not for layer 0)
+        if net._specs[l].type != 3:
+            bwd += in_n                               # the layer input is re-read for the weight gradient
+        act += fwd + bwd
+    act += 3 * net.layer_out_size(L - 1)              # cost: output, reference, derivative
+    return act * sz + 6.0 * net.param_count * sz / batch
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(real: str, batch: int, steps: int, warmup: int):
+    """Net<CpuDC>::learn of the UNMODIFIED reference (oracle/_ref) with all host threads; falls back to the C port of it
+    (one thread) when the prebuilt library is missing.  One step = one mini-batch."""
+    from oracle import binding as ob
+    specs = ob.lenet_specs()
+    dtype = ob.dtype_of(real)
+    cores = os.cpu_count() or 1
+    n_w, n_t = max(warmup, 1) * batch, steps * batch
+    x, y = synthetic_data(n_w + n_t, 784, 10, dtype)
+    if ob.ref_available():
+        net = ob.RefNet(specs, real, seed=0)
+        net.learn(x[:n_w], y[:n_w], batch, 1, LR, CROSS_ENTROPY, LAMBDA, parallelism=-1, shuffle_seed=1)
+        sec = net.learn(x[n_w:], y[n_w:], batch, 1, LR, CROSS_ENTROPY, LAMBDA, parallelism=-1, shuffle_seed=2)
+        kind, used = "reference", min(cores, batch)
+    else:
+        from tests import helpers as H
+        net = ob.OracleNet(specs, real)
+        net.set_params(H.synthetic_params(net.param_count, specs, real))
+        perm = np.arange(n_t, dtype=np.int64)[None, :]
+        t0 = time.perf_counter()
+        net.learn(x[n_w:], y[n_w:], batch, 1, LR, CROSS_ENTROPY, LAMBDA, 1, perm)
+        sec = time.perf_counter() - t0
+        kind, used = "port", 1
+    return {"value": n_t / sec, "seconds": sec, "kind": kind, "cores": used,
+            "sample": f"{steps} mini-batches of {batch} (= {n_t} items, 1 epoch) after {max(warmup, 1)} warm-up batches"}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2048)
+    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--real", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--batch", type=int, default=0, help="override the (global) mini-batch size")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != max(args.gpus, 1) and world > 1:
+        args.gpus = world
+    n_gpus = max(args.gpus, 1)
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
+    batch = args.batch or (256 if n_gpus == 1 else 8192)
+    workload = ("LeNet-style CNN: CLayer 5x5x20 ReLU -> PLayer max 2x2 -> NLayer 100 ReLU -> NLayer 10 softmax, cross-entropy, "
+                + (f"mini-batch {batch}, 1 B200 (BASELINE configs[1])" if n_gpus == 1 else
+                   f"data-parallel, global mini-batch {batch} sharded over {n_gpus} B200 with NCCL gradient all-reduce (BASELINE configs[4])"))
+    config = {"workload": workload, "global_batch": batch, "n_items": N_ITEMS, "lr": LR, "lambda": LAMBDA,
+              "parallelism": f"dp{n_gpus}", "l2_policy": "inputs larger than L2: 65536-item resident data set (205 MB f32), "
+              "each step gathers a fresh slice of the epoch permutation; no explicit flush"}
+    sz = 4 if args.real == "f32" else 8
+
+    # ---------------- reference arm -----------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ref_steps = min(steps, 64 if batch <= 256 else 8)
+        r = run_reference(args.real, batch, ref_steps, min(warmup, 4))
+        line = {"impl": "reference", "metric": "train_samples_per_sec", "value": r["value"], "unit": "samples/s", "n_gpus": n_gpus,
+                "steps": ref_steps, "warmup": min(warmup, 4), "ms_per_step": 1e3 * r["seconds"] / ref_steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": args.real, "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"], "cpu": cpu_model()},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- our arm -------------------------------------------------------------------------------------
+    import deeplearning_b200 as dl
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist   # plumbing only: rendezvous, barrier, max-over-ranks
+        dist.init_process_group(backend="gloo")
+    ctx = dl.Context(device=local_rank)
+    net = dl.lenet(real=args.real, context=ctx)
+    net.init_params(seed=0)
+    if world > 1:
+        uid = [dl.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        net.set_distributed(rank, world, uid[0])
+    dtype = net.dtype
+    x, y = synthetic_data(N_ITEMS, 784, 10, dtype)
+    net.set_dataset(x, y)
+    net.reset_random_generator(0)
+    cost_id = dl.CostFunctionId.CROSS_ENTROPY
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = dl.Event(ctx), dl.Event(ctx)
+
+    # resident-data throughput
+    net.train_steps(batch, warmup, LR, cost_id, LAMBDA)
+    barrier()
+    launches0 = ctx.launch_count()
+    w0 = time.time()
+    e0.record()
+    items = net.train_steps(batch, steps, LR, cost_id, LAMBDA)
+    e1.record()
+    ms = e0.elapsed_ms(e1)
+    barrier()
+    w1 = time.time()
+    launches = ctx.launch_count() - launches0
+    ms = max_over_ranks(ms)
+    value = items / (ms / 1e3)
+    if sampler:
+        sampler.window(w0, w1)
+
+    # end to end through host buffers (this rank's share of every batch)
+    first, mine = dl.rank_slice(batch, rank, world)
+    e2e_steps = min(steps, 512)
+    n_host = 8
+    hx = dl.pinned_array((n_host, mine, 784), dtype); hy = dl.pinned_array((n_host, mine, 10), dtype)
+    for i in range(n_host):
+        lo = (i * batch + first) % (N_ITEMS - batch)
+        hx[i] = x[lo:lo + mine]; hy[i] = y[lo:lo + mine]
+    reg_factor = LAMBDA / N_ITEMS
+    for i in range(3):
+        net.step_host(hx[i % n_host], hy[i % n_host], LR, cost_id, reg_factor)
+    barrier()
+    w0 = time.time()
+    e0.record()
+    cost = 0.0
+    for i in range(e2e_steps):
+        cost = net.step_host(hx[i % n_host], hy[i % n_host], LR, cost_id, reg_factor)
+    e1.record()
+    e2e_ms = max_over_ranks(e0.elapsed_ms(e1))
+    barrier()
+    w1 = time.time()
+    if sampler:
+        sampler.window(w0, w1)
+    e2e = {"value": e2e_steps * batch / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms / e2e_steps,
+           "h2d_bytes_per_step": int(mine * (784 + 10) * sz), "d2h_bytes_per_step": 8, "steps": e2e_steps,
+           "api": "dlb_net_step_host (pinned host batch in, batch cost out)", "last_batch_cost": cost}
+
+    line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.real,
+            "data": "synthetic", "config": config, "e2e": e2e, "gpu_launches": int(launches)}
+
+    if rank == 0 and n_gpus == 1:
+        # per-kernel pass (instrumented with events; not part of `value`)
+        dl.timing_enable(True)
+        t_steps = min(steps, 64)
+        net.train_steps(batch, t_steps, LR, cost_id, LAMBDA)
+        rep = dl.timing_report()
+        dl.timing_enable(False)
+        total_ms = sum(v[1] for v in rep.values()) or 1.0
+        kernels = []
+        for k, (n, t) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+            ab = algorithmic_bytes(net, k, batch, sz)
+            per_launch_us = 1e3 * t / n
+            kernels.append({"kernel": k, "launches_per_step": n / t_steps, "us_per_launch": per_launch_us, "share": t / total_ms,
+                            "algorithmic_bytes": ab, "gbs": (ab / (per_launch_us * 1e-6) / 1e9) if ab else None})
+        peak, peak_src = hbm_peak()
+        top = kernels[0] if kernels else {"kernel": None, "gbs": None, "share": None, "us_per_launch": None}
+        line["roofline"] = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+                            "frac": (top["gbs"] / peak) if top["gbs"] else None, "traffic": None, "peak_source": peak_src,
+                            "share_of_step": top["share"], "us_per_launch": top["us_per_launch"]}
+        line["kernels"] = kernels[:12]
+        bps = step_bytes_per_sample(net, batch, sz)
+        line["step_roofline"] = {"bytes_per_sample": bps, "roofline_samples_per_s": peak * 1e9 / bps, "frac": value / (peak * 1e9 / bps)}
+
+        # the data-parallel workload's per-GPU share on one GPU, for reading the scaling series
+        net.train_steps(8192, 3, LR, cost_id, LAMBDA)
+        ctx.synchronize()
+        e0.record(); it = net.train_steps(8192, 16, LR, cost_id, LAMBDA); e1.record()
+        line["config5_on_1_gpu"] = {"global_batch": 8192, "value": it / (e0.elapsed_ms(e1) / 1e3), "unit": "samples/s"}
+
+        r = run_reference(args.real, 256, 64, 2)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                "cpu": cpu_model()}
+    if sampler:
+        line["clocks"] = sampler.stop()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,937 @@
+// dlb200.cu — libdlb200.so: context, the batched Net<GpuDC> and the extern "C" boundary (include/dlb200.h).
+//
+// Host-side structure of one training step (Net<D>::learn's per-batch body, Net.inl:226-317, batched):
+//   forward   : one kernel chain per layer over the whole mini-batch, traces (Derivatives / IndexMapping) kept
+//   cost      : derivative of the cost w.r.t. the net output for every sample
+//   backward  : per layer  g = dC/dz, bias gradient (batch sum), weight/filter gradient (batch contraction),
+//               input gradient for every layer but the first (Net.inl:272)
+//   allreduce : (data parallel only) sum of the flat gradient over ranks
+//   update    : one launch over the flat parameter buffer (ALayer.inl:97-122)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <random>
+#include <ranges>
+#include <vector>
+
+#ifndef DLB_CUDA_EMU
+#include <dlfcn.h>
+#endif
+
+#include "../../include/dlb200.h"
+#include "layers.cuh"
+
+namespace dlb {
+
+std::atomic<long long> g_launch_count{0};
+bool g_timing_on = false;
+thread_local const char* g_tag = "";
+thread_local int g_tag_layer = -1;
+
+#ifndef DLB_CUDA_EMU
+// Per-kernel device timing for bench.py's roofline pass: every launch is bracketed by two events on the launching
+// stream; dlb_timing_report() synchronises once and aggregates by "<layer>:<operator tag>:<kernel text>".
+namespace {
+struct TimedLaunch { cudaEvent_t e0, e1; std::string key; };
+std::vector<TimedLaunch> g_timed;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e; DLB_CUDA(cudaEventCreate(&e)); return e;
+}
+}  // namespace
+void timing_begin(cudaStream_t stream, const char* kernel_text) {
+    TimedLaunch t;
+    t.e0 = take_event(); t.e1 = take_event();
+    std::string k(kernel_text);
+    const size_t lt = k.find('<');
+    if (lt != std::string::npos) k = k.substr(0, lt);
+    while (!k.empty() && (k.front() == '(' || k.front() == ' ')) k.erase(k.begin());
+    while (!k.empty() && (k.back() == ')' || k.back() == ' ')) k.pop_back();
+    t.key = std::to_string(g_tag_layer) + ":" + g_tag + ":" + k;
+    DLB_CUDA(cudaEventRecord(t.e0, stream));
+    g_timed.push_back(std::move(t));
+}
+void timing_end(cudaStream_t stream) { DLB_CUDA(cudaEventRecord(g_timed.back().e1, stream)); }
+#else
+void timing_begin(cudaStream_t, const char*) {}
+void timing_end(cudaStream_t) {}
+#endif
+
+thread_local std::string g_last_error;
+
+struct arg_error : std::invalid_argument { using std::invalid_argument::invalid_argument; };
+
+template <class F>
+int guarded(F&& f) noexcept {
+    try { f(); return 0; }
+    catch (const arg_error& e) { g_last_error = e.what(); return 2; }
+    catch (const cuda_error& e) { g_last_error = e.what(); return 3; }
+    catch (const std::exception& e) { g_last_error = e.what(); return 1; }
+    catch (...) { g_last_error = "unknown error"; return 1; }
+}
+
+#define DLB_REQUIRE(cond, msg) do { if (!(cond)) throw ::dlb::arg_error(msg); } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time: whichever libnccl.so.2 the process already has (torch bundles one) is used, else
+// the system library is opened.  Nothing is linked at build time, so a single-GPU process never needs NCCL.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef DLB_CUDA_EMU
+struct NcclApi {
+    typedef struct { char internal[128]; } unique_id;
+    typedef void* comm_t;
+    int (*GetUniqueId)(unique_id*) = nullptr;
+    int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+
+    static NcclApi& get() {
+        static NcclApi api = load();
+        return api;
+    }
+    static NcclApi load() {
+        NcclApi a;
+        void* h = RTLD_DEFAULT;
+        if (!dlsym(h, "ncclAllReduce")) {
+            h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) { a.why = std::string("libnccl.so.2 not found: ") + dlerror(); return a; }
+        }
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+        a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.GetErrorString;
+        if (!a.ok) a.why = "NCCL symbols missing";
+        return a;
+    }
+    void check(int rc, const char* what) const {
+        if (rc != 0) throw std::runtime_error(std::string(what) + ": " + (GetErrorString ? GetErrorString(rc) : "nccl error"));
+    }
+};
+constexpr int kNcclFloat = 7, kNcclDouble = 8, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+#endif
+
+}  // namespace dlb
+
+using namespace dlb;
+
+// =================================================================================================================
+// Context
+// =================================================================================================================
+struct dlb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    GemmWorkspace ws;
+
+    LaunchCtx lc() const { return LaunchCtx{stream, ws}; }
+    void ensure_ws(size_t bytes) {
+        if (bytes <= ws.bytes) return;
+        if (ws.ptr) { DLB_CUDA(cudaStreamSynchronize(stream)); DLB_CUDA(cudaFree(ws.ptr)); ws.ptr = nullptr; ws.bytes = 0; }
+        DLB_CUDA(cudaMalloc(&ws.ptr, bytes));
+        ws.bytes = bytes;
+    }
+};
+
+namespace {
+
+void use_device(const dlb_context* ctx) { DLB_CUDA(cudaSetDevice(ctx->device)); }
+
+template <class T> T* dev_alloc(size_t n) {
+    T* p = nullptr;
+    DLB_CUDA(cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+template <class T> void dev_free(T*& p) {
+    if (p) { cudaFree(p); p = nullptr; }
+}
+
+struct LayerRt {
+    dlb_layer_spec s{};
+    ConvGeom cg{};
+    int out_c = 0, out_h = 0, out_w = 0;
+    int64_t in_n = 0, out_n = 0, param_off = 0, bias_n = 0, weight_n = 0;
+};
+
+// Validates the specs the way the reference's constructors and script loader would (CLayer.inl:29-40,
+// PLayer.inl:27-33, Net.inl:83-88) and lays out the flat parameter buffer.
+std::vector<LayerRt> build_layers(const dlb_layer_spec* specs, int n, int64_t& n_params) {
+    DLB_REQUIRE(specs && n > 0, "Invalid collection of layer dimensions.");
+    std::vector<LayerRt> out((size_t)n);
+    int64_t off = 0;
+    for (int l = 0; l < n; ++l) {
+        LayerRt& L = out[(size_t)l];
+        L.s = specs[l];
+        const auto& s = L.s;
+        L.in_n = (int64_t)s.in_c * s.in_h * s.in_w;
+        L.param_off = off;
+        DLB_REQUIRE(s.in_c > 0 && s.in_h > 0 && s.in_w > 0, "Invalid input size of a layer");
+        switch (s.type) {
+        case DLB_LAYER_FULL:
+            DLB_REQUIRE(s.out_c > 0, "Can't parse output dimensions of NLayer");
+            DLB_REQUIRE(s.activation >= DLB_ACT_SIGMOID && s.activation <= DLB_ACT_LINEAR, "Unknown activation function");
+            L.out_c = 1; L.out_h = 1; L.out_w = s.out_c;
+            L.bias_n = s.out_c; L.weight_n = (int64_t)s.out_c * L.in_n;
+            break;
+        case DLB_LAYER_CONVOLUTION:
+            DLB_REQUIRE(s.out_c > 0, "Can't parse number of filters of CLayer");
+            DLB_REQUIRE(s.win_h > 0 && s.win_w > 0, "Can't parse filter window size of CLayer");
+            DLB_REQUIRE(s.stride_h > 0 && s.stride_w > 0 && s.pad_h >= 0 && s.pad_w >= 0, "Invalid paddings/strides of CLayer");
+            DLB_REQUIRE(s.activation >= DLB_ACT_SIGMOID && s.activation <= DLB_ACT_LINEAR, "Unknown activation function");
+            L.cg = make_conv_geom(s);
+            L.out_c = s.out_c; L.out_h = L.cg.OH; L.out_w = L.cg.OW;
+            L.bias_n = (int64_t)L.out_c * L.out_h * L.out_w;
+            L.weight_n = (int64_t)s.out_c * L.cg.K;
+            break;
+        case DLB_LAYER_PULL:
+            DLB_REQUIRE(s.win_h > 0 && s.win_w > 0, "Can't parse window size of PLayer");
+            DLB_REQUIRE(s.pool_type >= DLB_POOL_MAX && s.pool_type <= DLB_POOL_AVERAGE, "Unsupported pool type");
+            L.out_c = s.in_c;
+            L.out_h = conv_out_size(s.in_h, s.win_h, 0, s.win_h);
+            L.out_w = conv_out_size(s.in_w, s.win_w, 0, s.win_w);
+            break;
+        default: throw arg_error("Unknown layer type");
+        }
+        L.out_n = (int64_t)L.out_c * L.out_h * L.out_w;
+        DLB_REQUIRE(L.out_n > 0, "A layer has an empty output");
+        DLB_REQUIRE(L.in_n < (1LL << 30) && L.out_n < (1LL << 30), "Layer too large");
+        if (l > 0) {
+            const LayerRt& P = out[(size_t)l - 1];
+            const bool ok = s.type == DLB_LAYER_FULL ? P.out_n == L.in_n
+                                                     : (P.out_c == s.in_c && P.out_h == s.in_h && P.out_w == s.in_w);
+            DLB_REQUIRE(ok, "Inconsistent input/output dimensions");
+        }
+        off += L.bias_n + L.weight_n;
+    }
+    n_params = off;
+    return out;
+}
+
+}  // namespace
+
+// =================================================================================================================
+// Net
+// =================================================================================================================
+struct dlb_net {
+    dlb_context* ctx = nullptr;
+    int real_bytes = 4;
+    std::vector<LayerRt> layers;
+    int64_t n_params = 0;
+    std::mt19937 rng{std::random_device{}()};  // Net<D>::ran_gen, Net.inl:392-396
+    int rank = 0, world = 1;
+#ifndef DLB_CUDA_EMU
+    NcclApi::comm_t comm = nullptr;
+#endif
+    virtual ~dlb_net() {}
+    virtual void set_params(const void* h) = 0;
+    virtual void get_params(void* h) = 0;
+    virtual void* device_params() = 0;
+    virtual void* device_grads() = 0;
+    virtual void set_dataset(const void* x, const void* y, int64_t n, bool on_device) = 0;
+    virtual void learn(int64_t batch, int64_t epochs, double lr, int cost, double lambda, dlb_epoch_callback cb, void* user) = 0;
+    virtual int64_t train_steps(int64_t batch, int64_t n_steps, double lr, int cost, double lambda) = 0;
+    virtual void step_indices(const int64_t* idx, int64_t n, double lr, int cost, double reg_factor) = 0;
+    virtual void step_host(const void* x, const void* y, int64_t n, double lr, int cost, double reg_factor, double* cost_out) = 0;
+    virtual void forward_backward_host(const void* x, const void* y, int64_t n, int cost, double scale) = 0;
+    virtual void read(int what, int layer, void* dst, int64_t bytes) = 0;
+    virtual void write_gradient(const void* src) = 0;
+    virtual void eval_host(const void* x, int64_t n, int32_t* classes, void* outputs) = 0;
+};
+
+namespace {
+
+template <class R>
+struct NetT final : dlb_net {
+    R* params = nullptr;
+    R* grads = nullptr;
+    int cap = 0;                    // batch capacity of the workspace below (grow-only, like the reference's buffers)
+    std::vector<R*> out, deriv, in_grad;   // per layer [cap][out_n] / [cap][out_n] / [cap][in_n]; in_grad[L] = cost gradient
+    std::vector<int*> imap;
+    R* g = nullptr;                 // [cap][max out_n] activation-gradient scratch
+    R* stage_x = nullptr;           // [cap][in_n(0)]   staged host batch
+    R* stage_y = nullptr;           // [cap][out_n(L-1)]
+    int* gather_dev = nullptr;      // [cap]
+    R* data_x = nullptr; R* data_y = nullptr; int64_t n_items = 0; bool own_data = false;
+    int* perm_dev = nullptr; int64_t perm_cap = 0;
+    double* cost_dev = nullptr;
+    int last_B = 0;
+    UpdateSegments segs{};
+
+    int L() const { return (int)layers.size(); }
+    int64_t in0() const { return layers.front().in_n; }
+    int64_t outN() const { return layers.back().out_n; }
+
+    NetT(dlb_context* c, std::vector<LayerRt> ls, int64_t np) {
+        ctx = c; real_bytes = (int)sizeof(R); layers = std::move(ls); n_params = np;
+        use_device(ctx);
+        params = dev_alloc<R>((size_t)n_params);
+        grads = dev_alloc<R>((size_t)n_params);
+        DLB_CUDA(cudaMemsetAsync(params, 0, (size_t)n_params * sizeof(R), ctx->stream));
+        DLB_CUDA(cudaMemsetAsync(grads, 0, (size_t)n_params * sizeof(R), ctx->stream));
+        cost_dev = dev_alloc<double>(1);
+        out.assign((size_t)L(), nullptr); deriv.assign((size_t)L(), nullptr); imap.assign((size_t)L(), nullptr);
+        in_grad.assign((size_t)L() + 1, nullptr);
+        segs.count = 0;
+        for (const auto& Y : layers) {
+            if (Y.bias_n + Y.weight_n == 0) continue;
+            DLB_REQUIRE(segs.count + 2 <= kMaxSegments, "Too many parameter containers");
+            segs.end[segs.count] = Y.param_off + Y.bias_n; segs.regularised[segs.count++] = 0;           // biases
+            segs.end[segs.count] = Y.param_off + Y.bias_n + Y.weight_n; segs.regularised[segs.count++] = 1;  // weights / filters
+        }
+        if (segs.count == 0) { segs.count = 1; segs.end[0] = 0; segs.regularised[0] = 0; }
+    }
+
+    ~NetT() override {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        free_workspace();
+        dev_free(params); dev_free(grads); dev_free(cost_dev); dev_free(perm_dev);
+        if (own_data) { dev_free(data_x); dev_free(data_y); }
+#ifndef DLB_CUDA_EMU
+        if (comm) NcclApi::get().CommDestroy(comm);
+#endif
+    }
+
+    void free_workspace() {
+        for (auto& p : out) dev_free(p);
+        for (auto& p : deriv) dev_free(p);
+        for (auto& p : in_grad) dev_free(p);
+        for (auto& p : imap) dev_free(p);
+        dev_free(g); dev_free(stage_x); dev_free(stage_y); dev_free(gather_dev);
+        cap = 0;
+    }
+
+    void ensure_capacity(int64_t B) {
+        DLB_REQUIRE(B > 0 && B < (1LL << 24), "Invalid batch size");
+        for (const auto& Y : layers)
+            DLB_REQUIRE(B * std::max(Y.in_n, Y.out_n) < (1LL << 31), "batch * layer size exceeds the 32-bit index range");
+        if (B <= cap) return;
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        free_workspace();
+        const size_t b = (size_t)B;
+        int64_t max_out = 1;
+        for (int l = 0; l < L(); ++l) {
+            const auto& Y = layers[(size_t)l];
+            out[(size_t)l] = dev_alloc<R>(b * (size_t)Y.out_n);
+            deriv[(size_t)l] = dev_alloc<R>(b * (size_t)Y.out_n);
+            imap[(size_t)l] = dev_alloc<int>(b * (size_t)Y.out_n);
+            if (l > 0) in_grad[(size_t)l] = dev_alloc<R>(b * (size_t)Y.in_n);
+            max_out = std::max(max_out, Y.out_n);
+        }
+        in_grad[(size_t)L()] = dev_alloc<R>(b * (size_t)outN());
+        g = dev_alloc<R>(b * (size_t)max_out);
+        stage_x = dev_alloc<R>(b * (size_t)in0());
+        stage_y = dev_alloc<R>(b * (size_t)outN());
+        gather_dev = dev_alloc<int>(b);
+        cap = (int)B;
+        // Split-partial scratch: enough for ~2 waves of partial tiles of the largest gradient, at least 64 MiB.
+        size_t need = 64u << 20;
+        for (const auto& Y : layers) need = std::max(need, (size_t)(Y.weight_n + Y.bias_n) * sizeof(R) * 8);
+        ctx->ensure_ws(need);
+    }
+
+    // ---- parameter / data movement ---------------------------------------------------------------------------
+    void set_params(const void* h) override {
+        use_device(ctx);
+        DLB_CUDA(cudaMemcpyAsync(params, h, (size_t)n_params * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    void get_params(void* h) override {
+        use_device(ctx);
+        DLB_CUDA(cudaMemcpyAsync(h, params, (size_t)n_params * sizeof(R), cudaMemcpyDeviceToHost, ctx->stream));
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    void* device_params() override { return params; }
+    void* device_grads() override { return grads; }
+
+    void set_dataset(const void* x, const void* y, int64_t n, bool on_device) override {
+        DLB_REQUIRE(x && y && n > 0 && n < (1LL << 31), "Incompatible collection of training and reference items.");
+        use_device(ctx);
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (own_data) { dev_free(data_x); dev_free(data_y); }
+        if (on_device) {
+            data_x = (R*)x; data_y = (R*)y; own_data = false;
+        } else {
+            data_x = dev_alloc<R>((size_t)n * (size_t)in0());
+            data_y = dev_alloc<R>((size_t)n * (size_t)outN());
+            own_data = true;
+            DLB_CUDA(cudaMemcpyAsync(data_x, x, (size_t)n * (size_t)in0() * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+            DLB_CUDA(cudaMemcpyAsync(data_y, y, (size_t)n * (size_t)outN() * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+            DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        n_items = n;
+    }
+
+    // ---- forward / backward over one batch --------------------------------------------------------------------
+    // x: [rows][in0] device; gather (nullable): batch slot -> row of x.
+    void forward(int B, const R* x, const int* gather, bool traces) {
+        const LaunchCtx lc = ctx->lc();
+        const R* in = x;
+        const int* ga = gather;
+        for (int l = 0; l < L(); ++l) {
+            const auto& Y = layers[(size_t)l];
+            g_tag_layer = l;
+            R* y = out[(size_t)l];
+            R* d = traces ? deriv[(size_t)l] : nullptr;
+            const R* bias = params + Y.param_off;
+            const R* w = bias + Y.bias_n;
+            switch (Y.s.type) {
+            case DLB_LAYER_CONVOLUTION: conv_forward<R>(lc, B, Y.cg, Y.s.activation, in, ga, bias, w, y, d); break;
+            case DLB_LAYER_FULL: full_forward<R>(lc, B, (int)Y.in_n, (int)Y.out_n, Y.s.activation, in, ga, bias, w, y, d); break;
+            default:
+                DLB_REQUIRE(ga == nullptr, "A pooling first layer cannot read a gathered data set");
+                pool_forward<R>(lc, B, Y.s, in, y, traces ? imap[(size_t)l] : nullptr);
+            }
+            in = y; ga = nullptr;
+        }
+    }
+
+    // Deltas enter in in_grad[L] (cost derivative).  scale: gradient_scale_factor on the previous gradient content.
+    void backward(int B, const R* x, const int* gather, R scale) {
+        const LaunchCtx lc = ctx->lc();
+        const R* delta = in_grad[(size_t)L()];
+        for (int l = L() - 1; l >= 0; --l) {
+            const auto& Y = layers[(size_t)l];
+            g_tag_layer = l;
+            const R* in = l == 0 ? x : out[(size_t)l - 1];
+            const int* ga = l == 0 ? gather : nullptr;
+            R* dx = l == 0 ? nullptr : in_grad[(size_t)l];   // evaluate_input_gradient = layer_id != 0 (Net.inl:272)
+            R* db = grads + Y.param_off;
+            R* dw = db + Y.bias_n;
+            const R* w = params + Y.param_off + Y.bias_n;
+            switch (Y.s.type) {
+            case DLB_LAYER_CONVOLUTION:
+                conv_backward<R>(lc, B, Y.cg, Y.s.activation, in, ga, delta, deriv[(size_t)l], w, g, db, dw, dx, scale); break;
+            case DLB_LAYER_FULL:
+                full_backward<R>(lc, B, (int)Y.in_n, (int)Y.out_n, Y.s.activation, in, ga, delta, deriv[(size_t)l], w, g, db, dw, dx, scale); break;
+            default:
+                if (dx) pool_backward<R>(lc, B, Y.s, delta, imap[(size_t)l], dx);
+            }
+            delta = dx;
+        }
+    }
+
+    void forward_backward(int B, const R* x, const R* refs, const int* gather, int cost, R scale) {
+        forward(B, x, gather, true);
+        g_tag_layer = L();
+        cost_gradient<R>(ctx->lc(), B, (int)outN(), cost, out[(size_t)L() - 1], refs, gather, in_grad[(size_t)L()]);
+        backward(B, x, gather, scale);
+        last_B = B;
+    }
+
+    void allreduce_gradient() {
+#ifndef DLB_CUDA_EMU
+        if (world <= 1) return;
+        auto& api = NcclApi::get();
+        api.check(api.AllReduce(grads, grads, (size_t)n_params, sizeof(R) == 4 ? kNcclFloat : kNcclDouble, kNcclSum, comm, ctx->stream),
+                  "ncclAllReduce");
+#endif
+    }
+
+    // ALayer<D>::update for every layer (Net.inl:309-316): l_rate = -lr, grad_scale_factor = 1 / B_actual.
+    void update(double lr, double reg_factor, int64_t batch_items) {
+        const R l_rate = -static_cast<R>(lr);
+        const R reg = static_cast<R>(reg_factor);
+        const R grad_norm = static_cast<R>(1) / static_cast<R>(batch_items);
+        const R param_scale = static_cast<R>(1) + reg * l_rate;
+        const R grad_total_scale = l_rate * grad_norm;
+        g_tag_layer = -1;
+        sgd_update<R>(ctx->lc(), params, grads, (size_t)n_params, segs, param_scale, grad_total_scale, reg > static_cast<R>(0));
+    }
+
+    // One step on this rank's share [first, first + mine) of a global batch of `global` items.
+    void step_device(const R* x, const R* refs, const int* gather, int64_t mine, int64_t global, double lr, int cost, double reg_factor) {
+        if (mine > 0) {
+            ensure_capacity(mine);
+            forward_backward((int)mine, x, refs, gather, cost, R(0));
+        } else {
+            DLB_CUDA(cudaMemsetAsync(grads, 0, (size_t)n_params * sizeof(R), ctx->stream));
+        }
+        allreduce_gradient();
+        update(lr, reg_factor, global);
+    }
+
+    void rank_slice(int64_t count, int64_t& first, int64_t& mine) const {
+        const int64_t per = (count + world - 1) / world;
+        first = std::min<int64_t>(count, (int64_t)rank * per);
+        mine = std::min<int64_t>(count, first + per) - first;
+    }
+
+    void learn(int64_t batch, int64_t epochs, double lr, int cost, double lambda, dlb_epoch_callback cb, void* user) override {
+        DLB_REQUIRE(data_x && data_y, "Incompatible collection of training and reference items.");
+        if (n_items == 0 || batch == 0) return;   // Net.inl:200-201
+        DLB_REQUIRE(batch > 0 && epochs >= 0, "Invalid batch size / epoch count");
+        use_device(ctx);
+        const R reg_factor = static_cast<R>(lambda) / static_cast<R>(n_items);   // Net.inl:203
+        std::vector<std::size_t> index_map((size_t)n_items);
+        std::iota(index_map.begin(), index_map.end(), 0);                         // Net.inl:164-171
+        std::vector<int> perm32((size_t)n_items);
+        if (perm_cap < n_items) { dev_free(perm_dev); perm_dev = dev_alloc<int>((size_t)n_items); perm_cap = n_items; }
+        for (int64_t e = 0; e < epochs; ++e) {
+            std::ranges::shuffle(index_map, rng);                                 // Net.inl:158-161, 223
+            for (int64_t i = 0; i < n_items; ++i) perm32[(size_t)i] = (int)index_map[(size_t)i];
+            DLB_CUDA(cudaStreamSynchronize(ctx->stream));   // previous epoch's kernels may still read perm_dev
+            DLB_CUDA(cudaMemcpyAsync(perm_dev, perm32.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            int64_t start = 0;
+            while (start < n_items) {
+                // Net.inl:235-236: fewer than 1.5 * batch_size remaining items are taken as one batch
+                const int64_t end = (double)(n_items - start) < 1.5 * (double)batch ? n_items : start + batch;
+                int64_t first, mine;
+                rank_slice(end - start, first, mine);
+                step_device(data_x, data_y, perm_dev + start + first, mine, end - start, lr, cost, (double)reg_factor);
+                start = end;
+            }
+            if (cb) { DLB_CUDA(cudaStreamSynchronize(ctx->stream)); cb(e, 0.5 * (double)reg_factor, user); }   // Net.inl:319
+        }
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+
+    // Net::learn's loop made resumable: runs the next `n_steps` mini-batches of the reference's epoch sequence
+    // (reshuffling when an epoch is exhausted) and returns the number of items consumed by all ranks.
+    std::vector<std::size_t> ts_index_map;
+    int64_t ts_cursor = -1;
+    int64_t train_steps(int64_t batch, int64_t n_steps, double lr, int cost, double lambda) override {
+        DLB_REQUIRE(data_x && data_y, "Incompatible collection of training and reference items.");
+        DLB_REQUIRE(batch > 0 && n_steps >= 0, "Invalid batch size / step count");
+        use_device(ctx);
+        const R reg_factor = static_cast<R>(lambda) / static_cast<R>(n_items);
+        if (perm_cap < n_items) { dev_free(perm_dev); perm_dev = dev_alloc<int>((size_t)n_items); perm_cap = n_items; ts_cursor = -1; }
+        if ((int64_t)ts_index_map.size() != n_items) { ts_index_map.resize((size_t)n_items); std::iota(ts_index_map.begin(), ts_index_map.end(), 0); ts_cursor = -1; }
+        int64_t consumed = 0;
+        for (int64_t s = 0; s < n_steps; ++s) {
+            if (ts_cursor < 0 || ts_cursor >= n_items) {
+                std::ranges::shuffle(ts_index_map, rng);
+                std::vector<int> perm32((size_t)n_items);
+                for (int64_t i = 0; i < n_items; ++i) perm32[(size_t)i] = (int)ts_index_map[(size_t)i];
+                DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+                DLB_CUDA(cudaMemcpyAsync(perm_dev, perm32.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+                ts_cursor = 0;
+            }
+            const int64_t start = ts_cursor;
+            const int64_t end = (double)(n_items - start) < 1.5 * (double)batch ? n_items : start + batch;
+            int64_t first, mine;
+            rank_slice(end - start, first, mine);
+            step_device(data_x, data_y, perm_dev + start + first, mine, end - start, lr, cost, (double)reg_factor);
+            consumed += end - start;
+            ts_cursor = end;
+        }
+        return consumed;
+    }
+
+    void step_indices(const int64_t* idx, int64_t n, double lr, int cost, double reg_factor) override {
+        DLB_REQUIRE(data_x && data_y && idx && n > 0, "Invalid input.");
+        use_device(ctx);
+        int64_t first, mine;
+        rank_slice(n, first, mine);
+        ensure_capacity(std::max<int64_t>(mine, 1));
+        std::vector<int> tmp((size_t)std::max<int64_t>(mine, 1));
+        for (int64_t i = 0; i < mine; ++i) {
+            DLB_REQUIRE(idx[first + i] >= 0 && idx[first + i] < n_items, "Item index out of range");
+            tmp[(size_t)i] = (int)idx[first + i];
+        }
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        DLB_CUDA(cudaMemcpyAsync(gather_dev, tmp.data(), (size_t)mine * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));   // tmp is pageable and goes out of scope
+        step_device(data_x, data_y, gather_dev, mine, n, lr, cost, reg_factor);
+    }
+
+    void stage_host_batch(const void* x, const void* y, int64_t n) {
+        ensure_capacity(n);
+        DLB_CUDA(cudaMemcpyAsync(stage_x, x, (size_t)n * (size_t)in0() * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+        if (y) DLB_CUDA(cudaMemcpyAsync(stage_y, y, (size_t)n * (size_t)outN() * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+    }
+
+    void step_host(const void* x, const void* y, int64_t n, double lr, int cost, double reg_factor, double* cost_out) override {
+        DLB_REQUIRE(x && y && n > 0, "Invalid input.");
+        use_device(ctx);
+        stage_host_batch(x, y, n);
+        forward_backward((int)n, stage_x, stage_y, nullptr, cost, R(0));
+        if (cost_out)
+            DLB_LAUNCH((cost_sum_kernel<R>), dim3(1), dim3(256), ctx->stream, (const R*)out[(size_t)L() - 1], (const R*)stage_y,
+                       (const int*)nullptr, (int)n, (int)outN(), cost, cost_dev);
+        allreduce_gradient();
+        update(lr, reg_factor, n * world);
+        if (cost_out) {
+            DLB_CUDA(cudaMemcpyAsync(cost_out, cost_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+
+    void forward_backward_host(const void* x, const void* y, int64_t n, int cost, double scale) override {
+        DLB_REQUIRE(x && y && n > 0, "Invalid input.");
+        use_device(ctx);
+        stage_host_batch(x, y, n);
+        forward_backward((int)n, stage_x, stage_y, nullptr, cost, static_cast<R>(scale));
+    }
+
+    void read(int what, int layer, void* dst, int64_t bytes) override {
+        use_device(ctx);
+        const void* src = nullptr;
+        size_t need = 0;
+        const size_t b = (size_t)last_B;
+        auto check_layer = [&](int lo) { DLB_REQUIRE(layer >= lo && layer < L(), "Invalid layer index"); };
+        switch (what) {
+        case DLB_BUF_OUTPUT: check_layer(0); src = out[(size_t)layer]; need = b * (size_t)layers[(size_t)layer].out_n * sizeof(R); break;
+        case DLB_BUF_DERIVATIVES: check_layer(0); src = deriv[(size_t)layer]; need = b * (size_t)layers[(size_t)layer].out_n * sizeof(R); break;
+        case DLB_BUF_INDEX_MAP: check_layer(0); src = imap[(size_t)layer]; need = b * (size_t)layers[(size_t)layer].out_n * sizeof(int); break;
+        case DLB_BUF_INPUT_GRAD: check_layer(1); src = in_grad[(size_t)layer]; need = b * (size_t)layers[(size_t)layer].in_n * sizeof(R); break;
+        case DLB_BUF_COST_GRAD: src = in_grad[(size_t)L()]; need = b * (size_t)outN() * sizeof(R); break;
+        case DLB_BUF_GRADIENT: src = grads; need = (size_t)n_params * sizeof(R); break;
+        default: throw arg_error("Unknown buffer id");
+        }
+        DLB_REQUIRE(what == DLB_BUF_GRADIENT || last_B > 0, "No forward/backward pass has run yet");
+        DLB_REQUIRE((size_t)bytes >= need, "Destination buffer too small");
+        DLB_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+
+    void write_gradient(const void* src) override {
+        use_device(ctx);
+        DLB_CUDA(cudaMemcpyAsync(grads, src, (size_t)n_params * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+
+    void eval_host(const void* x, int64_t n, int32_t* classes, void* outputs) override {
+        DLB_REQUIRE(x && n >= 0, "Invalid input.");
+        use_device(ctx);
+        const int64_t chunk = std::min<int64_t>(std::max<int64_t>(n, 1), 4096);
+        ensure_capacity(chunk);
+        const R* hx = static_cast<const R*>(x);
+        for (int64_t s = 0; s < n; s += chunk) {
+            const int64_t m = std::min(chunk, n - s);
+            DLB_CUDA(cudaMemcpyAsync(stage_x, hx + s * in0(), (size_t)m * (size_t)in0() * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+            forward((int)m, stage_x, nullptr, false);
+            const R* y = out[(size_t)L() - 1];
+            if (classes) {
+                DLB_LAUNCH((argmax_rows_kernel<R>), dim3((unsigned)ceil_div<int64_t>(m, 128)), dim3(128), ctx->stream, y, gather_dev, (int)m, (int)outN());
+                DLB_CUDA(cudaMemcpyAsync(classes + s, gather_dev, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            if (outputs)
+                DLB_CUDA(cudaMemcpyAsync(static_cast<R*>(outputs) + s * outN(), y, (size_t)m * (size_t)outN() * sizeof(R), cudaMemcpyDeviceToHost, ctx->stream));
+            DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+};
+
+// Scratch big enough for the op-level entry points.
+void ensure_op_ws(dlb_context* ctx) { ctx->ensure_ws(64u << 20); }
+
+template <class R>
+void op_sgd_update(dlb_context* ctx, R* p, const R* gr, int64_t n, int regularised, double lr, double reg_factor, double gsf) {
+    DLB_REQUIRE(p && gr && n >= 0, "Collections must be of the same size");
+    use_device(ctx);
+    UpdateSegments segs{}; segs.count = 1; segs.end[0] = n; segs.regularised[0] = regularised ? 1 : 0;
+    const R l_rate = static_cast<R>(lr);   // ALayer::update receives -learning_rate from Net (Net.inl:315); callers pass l_rate as is
+    const R reg = static_cast<R>(reg_factor);
+    sgd_update<R>(ctx->lc(), p, gr, (size_t)n, segs, static_cast<R>(1) + reg * l_rate, l_rate * static_cast<R>(gsf), reg > static_cast<R>(0));
+}
+
+void check_spec(const dlb_layer_spec* s, int type) {
+    DLB_REQUIRE(s && s->type == type, "Layer spec of the wrong type");
+    int64_t np = 0;
+    (void)build_layers(s, 1, np);
+}
+
+}  // namespace
+
+// =================================================================================================================
+// extern "C"
+// =================================================================================================================
+extern "C" {
+
+int dlb_version(void) { return 100; }
+const char* dlb_last_error(void) { return g_last_error.c_str(); }
+
+int dlb_context_create(int device, void* external_stream, dlb_context** out) {
+    return guarded([&] {
+        DLB_REQUIRE(out, "null output pointer");
+        int count = 0;
+        DLB_CUDA(cudaGetDeviceCount(&count));
+        DLB_REQUIRE(device >= 0 && device < count, "No such CUDA device (libdlb200 has no CPU fallback)");
+        DLB_CUDA(cudaSetDevice(device));
+        auto ctx = std::make_unique<dlb_context>();
+        ctx->device = device;
+        if (external_stream) { ctx->stream = (cudaStream_t)external_stream; ctx->own_stream = false; }
+        else { DLB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+        *out = ctx.release();
+    });
+}
+
+int dlb_context_destroy(dlb_context* ctx) {
+    return guarded([&] {
+        if (!ctx) return;
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->ws.ptr) cudaFree(ctx->ws.ptr);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+    });
+}
+
+int dlb_context_synchronize(dlb_context* ctx) { return guarded([&] { DLB_REQUIRE(ctx, "null context"); DLB_CUDA(cudaStreamSynchronize(ctx->stream)); }); }
+void* dlb_context_stream(dlb_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int64_t dlb_context_launch_count(dlb_context*) { return (int64_t)g_launch_count.load(); }
+
+int dlb_malloc(dlb_context* ctx, size_t bytes, void** out) {
+    return guarded([&] { DLB_REQUIRE(ctx && out, "null argument"); use_device(ctx); DLB_CUDA(cudaMalloc(out, bytes ? bytes : 1)); });
+}
+int dlb_free(dlb_context* ctx, void* ptr) {
+    return guarded([&] { DLB_REQUIRE(ctx, "null context"); use_device(ctx); if (ptr) { DLB_CUDA(cudaStreamSynchronize(ctx->stream)); DLB_CUDA(cudaFree(ptr)); } });
+}
+int dlb_memcpy_h2d(dlb_context* ctx, void* dst, const void* src, size_t bytes) {
+    return guarded([&] { DLB_REQUIRE(ctx, "null context"); use_device(ctx); DLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); });
+}
+int dlb_memcpy_d2h(dlb_context* ctx, void* dst, const void* src, size_t bytes) {
+    return guarded([&] {
+        DLB_REQUIRE(ctx, "null context"); use_device(ctx);
+        DLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int dlb_memcpy_d2d(dlb_context* ctx, void* dst, const void* src, size_t bytes) {
+    return guarded([&] { DLB_REQUIRE(ctx, "null context"); use_device(ctx); DLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream)); });
+}
+int dlb_memset(dlb_context* ctx, void* dst, int value, size_t bytes) {
+    return guarded([&] { DLB_REQUIRE(ctx, "null context"); use_device(ctx); DLB_CUDA(cudaMemsetAsync(dst, value, bytes, ctx->stream)); });
+}
+int dlb_host_alloc_pinned(size_t bytes, void** out) { return guarded([&] { DLB_REQUIRE(out, "null argument"); DLB_CUDA(cudaMallocHost(out, bytes ? bytes : 1)); }); }
+int dlb_host_free_pinned(void* ptr) { return guarded([&] { if (ptr) DLB_CUDA(cudaFreeHost(ptr)); }); }
+
+#define DLB_DEFINE_OPS(SFX, REAL)                                                                                                  \
+    int dlb_conv_forward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* x, const int32_t* gather,      \
+                               const REAL* bias, const REAL* filters, REAL* y, REAL* deriv) {                                     \
+        return guarded([&] {                                                                                                       \
+            DLB_REQUIRE(ctx && x && bias && filters && y && batch > 0, "Unexpected size of the input tensor");                     \
+            check_spec(spec, DLB_LAYER_CONVOLUTION); use_device(ctx); ensure_op_ws(ctx);                                           \
+            conv_forward<REAL>(ctx->lc(), batch, make_conv_geom(*spec), spec->activation, x, gather, bias, filters, y, deriv);     \
+        });                                                                                                                        \
+    }                                                                                                                              \
+    int dlb_conv_backward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* x, const int32_t* gather,     \
+                                const REAL* delta, const REAL* deriv, const REAL* filters, REAL* g, REAL* dbias, REAL* dfilters,   \
+                                REAL* dx, double scale) {                                                                          \
+        return guarded([&] {                                                                                                       \
+            DLB_REQUIRE(ctx && x && delta && deriv && filters && g && dbias && dfilters && batch > 0,                              \
+                        "Unexpected size of the input tensor of derivatives");                                                     \
+            check_spec(spec, DLB_LAYER_CONVOLUTION); use_device(ctx); ensure_op_ws(ctx);                                           \
+            conv_backward<REAL>(ctx->lc(), batch, make_conv_geom(*spec), spec->activation, x, gather, delta, deriv, filters, g,    \
+                                dbias, dfilters, dx, static_cast<REAL>(scale));                                                    \
+        });                                                                                                                        \
+    }                                                                                                                              \
+    int dlb_pool_forward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* x, REAL* y, int32_t* map) {    \
+        return guarded([&] {                                                                                                       \
+            DLB_REQUIRE(ctx && x && y && batch > 0, "Unexpected size of the input tensor");                                        \
+            check_spec(spec, DLB_LAYER_PULL); use_device(ctx);                                                                     \
+            pool_forward<REAL>(ctx->lc(), batch, *spec, x, y, map);                                                                \
+        });                                                                                                                        \
+    }                                                                                                                              \
+    int dlb_pool_backward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* delta, const int32_t* map,    \
+                                REAL* dx) {                                                                                        \
+        return guarded([&] {                                                                                                       \
+            DLB_REQUIRE(ctx && delta && dx && batch > 0, "Unexpected size of the input tensor of derivatives");                    \
+            check_spec(spec, DLB_LAYER_PULL);                                                                                      \
+            DLB_REQUIRE(map || spec->pool_type == DLB_POOL_AVERAGE, "Invalid index mapping");                                      \
+            use_device(ctx);                                                                                                       \
+            pool_backward<REAL>(ctx->lc(), batch, *spec, delta, map, dx);                                                          \
+        });                                                                                                                        \
+    }                                                                                                                              \
+    int dlb_full_forward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* x, const int32_t* gather,      \
+                               const REAL* bias, const REAL* weights, REAL* y, REAL* deriv) {                                     \
+        return guarded([&] {                                                                                                       \
+            DLB_REQUIRE(ctx && x && bias && weights && y && batch > 0, "Incompatible matrix-vector dimensionality");               \
+            check_spec(spec, DLB_LAYER_FULL); use_device(ctx); ensure_op_ws(ctx);                                                  \
+            full_forward<REAL>(ctx->lc(), batch, spec->in_c * spec->in_h * spec->in_w, spec->out_c, spec->activation, x, gather,   \
+                               bias, weights, y, deriv);                                                                           \
+        });                                                                                                                        \
+    }                                                                                                                              \
+    int dlb_full_backward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* x, const int32_t* gather,     \
+                                const REAL* delta, const REAL* deriv, const REAL* weights, REAL* g, REAL* dbias, REAL* dweights,   \
+                                REAL* dx, double scale) {                                                                          \
+        return guarded([&] {                                                                                                       \
+            DLB_REQUIRE(ctx && x && delta && deriv && weights && g && dbias && dweights && batch > 0, "Invalid input");            \
+            check_spec(spec, DLB_LAYER_FULL); use_device(ctx); ensure_op_ws(ctx);                                                  \
+            full_backward<REAL>(ctx->lc(), batch, spec->in_c * spec->in_h * spec->in_w, spec->out_c, spec->activation, x, gather,  \
+                                delta, deriv, weights, g, dbias, dweights, dx, static_cast<REAL>(scale));                          \
+        });                                                                                                                        \
+    }                                                                                                                              \
+    int dlb_cost_gradient_##SFX(dlb_context* ctx, int cost_id, int batch, int n, const REAL* out, const REAL* ref,                 \
+                                const int32_t* gather, REAL* grad) {                                                               \
+        return guarded([&] {                                                                                                       \
+            DLB_REQUIRE(ctx && out && ref && grad && batch > 0 && n > 0, "Inconsistent input.");                                   \
+            DLB_REQUIRE(cost_id >= DLB_COST_SQUARED_ERROR && cost_id <= DLB_COST_LINEAR, "Unknown cost function");                 \
+            use_device(ctx);                                                                                                       \
+            cost_gradient<REAL>(ctx->lc(), batch, n, cost_id, out, ref, gather, grad);                                             \
+        });                                                                                                                        \
+    }                                                                                                                              \
+    int dlb_sgd_update_##SFX(dlb_context* ctx, REAL* params, const REAL* grads, int64_t n, int regularised, double l_rate,         \
+                             double reg_factor, double grad_scale_factor) {                                                        \
+        return guarded([&] { DLB_REQUIRE(ctx, "null context"); op_sgd_update<REAL>(ctx, params, grads, n, regularised,             \
+                                                                                 l_rate, reg_factor, grad_scale_factor); });       \
+    }
+
+DLB_DEFINE_OPS(f32, float)
+DLB_DEFINE_OPS(f64, double)
+
+int dlb_net_create(dlb_context* ctx, const dlb_layer_spec* specs, int n_layers, int real_bytes, dlb_net** out) {
+    return guarded([&] {
+        DLB_REQUIRE(ctx && out, "null argument");
+        DLB_REQUIRE(real_bytes == 4 || real_bytes == 8, "real_bytes must be 4 (float) or 8 (double)");
+        int64_t np = 0;
+        auto layers = build_layers(specs, n_layers, np);
+        if (real_bytes == 4) *out = new NetT<float>(ctx, std::move(layers), np);
+        else *out = new NetT<double>(ctx, std::move(layers), np);
+    });
+}
+int dlb_net_destroy(dlb_net* net) { return guarded([&] { delete net; }); }
+int64_t dlb_net_param_count(const dlb_net* net) { return net ? net->n_params : -1; }
+int dlb_net_layer_count(const dlb_net* net) { return net ? (int)net->layers.size() : -1; }
+int64_t dlb_net_layer_in_size(const dlb_net* net, int l) { return (net && l >= 0 && l < (int)net->layers.size()) ? net->layers[(size_t)l].in_n : -1; }
+int64_t dlb_net_layer_out_size(const dlb_net* net, int l) { return (net && l >= 0 && l < (int)net->layers.size()) ? net->layers[(size_t)l].out_n : -1; }
+int64_t dlb_net_layer_param_offset(const dlb_net* net, int l) { return (net && l >= 0 && l < (int)net->layers.size()) ? net->layers[(size_t)l].param_off : -1; }
+int dlb_net_set_params(dlb_net* net, const void* h) { return guarded([&] { DLB_REQUIRE(net && h, "null argument"); net->set_params(h); }); }
+int dlb_net_get_params(dlb_net* net, void* h) { return guarded([&] { DLB_REQUIRE(net && h, "null argument"); net->get_params(h); }); }
+void* dlb_net_device_params(dlb_net* net) { return net ? net->device_params() : nullptr; }
+void* dlb_net_device_grads(dlb_net* net) { return net ? net->device_grads() : nullptr; }
+int dlb_net_set_dataset(dlb_net* net, const void* x, const void* y, int64_t n, int on_device) {
+    return guarded([&] { DLB_REQUIRE(net, "null net"); net->set_dataset(x, y, n, on_device != 0); });
+}
+int dlb_net_reset_random_generator(dlb_net* net, unsigned seed) { return guarded([&] { DLB_REQUIRE(net, "null net"); net->rng.seed(seed); }); }
+int dlb_net_learn(dlb_net* net, int64_t batch, int64_t epochs, double lr, int cost, double lambda, dlb_epoch_callback cb, void* user) {
+    return guarded([&] {
+        DLB_REQUIRE(net, "null net");
+        DLB_REQUIRE(cost >= DLB_COST_SQUARED_ERROR && cost <= DLB_COST_LINEAR, "Unknown cost function");
+        net->learn(batch, epochs, lr, cost, lambda, cb, user);
+    });
+}
+int dlb_net_step_indices(dlb_net* net, const int64_t* idx, int64_t n, double lr, int cost, double reg_factor) {
+    return guarded([&] { DLB_REQUIRE(net, "null net"); net->step_indices(idx, n, lr, cost, reg_factor); });
+}
+int dlb_net_step_host(dlb_net* net, const void* x, const void* y, int64_t n, double lr, int cost, double reg_factor, double* cost_out) {
+    return guarded([&] { DLB_REQUIRE(net, "null net"); net->step_host(x, y, n, lr, cost, reg_factor, cost_out); });
+}
+int dlb_net_forward_backward_host(dlb_net* net, const void* x, const void* y, int64_t n, int cost, double scale) {
+    return guarded([&] { DLB_REQUIRE(net, "null net"); net->forward_backward_host(x, y, n, cost, scale); });
+}
+int dlb_net_read(dlb_net* net, int what, int layer, void* dst, int64_t bytes) {
+    return guarded([&] { DLB_REQUIRE(net && dst, "null argument"); net->read(what, layer, dst, bytes); });
+}
+int dlb_net_write_gradient(dlb_net* net, const void* src) { return guarded([&] { DLB_REQUIRE(net && src, "null argument"); net->write_gradient(src); }); }
+int dlb_net_eval_host(dlb_net* net, const void* x, int64_t n, int32_t* classes, void* outputs) {
+    return guarded([&] { DLB_REQUIRE(net, "null net"); net->eval_host(x, n, classes, outputs); });
+}
+
+int dlb_net_train_steps(dlb_net* net, int64_t batch, int64_t n_steps, double lr, int cost, double lambda, int64_t* items_out) {
+    return guarded([&] {
+        DLB_REQUIRE(net, "null net");
+        DLB_REQUIRE(cost >= DLB_COST_SQUARED_ERROR && cost <= DLB_COST_LINEAR, "Unknown cost function");
+        const int64_t items = net->train_steps(batch, n_steps, lr, cost, lambda);
+        if (items_out) *items_out = items;
+    });
+}
+
+int dlb_rank_slice(int64_t count, int rank, int world, int64_t* first, int64_t* mine) {
+    return guarded([&] {
+        DLB_REQUIRE(first && mine && count >= 0 && world >= 1 && rank >= 0 && rank < world, "Invalid rank / world size");
+        const int64_t per = (count + world - 1) / world;
+        *first = std::min<int64_t>(count, (int64_t)rank * per);
+        *mine = std::min<int64_t>(count, *first + per) - *first;
+    });
+}
+
+#ifndef DLB_CUDA_EMU
+int dlb_event_create(void** out) { return guarded([&] { DLB_REQUIRE(out, "null argument"); cudaEvent_t e; DLB_CUDA(cudaEventCreate(&e)); *out = e; }); }
+int dlb_event_destroy(void* ev) { return guarded([&] { if (ev) DLB_CUDA(cudaEventDestroy((cudaEvent_t)ev)); }); }
+int dlb_event_record(dlb_context* ctx, void* ev) { return guarded([&] { DLB_REQUIRE(ctx && ev, "null argument"); DLB_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->stream)); }); }
+int dlb_event_elapsed_ms(void* start, void* stop, double* ms) {
+    return guarded([&] {
+        DLB_REQUIRE(start && stop && ms, "null argument");
+        DLB_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+        float f = 0; DLB_CUDA(cudaEventElapsedTime(&f, (cudaEvent_t)start, (cudaEvent_t)stop)); *ms = f;
+    });
+}
+int dlb_timing_enable(int on) { return guarded([&] { g_timing_on = on != 0; }); }
+// Writes "key\tcount\ttotal_ms\n" lines (NUL-terminated, truncated to cap) and clears the records.
+int dlb_timing_report(char* buf, int64_t cap) {
+    return guarded([&] {
+        DLB_REQUIRE(buf && cap > 0, "null argument");
+        DLB_CUDA(cudaDeviceSynchronize());
+        std::vector<std::string> keys; std::vector<long long> counts; std::vector<double> totals;
+        for (auto& t : g_timed) {
+            float ms = 0; DLB_CUDA(cudaEventElapsedTime(&ms, t.e0, t.e1));
+            size_t i = 0; for (; i < keys.size(); ++i) if (keys[i] == t.key) break;
+            if (i == keys.size()) { keys.push_back(t.key); counts.push_back(0); totals.push_back(0.0); }
+            counts[i]++; totals[i] += ms;
+            g_event_pool.push_back(t.e0); g_event_pool.push_back(t.e1);
+        }
+        g_timed.clear();
+        std::string out;
+        for (size_t i = 0; i < keys.size(); ++i) out += keys[i] + "\t" + std::to_string(counts[i]) + "\t" + std::to_string(totals[i]) + "\n";
+        std::snprintf(buf, (size_t)cap, "%s", out.c_str());
+    });
+}
+#else
+int dlb_event_create(void** out) { if (out) *out = (void*)0x1; return 0; }
+int dlb_event_destroy(void*) { return 0; }
+int dlb_event_record(dlb_context*, void*) { return 0; }
+int dlb_event_elapsed_ms(void*, void*, double* ms) { if (ms) *ms = 1.0; return 0; }
+int dlb_timing_enable(int) { return 0; }
+int dlb_timing_report(char* buf, int64_t cap) { if (buf && cap > 0) buf[0] = 0; return 0; }
+#endif
+
+int dlb_nccl_get_unique_id(void* id_out) {
+    return guarded([&] {
+#ifdef DLB_CUDA_EMU
+        (void)id_out; throw std::runtime_error("NCCL is not available");
+#else
+        DLB_REQUIRE(id_out, "null argument");
+        auto& api = NcclApi::get();
+        if (!api.ok) throw std::runtime_error(api.why);
+        NcclApi::unique_id id;
+        api.check(api.GetUniqueId(&id), "ncclGetUniqueId");
+        std::memcpy(id_out, &id, sizeof id);
+#endif
+    });
+}
+
+int dlb_net_set_distributed(dlb_net* net, int rank, int world, const void* unique_id) {
+    return guarded([&] {
+        DLB_REQUIRE(net && world >= 1 && rank >= 0 && rank < world, "Invalid rank / world size");
+#ifdef DLB_CUDA_EMU
+        (void)unique_id; DLB_REQUIRE(world == 1, "NCCL is not available");
+#else
+        if (world > 1) {
+            DLB_REQUIRE(unique_id, "null ncclUniqueId");
+            auto& api = NcclApi::get();
+            if (!api.ok) throw std::runtime_error(api.why);
+            use_device(net->ctx);
+            NcclApi::unique_id id;
+            std::memcpy(&id, unique_id, sizeof id);
+            if (net->comm) { api.CommDestroy(net->comm); net->comm = nullptr; }
+            api.check(api.CommInitRank(&net->comm, world, id, rank), "ncclCommInitRank");
+        }
+#endif
+        net->rank = rank; net->world = world;
+    });
+}
+
+int dlb_shuffle_sequence(unsigned seed, int64_t n, int64_t epochs, int64_t* out) {
+    return guarded([&] {
+        DLB_REQUIRE(out && n >= 0 && epochs >= 0, "Invalid input.");
+        std::mt19937 gen(seed);
+        std::vector<std::size_t> idx((size_t)n);
+        std::iota(idx.begin(), idx.end(), 0);
+        for (int64_t e = 0; e < epochs; ++e) {
+            std::ranges::shuffle(idx, gen);
+            for (int64_t i = 0; i < n; ++i) out[e * n + i] = (int64_t)idx[(size_t)i];
+        }
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,536 @@
+// layers.cuh — batched layer operators of the training path (forward / backward of CLayer, PLayer, NLayer, the
+// cost derivative and the SGD update) over a mini-batch packed as [B][C][H][W] (sample-major, each sample in the
+// reference's CHW order, Tensor.cpp:216-219).  The reference runs every one of these per sample
+// (Net.inl:257-277); here each runs once per step.
+#pragma once
+
+#include "gemm.cuh"
+
+namespace dlb {
+
+struct ConvGeom {
+    int C, H, W, KH, KW, F, OH, OW, ph, pw, sh, sw;
+    int KK, K, P, HW, in_n, out_n;
+};
+
+// ConvolutionUtils.cpp:29-44
+inline int conv_out_size(int in, int k, int pad, int stride) {
+    const long long t = (long long)in + 2LL * pad - k;
+    return t < 0 ? 0 : (int)(t / stride + 1);
+}
+
+inline ConvGeom make_conv_geom(const dlb_layer_spec& s) {
+    ConvGeom g{};
+    g.C = s.in_c; g.H = s.in_h; g.W = s.in_w; g.KH = s.win_h; g.KW = s.win_w; g.F = s.out_c;
+    g.ph = s.pad_h; g.pw = s.pad_w; g.sh = s.stride_h; g.sw = s.stride_w;
+    g.OH = conv_out_size(g.H, g.KH, g.ph, g.sh); g.OW = conv_out_size(g.W, g.KW, g.pw, g.sw);
+    g.KK = g.KH * g.KW; g.K = g.C * g.KK; g.P = g.OH * g.OW; g.HW = g.H * g.W;
+    g.in_n = g.C * g.HW; g.out_n = g.F * g.P;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Operand loaders (see gemm.cuh for the concept).  All are called as f(outer, red).
+// ---------------------------------------------------------------------------------------------------------------
+template <class R>
+struct DenseRowLoader {  // value = base[row(outer) * ld + red]; `gather` (optional) maps outer -> stored row
+    static constexpr bool kRedFast = true;
+    const R* base; size_t ld; const int* gather;
+    __device__ __forceinline__ R operator()(int o, int r) const {
+        const size_t row = gather ? (size_t)gather[o] : (size_t)o;
+        return base[row * ld + r];
+    }
+};
+
+template <class R>
+struct DenseColLoader {  // value = base[row(red) * ld + outer]; `gather` (optional) maps red -> stored row
+    static constexpr bool kRedFast = false;
+    const R* base; size_t ld; const int* gather;
+    __device__ __forceinline__ R operator()(int o, int r) const {
+        const size_t row = gather ? (size_t)gather[r] : (size_t)r;
+        return base[row * ld + o];
+    }
+};
+
+// Element (pixel = (b, oy, ox), k = (c, ky, kx)) of the receptive-field matrix of a mini-batch, with zero padding
+// (Tensor.cpp:40-72 builds this matrix per sample on the CPU; here it only ever exists as this index map).
+template <class R, bool PIXEL_IS_RED>
+struct Im2colLoader {
+    static constexpr bool kRedFast = PIXEL_IS_RED;
+    const R* x; const int* gather; ConvGeom g;
+    __device__ __forceinline__ R operator()(int o, int r) const {
+        const int pix = PIXEL_IS_RED ? r : o;
+        const int k = PIXEL_IS_RED ? o : r;
+        const int b = pix / g.P, p = pix - b * g.P;
+        const int oy = p / g.OW, ox = p - oy * g.OW;
+        const int c = k / g.KK, q = k - c * g.KK;
+        const int ky = q / g.KW, kx = q - ky * g.KW;
+        const int iy = oy * g.sh - g.ph + ky, ix = ox * g.sw - g.pw + kx;
+        if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return R(0);
+        const size_t s = gather ? (size_t)gather[b] : (size_t)b;
+        return x[(s * g.C + c) * g.HW + iy * g.W + ix];
+    }
+};
+
+template <class R>
+struct GradPixelLoader {  // outer = filter f, red = (b, p):  G[b][f][p]
+    static constexpr bool kRedFast = true;
+    const R* G; int F, P;
+    __device__ __forceinline__ R operator()(int f, int r) const {
+        const int b = r / P, p = r - b * P;
+        return G[((size_t)b * F + f) * P + p];
+    }
+};
+
+template <class R>
+struct FilterTLoader {  // outer = input channel c, red = (f, q=(ky,kx)):  filters[f][c][q]
+    static constexpr bool kRedFast = true;
+    const R* filt; int C, KK;
+    __device__ __forceinline__ R operator()(int c, int r) const {
+        const int f = r / KK, q = r - f * KK;
+        return filt[((size_t)f * C + c) * KK + q];
+    }
+};
+
+template <class R>
+struct GradGatherLoader {  // outer = (b, y, x) input pixel, red = (f, ky, kx): the output-gradient pixel this tap reaches
+    static constexpr bool kRedFast = false;
+    const R* G; ConvGeom g;
+    __device__ __forceinline__ R operator()(int o, int r) const {
+        const int b = o / g.HW, yx = o - b * g.HW;
+        const int y = yx / g.W, x = yx - y * g.W;
+        const int f = r / g.KK, q = r - f * g.KK;
+        const int ky = q / g.KW, kx = q - ky * g.KW;
+        const int ty = y + g.ph - ky, tx = x + g.pw - kx;
+        if (ty < 0 || tx < 0) return R(0);
+        const int oy = ty / g.sh, ox = tx / g.sw;
+        if (oy * g.sh != ty || ox * g.sw != tx || oy >= g.OH || ox >= g.OW) return R(0);
+        return G[((size_t)b * g.F + f) * g.P + oy * g.OW + ox];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogues.
+// ---------------------------------------------------------------------------------------------------------------
+template <class R>
+struct EpiFullForward {  // y[b][n] = act(acc + bias[n]);  deriv optional  (NLayer.inl:131-142)
+    R* y; R* deriv; const R* bias; int N; int act;
+    __device__ __forceinline__ void operator()(int b, int n, R acc) const {
+        R d; const R v = apply_activation<R>(act, acc + bias[n], d);
+        const size_t o = (size_t)b * N + n;
+        y[o] = v;
+        if (deriv) deriv[o] = d;
+    }
+};
+
+template <class R>
+struct EpiConvForward {  // i = filter f, j = (b, p): y[b][f][p] = act(acc + bias[f][p]) with the UNTIED bias (CLayer.inl:130)
+    R* y; R* deriv; const R* bias; int F, P; int act;
+    __device__ __forceinline__ void operator()(int f, int j, R acc) const {
+        const int b = j / P, p = j - b * P;
+        R d; const R v = apply_activation<R>(act, acc + bias[(size_t)f * P + p], d);
+        const size_t o = ((size_t)b * F + f) * P + p;
+        y[o] = v;
+        if (deriv) deriv[o] = d;
+    }
+};
+
+template <class R>
+struct EpiAccumulate {  // out = scale != 0 ? scale * out + acc : acc   (gradient_scale_factor, NLayer.inl:158-164)
+    R* out; size_t ld; R scale;
+    __device__ __forceinline__ void operator()(int i, int j, R acc) const {
+        const size_t o = (size_t)i * ld + j;
+        out[o] = scale != R(0) ? acc + scale * out[o] : acc;
+    }
+};
+
+template <class R>
+struct EpiStore {
+    R* out; size_t ld;
+    __device__ __forceinline__ void operator()(int i, int j, R acc) const { out[(size_t)i * ld + j] = acc; }
+};
+
+template <class R>
+struct EpiConvInputGrad {  // i = channel c, j = (b, yx): dx[b][c][yx]
+    R* dx; int C, HW;
+    __device__ __forceinline__ void operator()(int c, int j, R acc) const {
+        const int b = j / HW, yx = j - b * HW;
+        dx[((size_t)b * C + c) * HW + yx] = acc;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row kernels: softmax forward (ActivationFunction.inl:47-54, ActivationFunctionHelper.cpp:44-48) and its input
+// gradient (ActivationFunctionHelper.cpp:50-58).  One warp per sample; warp-shuffle reductions.
+// ---------------------------------------------------------------------------------------------------------------
+template <class R> __device__ __forceinline__ R warp_sum(R v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <class R> __device__ __forceinline__ R warp_max(R v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const R t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+
+template <class R>
+__global__ void softmax_forward_kernel(R* __restrict__ zy, R* __restrict__ aux, int rows, int n) {
+    const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    R* z = zy + (size_t)row * n;
+    R m = -real_limits<R>::max();
+    for (int i = lane; i < n; i += 32) m = z[i] > m ? z[i] : m;
+    m = warp_max<R>(m);
+    R s = R(0);
+    for (int i = lane; i < n; i += 32) { const R e = dl_exp<R>(z[i] - m); z[i] = e; s += e; }
+    s = warp_sum<R>(s);
+    const R factor = R(1) / s;
+    for (int i = lane; i < n; i += 32) {
+        const R e = z[i];
+        if (aux) aux[(size_t)row * n + i] = e;   // un-normalised exponents are the stored auxiliary data
+        z[i] = e * factor;
+    }
+}
+
+template <class R>
+__global__ void softmax_in_grad_kernel(const R* __restrict__ aux, const R* __restrict__ out_grad, R* __restrict__ res, int rows, int n) {
+    const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    const R* a = aux + (size_t)row * n;
+    const R* g = out_grad + (size_t)row * n;
+    R* r = res + (size_t)row * n;
+    R s = R(0);
+    for (int i = lane; i < n; i += 32) s += a[i];
+    s = warp_sum<R>(s);
+    const R ood = R(1) / s;
+    R t = R(0);
+    for (int i = lane; i < n; i += 32) { const R v = a[i] * g[i] * ood; r[i] = v; t += v; }
+    t = warp_sum<R>(t);
+    const R temp_sum = t * ood;
+    for (int i = lane; i < n; i += 32) r[i] = r[i] - a[i] * temp_sum;
+}
+
+// g[b][e] = delta[b][e] * deriv[b][e] (AFunction::calc_in_grad, ActivationFunction.inl:102-106) written once, and
+// its batch sum (the bias gradient, CLayer.inl:148-156 / NLayer.inl:156-160) accumulated in the same pass:
+// partial[chunk][e] = sum over the chunk's samples.  deriv == nullptr: g already holds the activation gradient.
+template <class R>
+__global__ void act_grad_bias_partial_kernel(const R* __restrict__ delta, const R* __restrict__ deriv, R* __restrict__ g,
+                                             R* __restrict__ partial, int B, int n, int chunk) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int b0 = blockIdx.y * chunk, b1 = min(B, b0 + chunk);
+    R acc = R(0);
+    for (int b = b0; b < b1; ++b) {
+        const size_t o = (size_t)b * n + e;
+        R v;
+        if (deriv) { v = deriv[o] * delta[o]; g[o] = v; } else v = g[o];
+        acc += v;
+    }
+    partial[(size_t)blockIdx.y * n + e] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pooling (PLayer.inl:115-168).  Forward: Tensor::min_max_pool<true> (Tensor.cpp:673-716; strict comparison, so the
+// first element in (ky, kx) scan order wins ties; the map stores the flat index into the SAMPLE's input tensor) and
+// scale_pool (Tensor.cpp:755-779).  Backward: the reference zero-fills and scatters through the map
+// (Tensor.cpp:721-734, thrust::scatter on the GPU, CudaTensor.cu:751-761); here every INPUT element looks up the
+// one window that covers it, so the pass is a single coalesced write with no memset and no scatter.
+// ---------------------------------------------------------------------------------------------------------------
+template <class R>
+__global__ void pool_forward_kernel(const R* __restrict__ x, R* __restrict__ y, int* __restrict__ map, size_t total,
+                                    int C, int H, int W, int wh, int ww, int OH, int OW, int type) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int ox = (int)(e % OW); size_t t = e / OW;
+    const int oy = (int)(t % OH); t /= OH;
+    const int c = (int)(t % C); const size_t b = t / C;
+    const R* xs = x + b * (size_t)C * H * W;
+    if (type == DLB_POOL_AVERAGE) {
+        R acc = R(0);
+        for (int ky = 0; ky < wh; ++ky)
+            for (int kx = 0; kx < ww; ++kx) acc += xs[((size_t)c * H + oy * wh + ky) * W + ox * ww + kx];
+        y[e] = acc * (R(1) / R(wh * ww));
+        return;
+    }
+    const bool is_max = type == DLB_POOL_MAX;
+    R best = is_max ? -real_limits<R>::max() : real_limits<R>::max();
+    int best_id = -1;
+    for (int ky = 0; ky < wh; ++ky)
+        for (int kx = 0; kx < ww; ++kx) {
+            const int id = (c * H + oy * wh + ky) * W + ox * ww + kx;
+            const R cur = xs[id];
+            if (is_max ? (best < cur) : (best > cur)) { best = cur; best_id = id; }
+        }
+    y[e] = best;
+    if (map) map[e] = best_id;
+}
+
+template <class R>
+__global__ void pool_backward_kernel(const R* __restrict__ delta, const int* __restrict__ map, R* __restrict__ dx, size_t total,
+                                     int C, int H, int W, int wh, int ww, int OH, int OW, int type) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int x = (int)(e % W); size_t t = e / W;
+    const int y = (int)(t % H); t /= H;
+    const int c = (int)(t % C); const size_t b = t / C;
+    const int oy = y / wh, ox = x / ww;
+    R v = R(0);
+    if (oy < OH && ox < OW) {
+        const size_t o = (b * C + c) * (size_t)OH * OW + (size_t)oy * OW + ox;
+        if (type == DLB_POOL_AVERAGE) v = delta[o] * (R(1) / R(wh * ww));
+        else if (map[o] == (c * H + y) * W + x) v = delta[o];
+    }
+    dx[e] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cost derivative (CostFunction.inl:47-51 -> CostFunctionHelper.cpp:52-57).  The reference obtains it by forward-mode
+// automatic differentiation (Dual.h) of the lambdas in CostFunctionFactory.h:29-55; the dual arithmetic is expanded
+// here term by term, including Func::nan_to_num (Functions.h:65-78) whose saturated branches have derivative 0.
+// ---------------------------------------------------------------------------------------------------------------
+template <class R> __device__ __forceinline__ bool not_finite(R v) { return isinf(v) || isnan(v); }
+
+template <class R>
+__device__ __forceinline__ R cost_derivative(int id, R x, R ref) {
+    switch (id) {
+    case DLB_COST_SQUARED_ERROR: { const R diff = x - ref; const R h = R(0.5) * diff; return R(1) * h + R(0.5) * diff; }
+    case DLB_COST_CROSS_ENTROPY: {
+        if (ref <= R(0)) {
+            const R a = R(1) - x;
+            const R da = R(-1) * (R(1) / a);
+            const R val = -dl_log<R>(a), d = da * R(-1);
+            return (not_finite(val) || not_finite(d)) ? R(0) : d;
+        }
+        if (ref >= R(1)) {
+            const R dl = R(1) * (R(1) / x);
+            const R val = -dl_log<R>(x), d = dl * R(-1);
+            return (not_finite(val) || not_finite(d)) ? R(0) : d;
+        }
+        const R lx = dl_log<R>(x), dlx = R(1) * (R(1) / x);
+        const R a = R(1) - x, la = dl_log<R>(a), dla = R(-1) * (R(1) / a);
+        const R omr = R(1) - ref;
+        const R v1 = ref * lx, d1 = dlx * ref + R(0) * lx;
+        const R v2 = omr * la, d2 = dla * omr + R(0) * la;
+        const R val = -(v1 + v2), d = (d1 + d2) * R(-1);
+        return (not_finite(val) || not_finite(d)) ? R(0) : d;
+    }
+    case DLB_COST_LINEAR: return R(1);
+    default: return R(0) / R(0);
+    }
+}
+
+template <class R> __device__ __forceinline__ R nan_to_num(R v) {
+    if (isinf(v)) return v < R(0) ? -real_limits<R>::max() : real_limits<R>::max();
+    if (isnan(v)) return R(0);
+    return v;
+}
+
+template <class R>
+__device__ __forceinline__ R cost_value(int id, R x, R ref) {  // CostFunctionFactory.h:33-53
+    switch (id) {
+    case DLB_COST_SQUARED_ERROR: { const R diff = x - ref; return R(0.5) * diff * diff; }
+    case DLB_COST_CROSS_ENTROPY:
+        if (ref <= R(0)) return nan_to_num<R>(-dl_log<R>(R(1) - x));
+        if (ref >= R(1)) return nan_to_num<R>(-dl_log<R>(x));
+        return nan_to_num<R>(-(ref * dl_log<R>(x) + (R(1) - ref) * dl_log<R>(R(1) - x)));
+    case DLB_COST_LINEAR: return x;
+    default: return R(0) / R(0);
+    }
+}
+
+template <class R>
+__global__ void cost_gradient_kernel(const R* __restrict__ out, const R* __restrict__ ref, const int* __restrict__ gather,
+                                     R* __restrict__ grad, size_t total, int n, int cost_id) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const size_t b = e / n; const int j = (int)(e - b * n);
+    const size_t row = gather ? (size_t)gather[b] : b;
+    grad[e] = cost_derivative<R>(cost_id, out[e], ref[row * n + j]);
+}
+
+// Sum over the mini-batch of the per-sample cost (CostFunctionHelper.cpp:27-35), one block, result in double.
+template <class R>
+__global__ void cost_sum_kernel(const R* __restrict__ out, const R* __restrict__ ref, const int* __restrict__ gather,
+                                int B, int n, int cost_id, double* __restrict__ result) {
+    __shared__ double part[256];
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const size_t row = gather ? (size_t)gather[b] : (size_t)b;
+        R s = R(0);
+        for (int j = 0; j < n; ++j) s += cost_value<R>(cost_id, out[(size_t)b * n + j], ref[row * n + j]);
+        acc += (double)s;
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *result = part[0];
+}
+
+// Per-row argmax (BasicCollection::max_element_id, first maximum), used by evaluation (Net.inl:432-433).
+template <class R>
+__global__ void argmax_rows_kernel(const R* __restrict__ y, int* __restrict__ cls, int rows, int n) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const R* p = y + (size_t)r * n;
+    int best = 0;
+    for (int j = 1; j < n; ++j) if (p[best] < p[j]) best = j;
+    cls[r] = best;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SGD update of the whole flat parameter buffer in one launch (ALayer.inl:97-122 applied to every layer,
+// Net.inl:309-316):  regularisable containers  w <- w * param_scale + g * grad_scale   (scale_and_add_scaled)
+//                    biases (or lambda == 0)   b <- b + g * grad_scale                  (add_scaled)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxSegments = 64;
+struct UpdateSegments {
+    int count;
+    long long end[kMaxSegments];        // exclusive end offset of each segment in the flat buffer
+    unsigned char regularised[kMaxSegments];
+};
+
+template <class R>
+__global__ void sgd_update_kernel(R* __restrict__ p, const R* __restrict__ g, size_t n, UpdateSegments segs,
+                                  R param_scale, R grad_scale, int nontrivial_reg) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    int s = 0;
+    while (s < segs.count - 1 && (long long)e >= segs.end[s]) ++s;
+    const bool reg = nontrivial_reg && segs.regularised[s];
+    const R x = p[e], y = g[e];
+    p[e] = reg ? x * param_scale + y * grad_scale : x + y * grad_scale;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Typed host-side launchers.
+// ---------------------------------------------------------------------------------------------------------------
+struct LaunchCtx {
+    cudaStream_t stream;
+    GemmWorkspace ws;
+};
+
+template <class R>
+void softmax_forward(const LaunchCtx& lc, R* zy, R* aux, int rows, int n) {
+    TagScope tag_("softmax_fwd");
+    DLB_LAUNCH((softmax_forward_kernel<R>), dim3(ceil_div(rows, 4)), dim3(128), lc.stream, zy, aux, rows, n);
+}
+
+// y = act(W x + b) over the batch.  x rows may be gathered (layer 0 reads the resident data set through the
+// step's slice of the epoch permutation).
+template <class R>
+void full_forward(const LaunchCtx& lc, int B, int in_n, int out_n, int act, const R* x, const int* gather,
+                  const R* bias, const R* W, R* y, R* deriv) {
+    {
+        TagScope tag_("full_fwd");
+        gemm<R>(lc.stream, B, out_n, in_n, DenseRowLoader<R>{x, (size_t)in_n, gather}, DenseRowLoader<R>{W, (size_t)in_n, nullptr},
+                EpiFullForward<R>{y, act == DLB_ACT_SOFTMAX ? nullptr : deriv, bias, out_n, act}, lc.ws);
+    }
+    if (act == DLB_ACT_SOFTMAX) softmax_forward<R>(lc, y, deriv, B, out_n);
+}
+
+template <class R>
+void conv_forward(const LaunchCtx& lc, int B, const ConvGeom& g, int act, const R* x, const int* gather,
+                  const R* bias, const R* filters, R* y, R* deriv) {
+    {
+        TagScope tag_("conv_fwd");
+        gemm<R>(lc.stream, g.F, B * g.P, g.K, DenseRowLoader<R>{filters, (size_t)g.K, nullptr}, Im2colLoader<R, false>{x, gather, g},
+                EpiConvForward<R>{y, act == DLB_ACT_SOFTMAX ? nullptr : deriv, bias, g.F, g.P, act}, lc.ws);
+    }
+    if (act == DLB_ACT_SOFTMAX) softmax_forward<R>(lc, y, deriv, B, g.out_n);
+}
+
+// g = dC/dz of the layer (activation gradient applied to the incoming deltas) and the bias gradient
+// dbias = scale * dbias + sum_b g[b].
+template <class R>
+void activation_grad_and_bias(const LaunchCtx& lc, int B, int n, int act, const R* delta, const R* deriv, R* g, R* dbias, R scale) {
+    TagScope tag_("act_grad_bias");
+    constexpr int kChunk = 16;
+    if (act == DLB_ACT_SOFTMAX)
+        DLB_LAUNCH((softmax_in_grad_kernel<R>), dim3(ceil_div(B, 4)), dim3(128), lc.stream, deriv, delta, g, B, n);
+    int chunk = kChunk;
+    int chunks = ceil_div(B, chunk);
+    const size_t cap = lc.ws.bytes / ((size_t)n * sizeof(R));
+    if ((size_t)chunks > cap) { chunks = (int)(cap > 0 ? cap : 1); chunk = ceil_div(B, chunks); chunks = ceil_div(B, chunk); }
+    R* partial = static_cast<R*>(lc.ws.ptr);
+    DLB_LAUNCH((act_grad_bias_partial_kernel<R>), dim3(ceil_div(n, 128), chunks), dim3(128), lc.stream,
+               delta, act == DLB_ACT_SOFTMAX ? (const R*)nullptr : deriv, g, partial, B, n, chunk);
+    DLB_LAUNCH((gemm_finalize_kernel<R, EpiAccumulate<R>>), dim3(ceil_div(n, 256)), dim3(256), lc.stream,
+               (const R*)partial, chunks, 1, n, EpiAccumulate<R>{dbias, (size_t)n, scale});
+}
+
+// NLayer<D>::backpropagate (NLayer.inl:144-171) over the batch.  dx may be nullptr (layer 0, Net.inl:272).
+template <class R>
+void full_backward(const LaunchCtx& lc, int B, int in_n, int out_n, int act, const R* x, const int* gather, const R* delta,
+                   const R* deriv, const R* W, R* g, R* dbias, R* dW, R* dx, R scale) {
+    activation_grad_and_bias<R>(lc, B, out_n, act, delta, deriv, g, dbias, scale);
+    {
+        TagScope tag_("full_dW");
+        gemm<R>(lc.stream, out_n, in_n, B, DenseColLoader<R>{g, (size_t)out_n, nullptr}, DenseColLoader<R>{x, (size_t)in_n, gather},
+                EpiAccumulate<R>{dW, (size_t)in_n, scale}, lc.ws);
+    }
+    if (dx) {
+        TagScope tag_("full_dX");
+        gemm<R>(lc.stream, B, in_n, out_n, DenseRowLoader<R>{g, (size_t)out_n, nullptr}, DenseColLoader<R>{W, (size_t)in_n, nullptr},
+                EpiStore<R>{dx, (size_t)in_n}, lc.ws);
+    }
+}
+
+// CLayer<D>::backpropagate (CLayer.inl:139-197) over the batch.
+template <class R>
+void conv_backward(const LaunchCtx& lc, int B, const ConvGeom& cg, int act, const R* x, const int* gather, const R* delta,
+                   const R* deriv, const R* filters, R* g, R* dbias, R* dfilters, R* dx, R scale) {
+    activation_grad_and_bias<R>(lc, B, cg.out_n, act, delta, deriv, g, dbias, scale);
+    {
+        TagScope tag_("conv_dK");
+        gemm<R>(lc.stream, cg.F, cg.K, B * cg.P, GradPixelLoader<R>{g, cg.F, cg.P}, Im2colLoader<R, true>{x, gather, cg},
+                EpiAccumulate<R>{dfilters, (size_t)cg.K, scale}, lc.ws);
+    }
+    if (dx) {
+        TagScope tag_("conv_dX");
+        gemm<R>(lc.stream, cg.C, B * cg.HW, cg.F * cg.KK, FilterTLoader<R>{filters, cg.C, cg.KK}, GradGatherLoader<R>{g, cg},
+                EpiConvInputGrad<R>{dx, cg.C, cg.HW}, lc.ws);
+    }
+}
+
+template <class R>
+void pool_forward(const LaunchCtx& lc, int B, const dlb_layer_spec& s, const R* x, R* y, int* map) {
+    TagScope tag_("pool_fwd");
+    const int OH = conv_out_size(s.in_h, s.win_h, 0, s.win_h), OW = conv_out_size(s.in_w, s.win_w, 0, s.win_w);
+    const size_t total = (size_t)B * s.in_c * OH * OW;
+    if (!total) return;
+    DLB_LAUNCH((pool_forward_kernel<R>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, x, y, map, total,
+               s.in_c, s.in_h, s.in_w, s.win_h, s.win_w, OH, OW, s.pool_type);
+}
+
+template <class R>
+void pool_backward(const LaunchCtx& lc, int B, const dlb_layer_spec& s, const R* delta, const int* map, R* dx) {
+    TagScope tag_("pool_bwd");
+    const int OH = conv_out_size(s.in_h, s.win_h, 0, s.win_h), OW = conv_out_size(s.in_w, s.win_w, 0, s.win_w);
+    const size_t total = (size_t)B * s.in_c * s.in_h * s.in_w;
+    if (!total) return;
+    DLB_LAUNCH((pool_backward_kernel<R>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, delta, map, dx, total,
+               s.in_c, s.in_h, s.in_w, s.win_h, s.win_w, OH, OW, s.pool_type);
+}
+
+template <class R>
+void cost_gradient(const LaunchCtx& lc, int B, int n, int cost_id, const R* out, const R* ref, const int* gather, R* grad) {
+    TagScope tag_("cost_grad");
+    const size_t total = (size_t)B * n;
+    DLB_LAUNCH((cost_gradient_kernel<R>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, out, ref, gather, grad, total, n, cost_id);
+}
+
+template <class R>
+void sgd_update(const LaunchCtx& lc, R* params, const R* grads, size_t n, const UpdateSegments& segs, R param_scale, R grad_scale, bool nontrivial_reg) {
+    TagScope tag_("sgd_update");
+    if (!n) return;
+    DLB_LAUNCH((sgd_update_kernel<R>), dim3((unsigned)ceil_div<size_t>(n, 256)), dim3(256), lc.stream, params, grads, n, segs,
+               param_scale, grad_scale, nontrivial_reg ? 1 : 0);
+}
+
+}  // namespace dlb

@@ -1,0 +1,196 @@
+/*
+ * dlb200.h — C ABI of libdlb200.so: the B200 (sm_100a) implementation of the mini-batch training hot path of
+ * dragunovdenis/DeepLearning (Net<D>::learn through CLayer / PLayer / NLayer with the GpuDC data context).
+ *
+ * This header is the drop-in boundary.  The reference has no FFI of its own — its GPU plug-in seam is the
+ * compile-time data-context policy `GpuDC` (DeepLearningCuda/NeuralNet/DataContextCuda.h:28-77) whose tensor
+ * types (CudaTensor / CudaMatrix / CudaVector, DeepLearningCuda/Math/*.cuh) call CUDA kernels directly.  Here the
+ * same operations are reached through plain `extern "C"` entry points (pointers + sizes + POD structs, `int`
+ * status, no C++ or torch types), and the host side that mirrors the reference's classes lives above this line:
+ * C++ (deeplearning_b200/host/) for reference client code, Python/ctypes (deeplearning_b200/) for tests and bench.
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success; on failure a non-zero code, and dlb_last_error() (thread-local) holds
+ *     the message — shape/argument violations and CUDA failures alike (the reference throws std::exception with
+ *     the message, CudaUtils.cpp:24-30; the C++ wrappers re-throw);
+ *   - `_f32` / `_f64` suffixes select the reference's `Real` (defs.h:25-29: double by default, float under
+ *     USE_SINGLE_PRECISION);
+ *   - device pointers are raw CUDA device pointers; all work is enqueued on the context's stream and is
+ *     asynchronous unless stated otherwise;
+ *   - a mini-batch is packed sample-major: [B][C][H][W], each sample in the reference's CHW order
+ *     (Tensor.cpp:216-219); matrices are row-major [out][in] (Matrix.cpp:125-128, NLayer.h:41-44);
+ *   - flat parameter / gradient layout = the reference's container order (NLayer.inl:180-193,
+ *     CLayer.inl:199-213): per layer [biases, weights] or [biases (F x OH x OW, untied), filter_0 .. filter_{F-1}].
+ *   - there is NO CPU fallback: every entry point that computes needs a CUDA device and fails loudly without one.
+ */
+#ifndef DLB200_H
+#define DLB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "dlb200_spec.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLB_API __attribute__((visibility("default")))
+
+typedef struct dlb_context dlb_context; /* one device + one stream + scratch; replaces CudaSetup/cudaStreamPerThread (CudaSetup.cpp:29-76, CudaUtils.h:43-108) */
+typedef struct dlb_net dlb_net;         /* batched Net<GpuDC>: parameters, traces, gradient buffers, resident data set */
+
+DLB_API int dlb_version(void);
+DLB_API const char* dlb_last_error(void);
+
+/* ---- context & memory (replaces CudaUtils::cuda_allocate/cuda_free/cuda_copy_*, CudaUtils.h:43-108) ---------- */
+/* external_stream: a cudaStream_t to enqueue on (e.g. torch's current stream) or NULL to create a private one. */
+DLB_API int dlb_context_create(int device, void* external_stream, dlb_context** out);
+DLB_API int dlb_context_destroy(dlb_context* ctx);
+DLB_API int dlb_context_synchronize(dlb_context* ctx);
+DLB_API void* dlb_context_stream(dlb_context* ctx);
+DLB_API int dlb_malloc(dlb_context* ctx, size_t bytes, void** out);
+DLB_API int dlb_free(dlb_context* ctx, void* ptr);
+DLB_API int dlb_memcpy_h2d(dlb_context* ctx, void* dst, const void* src, size_t bytes);
+DLB_API int dlb_memcpy_d2h(dlb_context* ctx, void* dst, const void* src, size_t bytes); /* synchronises the stream */
+DLB_API int dlb_memcpy_d2d(dlb_context* ctx, void* dst, const void* src, size_t bytes);
+DLB_API int dlb_memset(dlb_context* ctx, void* dst, int value, size_t bytes);
+DLB_API int dlb_host_alloc_pinned(size_t bytes, void** out);
+DLB_API int dlb_host_free_pinned(void* ptr);
+/* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
+DLB_API int64_t dlb_context_launch_count(dlb_context* ctx);
+
+/* ---- batched layer operators on raw device pointers ---------------------------------------------------------
+ * `gather` (nullable, device int32[B]) maps batch slot -> row of `x`, so layer 0 can read a resident data set
+ * through a slice of the epoch permutation (Net.inl:260-262) without a copy.
+ * `scale` is the reference's gradient_scale_factor: 0 overwrites the gradient, otherwise grad = scale*grad + new
+ * (NLayer.inl:158-164, CLayer.inl:148-156, Tensor.cpp:476-479).  `g` is scratch of B*out elements that receives
+ * the activation gradient dC/dz.  `dx` may be NULL (first layer, Net.inl:272).  `deriv`/`index_map` may be NULL in
+ * forward calls (inference, ALayer::act with trace_data == nullptr).
+ */
+#define DLB_DECLARE_OPS(SFX, REAL)                                                                                              \
+    /* CLayer<D>::act, CLayer.inl:108-137 (replaces CudaTensor::convolve, CudaTensor.cu:395-416 + `+= biases` + activation) */ \
+    DLB_API int dlb_conv_forward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* x,                  \
+                                       const int32_t* gather, const REAL* bias, const REAL* filters, REAL* y, REAL* deriv);     \
+    /* CLayer<D>::backpropagate, CLayer.inl:139-197 (replaces CudaTensor::convolution_gradient, CudaTensor.cu:492-518) */      \
+    DLB_API int dlb_conv_backward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* x,                 \
+                                        const int32_t* gather, const REAL* delta, const REAL* deriv, const REAL* filters,       \
+                                        REAL* g, REAL* dbias, REAL* dfilters, REAL* dx, double scale);                          \
+    /* PLayer<D>::act, PLayer.inl:115-138 (replaces CudaTensor::min_max_pool / average_pool, CudaTensor.cu:565-746) */         \
+    DLB_API int dlb_pool_forward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* x, REAL* y,         \
+                                       int32_t* index_map);                                                                     \
+    /* PLayer<D>::backpropagate, PLayer.inl:140-168 (replaces min_max_pool_input_gradient / average_pool_input_gradient) */    \
+    DLB_API int dlb_pool_backward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* delta,             \
+                                        const int32_t* index_map, REAL* dx);                                                    \
+    /* NLayer<D>::act, NLayer.inl:131-142 (replaces CudaMatrix::mul_add, CudaMatrix.cu:355-365 + activation) */                \
+    DLB_API int dlb_full_forward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* x,                  \
+                                       const int32_t* gather, const REAL* bias, const REAL* weights, REAL* y, REAL* deriv);     \
+    /* NLayer<D>::backpropagate, NLayer.inl:144-171 (replaces vector_col_times_vector_row + transpose_mul, CudaMatrix.cu) */   \
+    DLB_API int dlb_full_backward_##SFX(dlb_context* ctx, const dlb_layer_spec* spec, int batch, const REAL* x,                 \
+                                        const int32_t* gather, const REAL* delta, const REAL* deriv, const REAL* weights,       \
+                                        REAL* g, REAL* dbias, REAL* dweights, REAL* dx, double scale);                          \
+    /* CostFunction<T>::deriv_in_place, CostFunction.inl:47-51 (replaces CostFunctionHelperCuda::evaluate_gradient) */         \
+    DLB_API int dlb_cost_gradient_##SFX(dlb_context* ctx, int cost_id, int batch, int n, const REAL* out, const REAL* ref,      \
+                                        const int32_t* gather, REAL* grad);                                                     \
+    /* ALayer<D>::update on one container, ALayer.inl:97-122; l_rate is signed as there (Net passes -learning_rate) */      \
+    DLB_API int dlb_sgd_update_##SFX(dlb_context* ctx, REAL* params, const REAL* grads, int64_t n, int regularised,             \
+                                     double l_rate, double reg_factor, double grad_scale_factor);
+
+DLB_DECLARE_OPS(f32, float)
+DLB_DECLARE_OPS(f64, double)
+
+/* ---- the batched Net<GpuDC> --------------------------------------------------------------------------------- */
+/* real_bytes: 4 (float) or 8 (double).  Layers are validated like Net<D>::try_load_from_script (Net.inl:83-88). */
+DLB_API int dlb_net_create(dlb_context* ctx, const dlb_layer_spec* specs, int n_layers, int real_bytes, dlb_net** out);
+DLB_API int dlb_net_destroy(dlb_net* net);
+DLB_API int64_t dlb_net_param_count(const dlb_net* net);
+DLB_API int dlb_net_layer_count(const dlb_net* net);
+DLB_API int64_t dlb_net_layer_in_size(const dlb_net* net, int layer);
+DLB_API int64_t dlb_net_layer_out_size(const dlb_net* net, int layer);
+DLB_API int64_t dlb_net_layer_param_offset(const dlb_net* net, int layer);
+/* host <-> device parameter transfer in the flat layout (GpuDC::from_host / to_host, DataContextCuda.h:40-70) */
+DLB_API int dlb_net_set_params(dlb_net* net, const void* host_params);
+DLB_API int dlb_net_get_params(dlb_net* net, void* host_params);
+DLB_API void* dlb_net_device_params(dlb_net* net);
+DLB_API void* dlb_net_device_grads(dlb_net* net);
+
+/* Training data: n items [n][in_size] and references [n][out_size] in the net's Real; copied once into HBM and
+ * kept resident (the reference passes std::vector<tensor_t>, Net.inl:193-194). on_device != 0: the pointers are
+ * device pointers already and are adopted without a copy (they must outlive the net's use of them). */
+DLB_API int dlb_net_set_dataset(dlb_net* net, const void* inputs, const void* refs, int64_t n_items, int on_device);
+
+/* Net<D>::reset_random_generator(seed), Net.inl:599-603: seeds the generator that draws the epoch permutations. */
+DLB_API int dlb_net_reset_random_generator(dlb_net* net, unsigned seed);
+
+typedef void (*dlb_epoch_callback)(int64_t epoch, double scaled_l2_reg_factor, void* user);
+
+/* Net<D>::learn, Net.inl:193-324, on the resident data set: per epoch one std::ranges::shuffle of the index map,
+ * mini-batches of `batch_size` with the reference's tail rule (fewer than 1.5*batch_size remaining items form one
+ * batch), gradient = SUM over the batch, update with -lr/B and reg_factor = lambda / n_items.  Under data
+ * parallelism (dlb_net_set_distributed) every rank takes its contiguous slice of each batch and the summed
+ * gradients are all-reduced before the (identical) update.  The callback may be NULL. */
+DLB_API int dlb_net_learn(dlb_net* net, int64_t batch_size, int64_t epochs, double learning_rate, int cost_id, double lambda,
+                          dlb_epoch_callback callback, void* user);
+
+/* Net<D>::learn made resumable: runs the next n_steps mini-batches of the same epoch sequence (a new permutation
+ * is drawn whenever an epoch is exhausted; tail rule as in learn) and reports the items consumed over all ranks.
+ * learn(batch, epochs) == train_steps until epochs * steps_per_epoch steps have run. */
+DLB_API int dlb_net_train_steps(dlb_net* net, int64_t batch_size, int64_t n_steps, double learning_rate, int cost_id, double lambda,
+                                int64_t* items_out);
+
+/* One mini-batch step on explicit item indices of the resident data set (host int64 indices, n of them). */
+DLB_API int dlb_net_step_indices(dlb_net* net, const int64_t* indices, int64_t n, double learning_rate, int cost_id, double reg_factor);
+
+/* One mini-batch step on HOST buffers (inputs [n][in], refs [n][out], pinned or pageable): copies them to the
+ * device, runs forward + backward + update and, if `cost_out` is not NULL, copies back the summed cost of the batch
+ * evaluated before the update (a device->host read that synchronises). This is the end-to-end entry point. */
+DLB_API int dlb_net_step_host(dlb_net* net, const void* inputs, const void* refs, int64_t n, double learning_rate, int cost_id,
+                              double reg_factor, double* cost_out);
+
+/* Forward + cost derivative + backward on a host batch WITHOUT the update; the traces stay on the device for
+ * dlb_net_read.  `scale` is applied to the previous content of the gradient buffer (gradient_scale_factor). */
+DLB_API int dlb_net_forward_backward_host(dlb_net* net, const void* inputs, const void* refs, int64_t n, int cost_id, double scale);
+
+enum {
+    DLB_BUF_OUTPUT = 1,      /* [n][out_size(layer)]  output of `layer` (post-activation)            */
+    DLB_BUF_DERIVATIVES = 2, /* [n][out_size(layer)]  Trace.Derivatives (softmax: exp(x - max))       */
+    DLB_BUF_INDEX_MAP = 3,   /* [n][out_size(layer)]  int32 Trace.IndexMapping of a MIN/MAX PLayer    */
+    DLB_BUF_INPUT_GRAD = 4,  /* [n][in_size(layer)]   gradient w.r.t. the input of `layer` (layer>=1) */
+    DLB_BUF_COST_GRAD = 5,   /* [n][out_size(last)]   cost derivative fed to the last layer           */
+    DLB_BUF_GRADIENT = 6     /* [param_count]         flat summed gradient                            */
+};
+/* Copies a trace buffer of the last forward/backward (rows = its batch size) to the host; synchronises. */
+DLB_API int dlb_net_read(dlb_net* net, int what, int layer, void* host_dst, int64_t dst_bytes);
+DLB_API int dlb_net_write_gradient(dlb_net* net, const void* host_src);
+
+/* Net<D>::act + max_element_id (Net.inl:134-155, 432-433) over n host items; classes and/or outputs may be NULL. */
+DLB_API int dlb_net_eval_host(dlb_net* net, const void* inputs, int64_t n, int32_t* classes, void* outputs);
+
+/* Data parallelism: one process per GPU.  nccl_unique_id: the 128-byte ncclUniqueId created by rank 0
+ * (dlb_nccl_get_unique_id) and distributed by the launcher's own plumbing (torch.distributed, MPI, a file, ...). */
+DLB_API int dlb_nccl_get_unique_id(void* id_out_128_bytes);
+DLB_API int dlb_net_set_distributed(dlb_net* net, int rank, int world_size, const void* nccl_unique_id);
+
+/* The contiguous share [first, first + mine) of a global mini-batch of `count` items that `rank` of `world` takes
+ * (host-only helper; the data-parallel partitioning rule used by learn / train_steps / step_indices). */
+DLB_API int dlb_rank_slice(int64_t count, int rank, int world, int64_t* first, int64_t* mine);
+
+/* CUDA events on the context's stream (device-side timing for callers that do not link the CUDA runtime). */
+DLB_API int dlb_event_create(void** event_out);
+DLB_API int dlb_event_destroy(void* event);
+DLB_API int dlb_event_record(dlb_context* ctx, void* event);
+DLB_API int dlb_event_elapsed_ms(void* start, void* stop, double* ms_out); /* synchronises on `stop` */
+
+/* Per-kernel device timing (measurement aid for bench.py's roofline pass; off by default).  The report is text:
+ * one "<layer>:<operator>:<kernel>\t<launches>\t<total ms>" line per kernel; reading it clears the records. */
+DLB_API int dlb_timing_enable(int on);
+DLB_API int dlb_timing_report(char* buf, int64_t cap);
+
+/* The epoch permutations learn() would draw after reset_random_generator(seed): iota + one shuffle per epoch on
+ * the same std::mt19937 (Net.inl:158-171, 223).  Host-only helper for tests and for reference-side callers. */
+DLB_API int dlb_shuffle_sequence(unsigned seed, int64_t n, int64_t epochs, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLB200_H */

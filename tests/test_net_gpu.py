@@ -1,0 +1,156 @@
+"""GPU parity of whole nets against the CPU oracle (oracle/dl_oracle.c), through the C ABI (dlb_net_*).
+
+What is compared (BASELINE.json north_star): layer outputs, activation derivatives, gradients and updated weights
+within the stated relative tolerance (helpers.RTOL: 1e-5 float, 1e-12 double, atol = rtol * max|reference|);
+pooling index maps and predicted classes EXACTLY.  Nothing in the reference pins Net<GpuDC>::learn
+(DeepLearningCudaTest/NetCudaTest.cpp only instantiates the template), so whole-step parity is defined here.
+"""
+import numpy as np
+import pytest
+
+import deeplearning_b200 as dl
+from oracle import binding as ob
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+MINI_LENET = [ob.conv((1, 12, 12), (3, 3), 4, ob.RELU), ob.pool((4, 10, 10), (2, 2), ob.POOL_MAX),
+              ob.full((4, 5, 5), 16, ob.RELU), ob.full((1, 1, 16), 10, ob.SOFTMAX)]
+# the reference's layer-test fixtures chained into one net (Shared/NetLayersTestUtils.h:34-65)
+FIXTURE_NET = [ob.conv((5, 13, 17), (3, 3), 7, ob.SIGMOID, pad=(3, 6), stride=(2, 2)), ob.pool((7, 9, 14), (3, 4), ob.POOL_MIN),
+               ob.full((7, 3, 3), 23, ob.TANH), ob.full((1, 1, 23), 5, ob.LINEAR)]
+AVG_NET = [ob.conv((2, 9, 8), (2, 3), 3, ob.TANH, pad=(1, 0), stride=(1, 2)), ob.pool((3, 10, 3), (3, 2), ob.POOL_AVERAGE),
+           ob.conv((3, 3, 1), (2, 1), 5, ob.RELU, pad=(1, 1)), ob.full((5, 4, 3), 4, ob.SOFTMAX)]
+MINI_MLP = [ob.full((1, 1, 20), 15, ob.SIGMOID), ob.full((1, 1, 15), 10, ob.SIGMOID)]
+
+NETS = {"mini_lenet": (MINI_LENET, ob.CROSS_ENTROPY), "fixture": (FIXTURE_NET, ob.SQUARED_ERROR),
+        "avg": (AVG_NET, ob.CROSS_ENTROPY), "mini_mlp": (MINI_MLP, ob.CROSS_ENTROPY)}
+
+
+def compare_traces(orc, gpu, x, y, cost_id, real, scale=0.0, grads_in=None):
+    want = H.oracle_batch_trace(orc, x, y, cost_id, grads_in, scale)
+    if grads_in is not None:
+        gpu.write_gradient(grads_in)
+    gpu.forward_backward(x, y, cost_id, scale)
+    out_off = H.layer_offsets(orc.out_sizes)
+    in_off = H.layer_offsets(orc.in_sizes)
+    for l, s in enumerate(orc.specs):
+        sl = slice(out_off[l], out_off[l] + orc.out_sizes[l])
+        H.assert_close(f"layer {l} output", gpu.read(dl.BUF_OUTPUT, l), want["acts"][:, sl], real)
+        if s.type != ob.PULL:
+            H.assert_close(f"layer {l} derivatives", gpu.read(dl.BUF_DERIVATIVES, l), want["derivs"][:, sl], real, rtol_mult=5)
+        elif s.pool_type != ob.POOL_AVERAGE:
+            got = gpu.read(dl.BUF_INDEX_MAP, l)
+            assert np.array_equal(got, want["index_map"][:, sl]), f"layer {l}: pooling index map differs"
+        if l > 0:
+            isl = slice(in_off[l], in_off[l] + orc.in_sizes[l])
+            H.assert_close(f"layer {l} input gradient", gpu.read(dl.BUF_INPUT_GRAD, l), want["in_grads"][:, isl], real, rtol_mult=5)
+    H.assert_close("cost gradient", gpu.read(dl.BUF_COST_GRAD), want["cost_grad"], real, rtol_mult=5)
+    got_g = gpu.read(dl.BUF_GRADIENT)
+    for l, s in enumerate(orc.specs):   # per layer, so that each gradient is judged against its own scale
+        a = gpu.layer_param_offset(l)
+        b = gpu.layer_param_offset(l + 1) if l + 1 < len(orc.specs) else gpu.param_count
+        if b > a:
+            H.assert_close(f"layer {l} parameter gradient", got_g[a:b], want["grads"][a:b], real, rtol_mult=5)
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+@pytest.mark.parametrize("name", list(NETS))
+@pytest.mark.parametrize("batch", [1, 7])
+def test_forward_backward_matches_oracle(name, real, batch):
+    specs, cost = NETS[name]
+    orc, gpu = H.make_pair(specs, real, seed=3)
+    x, y = H.synthetic_batch(orc, batch, real, seed=5, one_hot=cost == ob.CROSS_ENTROPY)
+    compare_traces(orc, gpu, x, y, cost, real)
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_gradient_scale_factor(real):
+    """backpropagate(..., scale s) must yield s*G_in + G_pure (Shared/NetLayersTestUtils.h:70-100)."""
+    specs, cost = NETS["fixture"]
+    orc, gpu = H.make_pair(specs, real, seed=4)
+    x, y = H.synthetic_batch(orc, 3, real, seed=6, one_hot=False)
+    g_in = np.random.default_rng(9).normal(size=orc.param_count).astype(orc.dtype)
+    compare_traces(orc, gpu, x, y, cost, real, scale=0.37, grads_in=g_in)
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+@pytest.mark.parametrize("name,batch,n_items,lam", [("mini_lenet", 8, 50, 0.1), ("mini_mlp", 10, 64, 0.0), ("avg", 5, 23, 1.5)])
+def test_learn_matches_oracle(name, batch, n_items, lam, real):
+    """Weights after several epochs of Net::learn (permutations, tail-batch rule, regularised update) and the
+    predicted classes on the training set."""
+    specs, cost = NETS[name]
+    orc, gpu = H.make_pair(specs, real, seed=11)
+    x, y = H.synthetic_batch(orc, n_items, real, seed=12, lo=0.0, hi=1.0)
+    epochs, lr, seed = 3, 0.05, 5
+    perms = dl.shuffle_sequence(seed, n_items, epochs)
+    orc.learn(x, y, batch, epochs, lr, cost, lam, threads=1, perms=perms)
+    calls = []
+    gpu.reset_random_generator(seed)
+    gpu.learn(x, y, batch, epochs, lr, dl.CostFunctionId(cost), lam, epoch_callback=lambda e, r: calls.append((e, r)))
+    assert [c[0] for c in calls] == list(range(epochs))
+    assert np.allclose([c[1] for c in calls], 0.5 * lam / n_items, rtol=1e-6)
+    H.assert_close("parameters after learn", gpu.get_params(), orc.get_params(), real, rtol_mult=20)
+    assert np.array_equal(gpu.predict(x), orc.eval(x)), "predicted classes differ"
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_lenet_step_full_size(real):
+    """BASELINE configs[1] at its real size: one mini-batch of 256 through LeNet; gradient = sum over the batch of the
+    oracle's per-sample gradients; one update."""
+    specs = ob.lenet_specs()
+    orc, gpu = H.make_pair(specs, real, seed=21)
+    n = 256 if real == "f32" else 64
+    x, y = H.synthetic_batch(orc, n, real, seed=22, lo=0.0, hi=1.0)
+    want = H.oracle_batch_trace(orc, x, y, ob.CROSS_ENTROPY)
+    gpu.forward_backward(x, y, dl.CostFunctionId.CROSS_ENTROPY)
+    got = gpu.read(dl.BUF_GRADIENT)
+    for l in range(4):
+        a = gpu.layer_param_offset(l); b = gpu.layer_param_offset(l + 1) if l < 3 else gpu.param_count
+        if b > a:
+            H.assert_close(f"lenet layer {l} gradient", got[a:b], want["grads"][a:b], real, rtol_mult=10)
+    assert np.array_equal(gpu.read(dl.BUF_INDEX_MAP, 1), want["index_map"][:, 11520:11520 + 2880])
+    # the same batch as one training step on host buffers, with the batch cost read back
+    p0 = orc.get_params()
+    cost = gpu.step_host(x, y, 0.05, dl.CostFunctionId.CROSS_ENTROPY, reg_factor=0.001)
+    want_cost = sum(orc.cost(want["acts"][i, -10:], y[i]) for i in range(n))
+    assert abs(cost - want_cost) <= 1e-4 * abs(want_cost)
+    perm = np.arange(n, dtype=np.int64)[None, :]
+    orc.learn(x, y, n, 1, 0.05, ob.CROSS_ENTROPY, 0.001 * n, threads=1, perms=perm)
+    assert not np.array_equal(p0, orc.get_params())
+    H.assert_close("parameters after one step", gpu.get_params(), orc.get_params(), real, rtol_mult=10)
+
+
+def test_tail_batch_rule_and_step_indices():
+    """n_items = 24, batch 10: batches of 10 and 14, because fewer than 1.5 * batch remaining items form one batch
+    (Net.inl:235-236).  Reproduced with explicit step_indices calls."""
+    specs, cost = NETS["mini_mlp"]
+    real = "f64"
+    orc, gpu = H.make_pair(specs, real, seed=31)
+    x, y = H.synthetic_batch(orc, 24, real, seed=32)
+    perms = dl.shuffle_sequence(2, 24, 1)
+    orc.learn(x, y, 10, 1, 0.1, cost, 0.0, threads=1, perms=perms)
+    gpu.set_dataset(x, y)
+    gpu.step_indices(perms[0, :10], 0.1, dl.CostFunctionId(cost))
+    gpu.step_indices(perms[0, 10:], 0.1, dl.CostFunctionId(cost))
+    H.assert_close("parameters (10 + 14 split)", gpu.get_params(), orc.get_params(), real, rtol_mult=10)
+
+
+def test_eval_outputs_and_classes():
+    specs, _ = NETS["mini_lenet"]
+    orc, gpu = H.make_pair(specs, "f32", seed=41)
+    x, _ = H.synthetic_batch(orc, 33, "f32", seed=42)
+    cls, outs = orc.eval(x, want_outputs=True)
+    H.assert_close("net outputs", gpu.act(x), outs, "f32")
+    assert np.array_equal(gpu.predict(x), cls)
+
+
+def test_argument_errors_are_loud():
+    with pytest.raises(dl.DlbError):
+        bad = dl.Net([dl.NLayer(10, 5), dl.NLayer(7, 3)], real="f32")   # 5 != 7
+        bad.param_count
+    net = dl.Net([dl.NLayer(4, 3)], real="f32")
+    with pytest.raises(dl.DlbError):
+        net.set_params(np.zeros(5, np.float32))
+    with pytest.raises(dl.DlbError):
+        net.learn(np.zeros((3, 4)), np.zeros((2, 3)), 1, 1, 0.1, dl.CostFunctionId.SQUARED_ERROR)
