@@ -37,6 +37,9 @@ extern thread_local int g_tag_layer;
 void timing_begin(cudaStream_t stream, const char* kernel_text);
 void timing_end(cudaStream_t stream);
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory (once per kernel and size, not per launch).
+void allow_big_smem(const void* kernel, size_t bytes);
+
 struct TagScope {
     const char* prev;
     explicit TagScope(const char* t) : prev(g_tag) { g_tag = t; }
@@ -45,22 +48,29 @@ struct TagScope {
 
 #define DLB_UNPAREN(...) __VA_ARGS__
 #ifdef DLB_CUDA_EMU
-#define DLB_LAUNCH(kernel, grid, block, stream, ...)                       \
-    do {                                                                   \
-        ::dlb::g_launch_count.fetch_add(1, std::memory_order_relaxed);     \
-        ::cuemu::launch(DLB_UNPAREN kernel, (grid), (block), __VA_ARGS__); \
+#define DLB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)                         \
+    do {                                                                                \
+        ::dlb::g_launch_count.fetch_add(1, std::memory_order_relaxed);                  \
+        ::cuemu::launch_smem(DLB_UNPAREN kernel, (grid), (block), (smem), __VA_ARGS__); \
     } while (0)
+// dynamic shared memory of the running block, typed
+#define DLB_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(::cuemu::dyn_smem())
 #else
-#define DLB_LAUNCH(kernel, grid, block, stream, ...)                       \
-    do {                                                                   \
-        ::dlb::g_launch_count.fetch_add(1, std::memory_order_relaxed);     \
-        if (::dlb::g_timing_on) ::dlb::timing_begin((stream), #kernel);    \
-        auto dlb_kernel_ = DLB_UNPAREN kernel;                             \
-        dlb_kernel_<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);        \
-        DLB_CUDA(cudaGetLastError());                                      \
-        if (::dlb::g_timing_on) ::dlb::timing_end((stream));               \
+#define DLB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)                         \
+    do {                                                                                \
+        ::dlb::g_launch_count.fetch_add(1, std::memory_order_relaxed);                  \
+        if (::dlb::g_timing_on) ::dlb::timing_begin((stream), #kernel);                 \
+        auto dlb_kernel_ = DLB_UNPAREN kernel;                                          \
+        if ((smem) > 48 * 1024) ::dlb::allow_big_smem((const void*)dlb_kernel_, (size_t)(smem));                   \
+        dlb_kernel_<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                \
+        DLB_CUDA(cudaGetLastError());                                                   \
+        if (::dlb::g_timing_on) ::dlb::timing_end((stream));                            \
     } while (0)
+#define DLB_DYNAMIC_SMEM(type, name)                                  \
+    extern __shared__ __align__(16) unsigned char dlb_dyn_smem_raw[]; \
+    type* name = reinterpret_cast<type*>(dlb_dyn_smem_raw)
 #endif
+#define DLB_LAUNCH(kernel, grid, block, stream, ...) DLB_LAUNCH_SMEM(kernel, grid, block, 0, stream, __VA_ARGS__)
 
 template <class T> __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 

@@ -21,7 +21,7 @@
 #endif
 
 #include "../../include/dlb200.h"
-#include "layers.cuh"
+#include "fused.cuh"
 
 namespace dlb {
 
@@ -55,7 +55,14 @@ void timing_begin(cudaStream_t stream, const char* kernel_text) {
     g_timed.push_back(std::move(t));
 }
 void timing_end(cudaStream_t stream) { DLB_CUDA(cudaEventRecord(g_timed.back().e1, stream)); }
+void allow_big_smem(const void* kernel, size_t bytes) {
+    static std::vector<std::pair<const void*, size_t>> done;
+    for (auto& d : done) if (d.first == kernel && d.second >= bytes) return;
+    DLB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done.emplace_back(kernel, bytes);
+}
 #else
+void allow_big_smem(const void*, size_t) {}
 void timing_begin(cudaStream_t, const char*) {}
 void timing_end(cudaStream_t) {}
 #endif
@@ -243,6 +250,8 @@ struct dlb_net {
     virtual void read(int what, int layer, void* dst, int64_t bytes) = 0;
     virtual void write_gradient(const void* src) = 0;
     virtual void eval_host(const void* x, int64_t n, int32_t* classes, void* outputs) = 0;
+    virtual std::string describe_plan() = 0;
+    virtual void enable_graphs(bool on) = 0;
 };
 
 namespace {
@@ -263,6 +272,42 @@ struct NetT final : dlb_net {
     double* cost_dev = nullptr;
     int last_B = 0;
     UpdateSegments segs{};
+
+    // ---- train mode (fused fast path, fused.cuh) ----
+    struct TrainPlan {
+        bool ok = false;
+        bool has_cp = false;     // layers 0/1 are a fused CLayer + PLayer stage
+        int first_fc = 0;        // index of the first NLayer
+        ConvPoolPlan cp;
+        int head_nmax = 16;
+    } plan;
+    R* cp_partial = nullptr; int cp_grid = 0;          // [cp_grid][cp.n_par] per-CTA partial gradients of the conv stage
+    R* head_partial = nullptr; int head_chunks = 0;     // [head_chunks][n * (in_n + 1)]
+    int head_chunk_cap = 0;
+    int* d_cursor = nullptr;                            // device-side offset of the current batch in the epoch permutation
+    static constexpr int kHeadChunk = 32;
+
+    // CUDA graphs of the whole step, one per distinct (share, batch, hyper-parameters): the per-step launch sequence is
+    // identical for every batch of an epoch because the batch position lives in d_cursor on the device.
+    struct StepKey {
+        int64_t mine, global; double lr, reg; int cost;
+        bool operator==(const StepKey& o) const { return mine == o.mine && global == o.global && lr == o.lr && reg == o.reg && cost == o.cost; }
+    };
+    struct StepGraph {
+        StepKey key{}; int seen = 0; long long launches = 0;
+#ifndef DLB_CUDA_EMU
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+#endif
+    };
+    std::vector<StepGraph> step_graphs;
+    const void* ws_stamp = nullptr;   // the context scratch the captured graphs point into
+    bool graphs_enabled = true;
+    void drop_graphs() {
+#ifndef DLB_CUDA_EMU
+        for (auto& g : step_graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
+#endif
+        step_graphs.clear();
+    }
 
     int L() const { return (int)layers.size(); }
     int64_t in0() const { return layers.front().in_n; }
@@ -286,6 +331,35 @@ struct NetT final : dlb_net {
             segs.end[segs.count] = Y.param_off + Y.bias_n + Y.weight_n; segs.regularised[segs.count++] = 1;  // weights / filters
         }
         if (segs.count == 0) { segs.count = 1; segs.end[0] = 0; segs.regularised[0] = 0; }
+        d_cursor = dev_alloc<int>(1);
+        DLB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(int), ctx->stream));
+        build_plan();
+    }
+
+    // Which nets take the fused path:  [CLayer + PLayer(max|min) covered by plan_conv_pool]  NLayer*  NLayer(head)
+    // with element-wise activations on all but the head, a head of at most 32 outputs whose weights fit in shared
+    // memory, and at least two layers of parameters after the optional conv stage's position 0.
+    void build_plan() {
+        plan = TrainPlan{};
+        int idx = 0;
+        if (layers[0].s.type == DLB_LAYER_CONVOLUTION) {
+            if (L() < 3) return;
+            plan.cp = plan_conv_pool(layers[0].s, layers[1].s, sizeof(R));
+            if (!plan.cp.ok) return;
+            plan.has_cp = true;
+            idx = 2;
+        }
+        plan.first_fc = idx;
+        if (L() - idx < 2 - (plan.has_cp ? 1 : 0)) { if (!(plan.has_cp && L() - idx >= 1)) return; }
+        for (int l = idx; l < L(); ++l) {
+            if (layers[(size_t)l].s.type != DLB_LAYER_FULL) return;
+            if (l < L() - 1 && layers[(size_t)l].s.activation == DLB_ACT_SOFTMAX) return;
+        }
+        if (L() - 1 == 0) return;   // a single NLayer: the head would have to read the gathered data set
+        const auto& H = layers.back();
+        if (H.out_n > 32 || (size_t)H.out_n * (size_t)H.in_n * sizeof(R) > 96 * 1024) return;
+        plan.head_nmax = H.out_n <= 16 ? 16 : 32;
+        plan.ok = true;
     }
 
     ~NetT() override {
@@ -293,6 +367,8 @@ struct NetT final : dlb_net {
         cudaStreamSynchronize(ctx->stream);
         free_workspace();
         dev_free(params); dev_free(grads); dev_free(cost_dev); dev_free(perm_dev);
+        drop_graphs();
+        dev_free(cp_partial); dev_free(head_partial); dev_free(d_cursor);
         if (own_data) { dev_free(data_x); dev_free(data_y); }
 #ifndef DLB_CUDA_EMU
         if (comm) NcclApi::get().CommDestroy(comm);
@@ -314,6 +390,7 @@ struct NetT final : dlb_net {
             DLB_REQUIRE(B * std::max(Y.in_n, Y.out_n) < (1LL << 31), "batch * layer size exceeds the 32-bit index range");
         if (B <= cap) return;
         DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        drop_graphs();
         free_workspace();
         const size_t b = (size_t)B;
         int64_t max_out = 1;
@@ -331,6 +408,22 @@ struct NetT final : dlb_net {
         stage_y = dev_alloc<R>(b * (size_t)outN());
         gather_dev = dev_alloc<int>(b);
         cap = (int)B;
+        if (plan.ok) {
+            if (plan.has_cp && !cp_partial) {
+                cp_grid = kNumSMs;
+                cp_partial = dev_alloc<R>((size_t)cp_grid * (size_t)plan.cp.n_par);
+                // window positions the pooling never covers are never written and must read as zero
+                DLB_CUDA(cudaMemsetAsync(cp_partial, 0, (size_t)cp_grid * (size_t)plan.cp.n_par * sizeof(R), ctx->stream));
+            }
+            const int need = (int)ceil_div<int64_t>(B, kHeadChunk);
+            if (need > head_chunk_cap) {
+                drop_graphs();
+                dev_free(head_partial);
+                const auto& H = layers.back();
+                head_partial = dev_alloc<R>((size_t)need * (size_t)H.out_n * (size_t)(H.in_n + 1));
+                head_chunk_cap = need;
+            }
+        }
         // Split-partial scratch: enough for ~2 waves of partial tiles of the largest gradient, at least 64 MiB.
         size_t need = 64u << 20;
         for (const auto& Y : layers) need = std::max(need, (size_t)(Y.weight_n + Y.bias_n) * sizeof(R) * 8);
@@ -426,6 +519,130 @@ struct NetT final : dlb_net {
         last_B = B;
     }
 
+    // ---- train mode ---------------------------------------------------------------------------------------------
+    // One fused forward + backward over `B` samples.  x / refs are the bases the (optional) gather indexes into;
+    // `cursor` (device, nullable) is added to gather_base on the device, so that the launch sequence is identical
+    // for every batch of an epoch (CUDA-graph friendly).
+    void train_forward_backward(int B, const R* x, const R* refs, const int* gather_base, const int* cursor, int cost) {
+        const LaunchCtx lc = ctx->lc();
+        cudaStream_t st = ctx->stream;
+        const int Ln = L();
+        int l = 0;
+        if (plan.has_cp) {
+            g_tag_layer = 0;
+            const auto& Y = layers[0];
+            const int grid = std::min(B, 2 * kNumSMs);
+            conv_pool_forward<R>(st, plan.cp, grid, x, gather_base, cursor, params + Y.param_off, params + Y.param_off + Y.bias_n,
+                                 out[1], imap[1], B);
+            l = 2;
+        }
+        // hidden NLayers
+        for (; l < Ln - 1; ++l) {
+            const auto& Y = layers[(size_t)l];
+            g_tag_layer = l;
+            TagScope tag_("full_fwd");
+            const R* bias = params + Y.param_off;
+            if (l == 0)
+                gemm<R>(st, B, (int)Y.out_n, (int)Y.in_n, DenseRowCursorLoader<R>{x, (size_t)Y.in_n, gather_base, cursor},
+                        DenseRowLoader<R>{bias + Y.bias_n, (size_t)Y.in_n, nullptr},
+                        EpiFullForward<R>{out[(size_t)l], nullptr, bias, (int)Y.out_n, Y.s.activation}, lc.ws);
+            else
+                gemm<R>(st, B, (int)Y.out_n, (int)Y.in_n, DenseRowLoader<R>{out[(size_t)l - 1], (size_t)Y.in_n, nullptr},
+                        DenseRowLoader<R>{bias + Y.bias_n, (size_t)Y.in_n, nullptr},
+                        EpiFullForward<R>{out[(size_t)l], nullptr, bias, (int)Y.out_n, Y.s.activation}, lc.ws);
+        }
+        // head: forward + cost derivative + activation gradient + input gradient (already times the previous NLayer's derivative)
+        {
+            const int h = Ln - 1;
+            const auto& Y = layers[(size_t)h];
+            g_tag_layer = h;
+            const auto& Pv = layers[(size_t)h - 1];
+            const int prev_act = Pv.s.type == DLB_LAYER_FULL ? Pv.s.activation : 0;
+            const R* bias = params + Y.param_off;
+            const size_t smem = (size_t)Y.out_n * (size_t)Y.in_n * sizeof(R);
+            const int grid = std::min((int)ceil_div(B, 8), 4 * kNumSMs);
+            {
+                TagScope tag_("head");
+                if (plan.head_nmax == 16)
+                    DLB_LAUNCH_SMEM((full_head_kernel<R, 16>), dim3((unsigned)grid), dim3(256), smem, st, (const R*)out[(size_t)h - 1], bias,
+                                    bias + Y.bias_n, refs, gather_base, cursor, out[(size_t)h], in_grad[(size_t)Ln], in_grad[(size_t)h], B,
+                                    (int)Y.in_n, (int)Y.out_n, Y.s.activation, cost, prev_act);
+                else
+                    DLB_LAUNCH_SMEM((full_head_kernel<R, 32>), dim3((unsigned)grid), dim3(256), smem, st, (const R*)out[(size_t)h - 1], bias,
+                                    bias + Y.bias_n, refs, gather_base, cursor, out[(size_t)h], in_grad[(size_t)Ln], in_grad[(size_t)h], B,
+                                    (int)Y.in_n, (int)Y.out_n, Y.s.activation, cost, prev_act);
+            }
+            {
+                TagScope tag_("head_dW");
+                head_chunks = (int)ceil_div(B, kHeadChunk);
+                const int total = (int)Y.out_n * (int)(Y.in_n + 1);
+                DLB_LAUNCH((batch_outer_partial_kernel<R>), dim3((unsigned)ceil_div(total, 128), (unsigned)head_chunks), dim3(128), st,
+                           (const R*)in_grad[(size_t)Ln], (const R*)out[(size_t)h - 1], head_partial, B, (int)Y.out_n, (int)Y.in_n, kHeadChunk);
+            }
+        }
+        // hidden NLayers backward: in_grad[l + 1] holds g_l = dC/dz_l
+        for (l = Ln - 2; l >= plan.first_fc; --l) {
+            const auto& Y = layers[(size_t)l];
+            g_tag_layer = l;
+            const R* gl = in_grad[(size_t)l + 1];
+            R* db = grads + Y.param_off;
+            {
+                TagScope tag_("full_dW");
+                if (l == 0)
+                    gemm<R>(st, (int)Y.out_n, (int)Y.in_n + 1, B, DenseColLoader<R>{gl, (size_t)Y.out_n, nullptr},
+                            DenseColOnesLoader<R>{x, (size_t)Y.in_n, gather_base, cursor}, EpiWeightAndBias<R>{db, db + Y.bias_n, (int)Y.in_n}, lc.ws);
+                else
+                    gemm<R>(st, (int)Y.out_n, (int)Y.in_n + 1, B, DenseColLoader<R>{gl, (size_t)Y.out_n, nullptr},
+                            DenseColOnesLoader<R>{out[(size_t)l - 1], (size_t)Y.in_n, nullptr, nullptr},
+                            EpiWeightAndBias<R>{db, db + Y.bias_n, (int)Y.in_n}, lc.ws);
+            }
+            if (l > 0) {
+                TagScope tag_("full_dX");
+                const auto& Pv = layers[(size_t)l - 1];
+                const int prev_act = Pv.s.type == DLB_LAYER_FULL ? Pv.s.activation : 0;
+                gemm<R>(st, B, (int)Y.in_n, (int)Y.out_n, DenseRowLoader<R>{gl, (size_t)Y.out_n, nullptr},
+                        DenseColLoader<R>{params + Y.param_off + Y.bias_n, (size_t)Y.in_n, nullptr},
+                        EpiStoreTimesDeriv<R>{in_grad[(size_t)l], (size_t)Y.in_n, out[(size_t)l - 1], prev_act}, lc.ws);
+            }
+        }
+        if (plan.has_cp) {
+            g_tag_layer = 0;
+            const int grid = std::min(B, cp_grid);
+            if (grid < cp_grid)   // CTAs that do not run this time must not leave stale partial sums behind
+                DLB_CUDA(cudaMemsetAsync(cp_partial + (size_t)grid * plan.cp.n_par, 0, (size_t)(cp_grid - grid) * plan.cp.n_par * sizeof(R), st));
+            conv_pool_backward<R>(st, plan.cp, grid, x, gather_base, cursor, (const R*)in_grad[2], (const int*)imap[1], (const R*)out[1], cp_partial, B);
+        }
+        last_B = B;
+    }
+
+    // Sums the partial gradients into the flat gradient buffer and (optionally) updates the parameters in the same pass.
+    void train_reduce_update(bool do_update, double lr, double reg_factor, int64_t batch_items, int advance) {
+        ReduceSegments rs{};
+        rs.count = 0;
+        for (int l = 0; l < L(); ++l) {
+            const auto& Y = layers[(size_t)l];
+            if (Y.bias_n + Y.weight_n == 0) continue;
+            const bool conv_stage = plan.has_cp && l == 0;
+            const bool head = l == L() - 1;
+            for (int part = 0; part < 2; ++part) {
+                const int i = rs.count++;
+                rs.end[i] = Y.param_off + Y.bias_n + (part ? Y.weight_n : 0);
+                rs.regularised[i] = part ? 1 : 0;
+                rs.partial[i] = nullptr; rs.chunks[i] = 0; rs.stride[i] = 0; rs.local_off[i] = part ? Y.bias_n : 0;
+                if (conv_stage) { rs.partial[i] = cp_partial; rs.chunks[i] = cp_grid; rs.stride[i] = plan.cp.n_par; }
+                else if (head) { rs.partial[i] = head_partial; rs.chunks[i] = head_chunks; rs.stride[i] = Y.out_n * (Y.in_n + 1); }
+            }
+        }
+        const R l_rate = -static_cast<R>(lr);
+        const R reg = static_cast<R>(reg_factor);
+        const R grad_norm = static_cast<R>(1) / static_cast<R>(batch_items);
+        g_tag_layer = -1;
+        TagScope tag_("reduce_update");
+        DLB_LAUNCH((reduce_update_kernel<R>), dim3((unsigned)ceil_div<size_t>((size_t)n_params, 256)), dim3(256), ctx->stream, params, grads,
+                   (size_t)n_params, rs, do_update ? 1 : 0, static_cast<R>(1) + reg * l_rate, l_rate * grad_norm,
+                   reg > static_cast<R>(0) ? 1 : 0, advance ? d_cursor : (int*)nullptr, advance);
+    }
+
     void allreduce_gradient() {
 #ifndef DLB_CUDA_EMU
         if (world <= 1) return;
@@ -436,7 +653,11 @@ struct NetT final : dlb_net {
     }
 
     // ALayer<D>::update for every layer (Net.inl:309-316): l_rate = -lr, grad_scale_factor = 1 / B_actual.
-    void update(double lr, double reg_factor, int64_t batch_items) {
+    void update(double lr, double reg_factor, int64_t batch_items, int advance = 0) {
+        if (advance) {   // keep the device-side cursor in step (the unfused path reads its gather slice from the host-computed pointer)
+            ReduceSegments none{}; none.count = 1; none.end[0] = 0;
+            DLB_LAUNCH((reduce_update_kernel<R>), dim3(1), dim3(32), ctx->stream, params, grads, (size_t)0, none, 0, R(0), R(0), 0, d_cursor, advance);
+        }
         const R l_rate = -static_cast<R>(lr);
         const R reg = static_cast<R>(reg_factor);
         const R grad_norm = static_cast<R>(1) / static_cast<R>(batch_items);
@@ -447,21 +668,75 @@ struct NetT final : dlb_net {
     }
 
     // One step on this rank's share [first, first + mine) of a global batch of `global` items.
-    void step_device(const R* x, const R* refs, const int* gather, int64_t mine, int64_t global, double lr, int cost, double reg_factor) {
+    // gather_base + (*cursor if cursor) addresses this rank's slice; `advance` is added to the cursor at the end of the step.
+    void step_device(const R* x, const R* refs, const int* gather_base, const int* cursor, int advance, int64_t mine, int64_t global,
+                     double lr, int cost, double reg_factor) {
+        if (plan.ok && mine > 0) {
+            ensure_capacity(mine);
+            auto body = [&] {
+                train_forward_backward((int)mine, x, refs, gather_base, cursor, cost);
+                if (world <= 1) {
+                    train_reduce_update(true, lr, reg_factor, global, advance);
+                } else {
+                    train_reduce_update(false, lr, reg_factor, global, 0);
+                    allreduce_gradient();
+                    update(lr, reg_factor, global, advance);
+                }
+            };
+#ifndef DLB_CUDA_EMU
+            // Only the resident-data path (cursor-relative gather on fixed buffers) replays a graph; the first occurrence of a
+            // key runs eagerly (it also sets kernel attributes), the second is captured, later ones are one cudaGraphLaunch.
+            if (cursor && x == data_x && ws_stamp == ctx->ws.ptr && !g_timing_on && graphs_enabled) {
+                const StepKey key{mine, global, lr, reg_factor, cost};
+                StepGraph* sg = nullptr;
+                for (auto& g : step_graphs) if (g.key == key) { sg = &g; break; }
+                if (!sg) { if (step_graphs.size() >= 16) drop_graphs(); step_graphs.push_back(StepGraph{}); sg = &step_graphs.back(); sg->key = key; }
+                if (sg->exec) {
+                    DLB_CUDA(cudaGraphLaunch(sg->exec, ctx->stream));
+                    g_launch_count.fetch_add(sg->launches, std::memory_order_relaxed);
+                    last_B = (int)mine;
+                    return;
+                }
+                if (sg->seen++ >= 1) {
+                    const long long before = g_launch_count.load();
+                    DLB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                    try { body(); } catch (...) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(ctx->stream, &junk); if (junk) cudaGraphDestroy(junk); throw; }
+                    DLB_CUDA(cudaStreamEndCapture(ctx->stream, &sg->graph));
+                    sg->launches = g_launch_count.load() - before;
+                    g_launch_count.store(before);
+                    DLB_CUDA(cudaGraphInstantiate(&sg->exec, sg->graph, 0));
+                    DLB_CUDA(cudaGraphLaunch(sg->exec, ctx->stream));
+                    g_launch_count.fetch_add(sg->launches, std::memory_order_relaxed);
+                    return;
+                }
+            }
+            ws_stamp = ctx->ws.ptr;
+#endif
+            body();
+            return;
+        }
         if (mine > 0) {
             ensure_capacity(mine);
-            forward_backward((int)mine, x, refs, gather, cost, R(0));
+            forward_backward((int)mine, x, refs, gather_base, cost, R(0));
         } else {
             DLB_CUDA(cudaMemsetAsync(grads, 0, (size_t)n_params * sizeof(R), ctx->stream));
         }
         allreduce_gradient();
-        update(lr, reg_factor, global);
+        update(lr, reg_factor, global, advance);
     }
 
     void rank_slice(int64_t count, int64_t& first, int64_t& mine) const {
         const int64_t per = (count + world - 1) / world;
         first = std::min<int64_t>(count, (int64_t)rank * per);
         mine = std::min<int64_t>(count, first + per) - first;
+    }
+
+    // The mini-batch [start, end) of the current epoch permutation (perm_dev); d_cursor == start on the device.
+    void run_batch(int64_t start, int64_t end, double lr, int cost, double reg_factor) {
+        int64_t first, mine;
+        rank_slice(end - start, first, mine);
+        if (plan.ok) step_device(data_x, data_y, perm_dev + first, d_cursor, (int)(end - start), mine, end - start, lr, cost, reg_factor);
+        else step_device(data_x, data_y, perm_dev + start + first, nullptr, 0, mine, end - start, lr, cost, reg_factor);
     }
 
     void learn(int64_t batch, int64_t epochs, double lr, int cost, double lambda, dlb_epoch_callback cb, void* user) override {
@@ -479,13 +754,12 @@ struct NetT final : dlb_net {
             for (int64_t i = 0; i < n_items; ++i) perm32[(size_t)i] = (int)index_map[(size_t)i];
             DLB_CUDA(cudaStreamSynchronize(ctx->stream));   // previous epoch's kernels may still read perm_dev
             DLB_CUDA(cudaMemcpyAsync(perm_dev, perm32.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            DLB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(int), ctx->stream));
             int64_t start = 0;
             while (start < n_items) {
                 // Net.inl:235-236: fewer than 1.5 * batch_size remaining items are taken as one batch
                 const int64_t end = (double)(n_items - start) < 1.5 * (double)batch ? n_items : start + batch;
-                int64_t first, mine;
-                rank_slice(end - start, first, mine);
-                step_device(data_x, data_y, perm_dev + start + first, mine, end - start, lr, cost, (double)reg_factor);
+                run_batch(start, end, lr, cost, (double)reg_factor);
                 start = end;
             }
             if (cb) { DLB_CUDA(cudaStreamSynchronize(ctx->stream)); cb(e, 0.5 * (double)reg_factor, user); }   // Net.inl:319
@@ -512,14 +786,13 @@ struct NetT final : dlb_net {
                 for (int64_t i = 0; i < n_items; ++i) perm32[(size_t)i] = (int)ts_index_map[(size_t)i];
                 DLB_CUDA(cudaStreamSynchronize(ctx->stream));
                 DLB_CUDA(cudaMemcpyAsync(perm_dev, perm32.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                DLB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(int), ctx->stream));
                 DLB_CUDA(cudaStreamSynchronize(ctx->stream));
                 ts_cursor = 0;
             }
             const int64_t start = ts_cursor;
             const int64_t end = (double)(n_items - start) < 1.5 * (double)batch ? n_items : start + batch;
-            int64_t first, mine;
-            rank_slice(end - start, first, mine);
-            step_device(data_x, data_y, perm_dev + start + first, mine, end - start, lr, cost, (double)reg_factor);
+            run_batch(start, end, lr, cost, (double)reg_factor);
             consumed += end - start;
             ts_cursor = end;
         }
@@ -540,7 +813,7 @@ struct NetT final : dlb_net {
         DLB_CUDA(cudaStreamSynchronize(ctx->stream));
         DLB_CUDA(cudaMemcpyAsync(gather_dev, tmp.data(), (size_t)mine * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         DLB_CUDA(cudaStreamSynchronize(ctx->stream));   // tmp is pageable and goes out of scope
-        step_device(data_x, data_y, gather_dev, mine, n, lr, cost, reg_factor);
+        step_device(data_x, data_y, gather_dev, nullptr, 0, mine, n, lr, cost, reg_factor);
     }
 
     void stage_host_batch(const void* x, const void* y, int64_t n) {
@@ -553,12 +826,21 @@ struct NetT final : dlb_net {
         DLB_REQUIRE(x && y && n > 0, "Invalid input.");
         use_device(ctx);
         stage_host_batch(x, y, n);
-        forward_backward((int)n, stage_x, stage_y, nullptr, cost, R(0));
-        if (cost_out)
+        if (plan.ok) train_forward_backward((int)n, stage_x, stage_y, nullptr, nullptr, cost);
+        else forward_backward((int)n, stage_x, stage_y, nullptr, cost, R(0));
+        if (cost_out) {
+            g_tag_layer = L();
+            TagScope tag_("cost_sum");
             DLB_LAUNCH((cost_sum_kernel<R>), dim3(1), dim3(256), ctx->stream, (const R*)out[(size_t)L() - 1], (const R*)stage_y,
                        (const int*)nullptr, (int)n, (int)outN(), cost, cost_dev);
-        allreduce_gradient();
-        update(lr, reg_factor, n * world);
+        }
+        if (plan.ok && world <= 1) {
+            train_reduce_update(true, lr, reg_factor, n, 0);
+        } else {
+            if (plan.ok) train_reduce_update(false, lr, reg_factor, n, 0);
+            allreduce_gradient();
+            update(lr, reg_factor, n * world);
+        }
         if (cost_out) {
             DLB_CUDA(cudaMemcpyAsync(cost_out, cost_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             DLB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -598,6 +880,17 @@ struct NetT final : dlb_net {
         DLB_CUDA(cudaMemcpyAsync(grads, src, (size_t)n_params * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
         DLB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+
+    std::string describe_plan() override {
+        if (!plan.ok) return "unfused: every layer runs the generic operators (layers.cuh)";
+        std::string d = "fused:";
+        if (plan.has_cp)
+            d += " conv_pool(" + std::to_string(plan.cp.KH) + "x" + std::to_string(plan.cp.KW) + ", fpt " + std::to_string(plan.cp.fpt) +
+                 ", wpl " + std::to_string(plan.cp.wpl) + ")";
+        d += " + " + std::to_string(L() - 1 - plan.first_fc) + " hidden NLayer(s) + head(nmax " + std::to_string(plan.head_nmax) + ")";
+        return d;
+    }
+    void enable_graphs(bool on) override { graphs_enabled = on; if (!on) drop_graphs(); }
 
     void eval_host(const void* x, int64_t n, int32_t* classes, void* outputs) override {
         DLB_REQUIRE(x && n >= 0, "Invalid input.");
@@ -826,6 +1119,11 @@ int dlb_net_write_gradient(dlb_net* net, const void* src) { return guarded([&] {
 int dlb_net_eval_host(dlb_net* net, const void* x, int64_t n, int32_t* classes, void* outputs) {
     return guarded([&] { DLB_REQUIRE(net, "null net"); net->eval_host(x, n, classes, outputs); });
 }
+
+int dlb_net_describe_plan(dlb_net* net, char* buf, int64_t cap) {
+    return guarded([&] { DLB_REQUIRE(net && buf && cap > 0, "null argument"); std::snprintf(buf, (size_t)cap, "%s", net->describe_plan().c_str()); });
+}
+int dlb_net_enable_graphs(dlb_net* net, int on) { return guarded([&] { DLB_REQUIRE(net, "null net"); net->enable_graphs(on != 0); }); }
 
 int dlb_net_train_steps(dlb_net* net, int64_t batch, int64_t n_steps, double lr, int cost, double lambda, int64_t* items_out) {
     return guarded([&] {

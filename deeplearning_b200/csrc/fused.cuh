@@ -1,0 +1,499 @@
+// fused.cuh — the training step's fast path ("train mode"): kernels that fuse what the reference runs as separate
+// per-sample tensor operations, for nets of the shape  [CLayer -> PLayer(max|min)]  NLayer*  NLayer(head).
+//
+//   conv_pool_forward_kernel    CLayer::act + PLayer::act in one pass: convolution, untied bias, activation, window
+//                               max/min and its index map; the un-pooled activations never leave the SM
+//                               (CLayer.inl:108-137, PLayer.inl:115-138, Tensor.cpp:673-716).
+//   conv_pool_backward_kernel   PLayer::backpropagate + CLayer::backpropagate for a first layer: routes every pooled
+//                               gradient to its arg-max position, multiplies by the activation derivative (recomputed
+//                               from the pooled value), accumulates the untied bias gradient and the filter gradient
+//                               over the CTA's samples in registers (PLayer.inl:140-168, CLayer.inl:139-197,
+//                               Tensor.cpp:466-498, 721-734).  Zero gradients are skipped exactly like the reference.
+//   full_head_kernel            last NLayer forward + softmax/activation + cost derivative + activation gradient +
+//                               the input gradient (W^T g), optionally already multiplied by the previous layer's
+//                               activation derivative (NLayer.inl:131-171, CostFunction.inl:47-51).
+//   batch_outer_partial_kernel  weight + bias gradient of a narrow NLayer as per-chunk partial sums.
+//   reduce_update_kernel        sums the per-CTA / per-chunk partial gradients in a fixed order into the flat gradient
+//                               buffer and applies the SGD update in the same pass (ALayer.inl:97-122) — the weight
+//                               update fused into the gradient reduction.
+//
+// The trace mode (dlb_net_forward_backward_host + dlb_net_read, the op-level C ABI) keeps using the unfused operators
+// of layers.cuh, which materialise every Trace buffer of the reference.
+#pragma once
+
+#include "layers.cuh"
+
+namespace dlb {
+
+// Activation derivative recomputed from the activation VALUE; the same expressions the forward pass stores as
+// "Derivatives" (ActivationFunctionHelper.cpp:64-114), so the result is bit-identical to the stored trace.
+template <class R>
+__device__ __forceinline__ R deriv_from_value(int act, R v) {
+    switch (act) {
+    case DLB_ACT_SIGMOID: return v * (R(1) - v);
+    case DLB_ACT_TANH: return R(1) - v * v;
+    case DLB_ACT_RELU: return v > R(0) ? R(1) : R(0);
+    default: return R(1);
+    }
+}
+
+struct ConvPoolGeom {
+    int C, H, W, F, OH, OW, ph, pw, POH, POW, Hp, Wp, K, NPOS;
+};
+
+__device__ __forceinline__ const int* resolve_gather(const int* gather_base, const int* cursor) {
+    return gather_base ? gather_base + (cursor ? *cursor : 0) : nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Convolution (stride 1) + untied bias + activation + PH x PW max/min pooling.
+// One CTA walks over samples; a thread owns one pooled position and FPT filters: it keeps the (KH+PH-1)x(KW+PW-1)
+// input patch in registers and reads the filter taps as shared-memory broadcasts.
+// smem: filters [F][K] | bias [F][OH][OW] | zero-padded input [C][Hp][Wp]
+// ---------------------------------------------------------------------------------------------------------------
+template <class R, int KH, int KW, int PH, int PW, int FPT>
+__global__ void conv_pool_forward_kernel(const R* __restrict__ x, const int* __restrict__ gather_base, const int* __restrict__ cursor,
+                                         const R* __restrict__ bias, const R* __restrict__ filt, R* __restrict__ pooled,
+                                         int* __restrict__ map, int B, ConvPoolGeom g, int act, int is_max) {
+    DLB_DYNAMIC_SMEM(R, smem);
+    R* filt_s = smem;
+    R* bias_s = filt_s + g.F * g.K;
+    R* x_s = bias_s + g.F * g.OH * g.OW;
+    const int* gather = resolve_gather(gather_base, cursor);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < g.F * g.K; i += nt) filt_s[i] = filt[i];
+    for (int i = tid; i < g.F * g.OH * g.OW; i += nt) bias_s[i] = bias[i];
+    for (int i = tid; i < g.C * g.Hp * g.Wp; i += nt) x_s[i] = R(0);   // the border stays zero (padding)
+    __syncthreads();
+
+    const int fs = tid / g.NPOS, pos = tid - fs * g.NPOS;
+    const bool active = fs * FPT < g.F;
+    const int py = pos / g.POW, px = pos - py * g.POW;
+    const int HW = g.H * g.W;
+    constexpr int PR = KH + PH - 1, PC = KW + PW - 1;
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const R* xs = x + (size_t)(gather ? gather[b] : b) * g.C * HW;
+        for (int i = tid; i < g.C * HW; i += nt) {
+            const int c = i / HW, r = i - c * HW;
+            const int yy = r / g.W, xx = r - yy * g.W;
+            x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xs[i];
+        }
+        __syncthreads();
+        if (active) {
+            R acc[FPT][PH * PW];
+#pragma unroll
+            for (int fi = 0; fi < FPT; ++fi)
+#pragma unroll
+                for (int q = 0; q < PH * PW; ++q) acc[fi][q] = R(0);
+            for (int c = 0; c < g.C; ++c) {
+                R p[PR][PC];
+#pragma unroll
+                for (int r = 0; r < PR; ++r)
+#pragma unroll
+                    for (int s = 0; s < PC; ++s) p[r][s] = x_s[(c * g.Hp + py * PH + r) * g.Wp + px * PW + s];
+#pragma unroll
+                for (int fi = 0; fi < FPT; ++fi) {
+                    const int f = fs * FPT + fi;
+                    const R* w = filt_s + (f < g.F ? f : 0) * g.K + c * (KH * KW);
+#pragma unroll
+                    for (int ky = 0; ky < KH; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < KW; ++kx) {
+                            const R wv = w[ky * KW + kx];
+#pragma unroll
+                            for (int dy = 0; dy < PH; ++dy)
+#pragma unroll
+                                for (int dx = 0; dx < PW; ++dx) acc[fi][dy * PW + dx] += p[dy + ky][dx + kx] * wv;
+                        }
+                }
+            }
+#pragma unroll
+            for (int fi = 0; fi < FPT; ++fi) {
+                const int f = fs * FPT + fi;
+                if (f >= g.F) continue;
+                R best = is_max ? -real_limits<R>::max() : real_limits<R>::max();
+                int best_id = -1;
+#pragma unroll
+                for (int dy = 0; dy < PH; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < PW; ++dx) {
+                        const int id = (f * g.OH + py * PH + dy) * g.OW + px * PW + dx;
+                        R d;
+                        const R v = apply_activation<R>(act, acc[fi][dy * PW + dx] + bias_s[id], d);
+                        if (is_max ? (best < v) : (best > v)) { best = v; best_id = id; }
+                    }
+                const size_t o = ((size_t)b * g.F + f) * g.NPOS + pos;
+                pooled[o] = best;
+                map[o] = best_id;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the fused first stage.  One warp per filter; the lanes split the filter's pooled windows.  Per lane:
+// the K = C*KH*KW filter-gradient accumulators and the PH*PW bias-gradient accumulators of each of its windows, all in
+// registers across the CTA's samples.  partial layout per CTA = the layer's flat parameter layout [bias | filters].
+// ---------------------------------------------------------------------------------------------------------------
+template <class R, int C, int KH, int KW, int PH, int PW, int WPL>
+__global__ void conv_pool_backward_kernel(const R* __restrict__ x, const int* __restrict__ gather_base, const int* __restrict__ cursor,
+                                          const R* __restrict__ dpool, const int* __restrict__ map, const R* __restrict__ pooled,
+                                          R* __restrict__ partial, int B, ConvPoolGeom g, int act, int n_par) {
+    DLB_DYNAMIC_SMEM(R, x_s);
+    const int* gather = resolve_gather(gather_base, cursor);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int f = tid / 32, lane = tid % 32;
+    const int HW = g.H * g.W;
+    constexpr int K = C * KH * KW;
+    for (int i = tid; i < C * g.Hp * g.Wp; i += nt) x_s[i] = R(0);
+    __syncthreads();
+
+    R dk[K];
+    R db[WPL][PH * PW];
+#pragma unroll
+    for (int k = 0; k < K; ++k) dk[k] = R(0);
+#pragma unroll
+    for (int wi = 0; wi < WPL; ++wi)
+#pragma unroll
+        for (int q = 0; q < PH * PW; ++q) db[wi][q] = R(0);
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const R* xs = x + (size_t)(gather ? gather[b] : b) * C * HW;
+        for (int i = tid; i < C * HW; i += nt) {
+            const int c = i / HW, r = i - c * HW;
+            const int yy = r / g.W, xx = r - yy * g.W;
+            x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xs[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int wi = 0; wi < WPL; ++wi) {
+            const int win = lane + 32 * wi;
+            if (win >= g.NPOS) continue;
+            const size_t o = ((size_t)b * g.F + f) * g.NPOS + win;
+            const int m = map[o];
+            if (m < 0) continue;
+            const R gval = deriv_from_value<R>(act, pooled[o]) * dpool[o];
+            const int rem = m - f * g.OH * g.OW;
+            const int oy = rem / g.OW, ox = rem - oy * g.OW;
+            const int py = win / g.POW, px = win - py * g.POW;
+            const int sel = (oy - py * PH) * PW + (ox - px * PW);
+#pragma unroll
+            for (int q = 0; q < PH * PW; ++q) db[wi][q] += (q == sel) ? gval : R(0);
+            if (gval != R(0)) {   // the reference skips zero factors as well (Tensor.cpp:484-486)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int ky = 0; ky < KH; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < KW; ++kx)
+                            dk[(c * KH + ky) * KW + kx] += x_s[(c * g.Hp + oy + ky) * g.Wp + ox + kx] * gval;
+            }
+        }
+        __syncthreads();
+    }
+
+    R* pb = partial + (size_t)blockIdx.x * n_par;
+#pragma unroll
+    for (int wi = 0; wi < WPL; ++wi) {
+        const int win = lane + 32 * wi;
+        if (win >= g.NPOS) continue;
+        const int py = win / g.POW, px = win - py * g.POW;
+#pragma unroll
+        for (int dy = 0; dy < PH; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < PW; ++dx) pb[(f * g.OH + py * PH + dy) * g.OW + px * PW + dx] = db[wi][dy * PW + dx];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const R v = warp_sum<R>(dk[k]);
+        if (lane == 0) pb[g.F * g.OH * g.OW + f * K + k] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The head: last NLayer (n <= NMAX outputs) forward, activation (incl. whole-vector softmax), cost derivative,
+// activation gradient g = dC/dz, and the input gradient dx = W^T g (optionally times the previous layer's activation
+// derivative recomputed from x, which IS that layer's output).  One warp per sample; W lives in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+template <class R, int NMAX>
+__global__ void full_head_kernel(const R* __restrict__ x, const R* __restrict__ bias, const R* __restrict__ W, const R* __restrict__ ref,
+                                 const int* __restrict__ gather_base, const int* __restrict__ cursor, R* __restrict__ out,
+                                 R* __restrict__ g_out, R* __restrict__ dx, int B, int in_n, int n, int act, int cost_id, int prev_act) {
+    DLB_DYNAMIC_SMEM(R, W_s);
+    const int* gather = resolve_gather(gather_base, cursor);
+    for (int i = threadIdx.x; i < n * in_n; i += blockDim.x) W_s[i] = W[i];
+    __syncthreads();
+    const int lane = threadIdx.x % 32, wpb = blockDim.x / 32;
+    for (int b = blockIdx.x * wpb + threadIdx.x / 32; b < B; b += gridDim.x * wpb) {
+        const R* xb = x + (size_t)b * in_n;
+        R z[NMAX];
+#pragma unroll
+        for (int nn = 0; nn < NMAX; ++nn) z[nn] = R(0);
+        for (int k = lane; k < in_n; k += 32) {
+            const R xv = xb[k];
+#pragma unroll
+            for (int nn = 0; nn < NMAX; ++nn)
+                if (nn < n) z[nn] += W_s[nn * in_n + k] * xv;
+        }
+#pragma unroll
+        for (int nn = 0; nn < NMAX; ++nn)
+            if (nn < n) z[nn] = warp_sum<R>(z[nn]) + bias[nn];
+
+        // activation: y in z[], auxiliary (derivative or softmax exponent) in aux[]
+        R aux[NMAX];
+        R soft_sum = R(0);
+        if (act == DLB_ACT_SOFTMAX) {
+            R m = z[0];
+#pragma unroll
+            for (int nn = 1; nn < NMAX; ++nn)
+                if (nn < n && m < z[nn]) m = z[nn];
+#pragma unroll
+            for (int nn = 0; nn < NMAX; ++nn)
+                if (nn < n) { aux[nn] = dl_exp<R>(z[nn] - m); soft_sum += aux[nn]; }
+            const R factor = R(1) / soft_sum;
+#pragma unroll
+            for (int nn = 0; nn < NMAX; ++nn)
+                if (nn < n) z[nn] = aux[nn] * factor;
+        } else {
+#pragma unroll
+            for (int nn = 0; nn < NMAX; ++nn)
+                if (nn < n) { R d; z[nn] = apply_activation<R>(act, z[nn], d); aux[nn] = d; }
+        }
+        const size_t row = gather ? (size_t)gather[b] : (size_t)b;
+        R gg[NMAX];
+#pragma unroll
+        for (int nn = 0; nn < NMAX; ++nn) gg[nn] = nn < n ? cost_derivative<R>(cost_id, z[nn], ref[row * n + nn]) : R(0);
+        if (act == DLB_ACT_SOFTMAX) {   // ActivationFunctionHelper.cpp:50-58
+            const R ood = R(1) / soft_sum;
+            R t = R(0);
+#pragma unroll
+            for (int nn = 0; nn < NMAX; ++nn)
+                if (nn < n) { gg[nn] = aux[nn] * gg[nn] * ood; t += gg[nn]; }
+            const R temp_sum = t * ood;
+#pragma unroll
+            for (int nn = 0; nn < NMAX; ++nn)
+                if (nn < n) gg[nn] = gg[nn] - aux[nn] * temp_sum;
+        } else {
+#pragma unroll
+            for (int nn = 0; nn < NMAX; ++nn)
+                if (nn < n) gg[nn] = aux[nn] * gg[nn];
+        }
+#pragma unroll
+        for (int nn = 0; nn < NMAX; ++nn)
+            if (nn < n && lane == (nn % 32)) {
+                g_out[(size_t)b * n + nn] = gg[nn];
+                if (out) out[(size_t)b * n + nn] = z[nn];
+            }
+        if (dx) {
+            for (int k = lane; k < in_n; k += 32) {
+                R s = R(0);
+#pragma unroll
+                for (int nn = 0; nn < NMAX; ++nn)
+                    if (nn < n) s = W_s[nn * in_n + k] * gg[nn] + s;
+                if (prev_act) s = deriv_from_value<R>(prev_act, xb[k]) * s;
+                dx[(size_t)b * in_n + k] = s;
+            }
+        }
+    }
+}
+
+// Weight and bias gradient of a narrow layer: partial[chunk][bias n | W n*in_n] = sum over the chunk's samples.
+template <class R>
+__global__ void batch_outer_partial_kernel(const R* __restrict__ g, const R* __restrict__ x, R* __restrict__ partial,
+                                           int B, int n, int in_n, int chunk) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cols = in_n + 1;
+    if (e >= n * cols) return;
+    const int nn = e / cols, k = e - nn * cols;
+    const int b0 = blockIdx.y * chunk, b1 = min(B, b0 + chunk);
+    R acc = R(0);
+    for (int b = b0; b < b1; ++b) acc += g[(size_t)b * n + nn] * (k == in_n ? R(1) : x[(size_t)b * in_n + k]);
+    partial[(size_t)blockIdx.y * (n * cols) + (k == in_n ? nn : n + nn * in_n + k)] = acc;
+}
+
+// Hidden-NLayer gradient contraction with the bias folded in as a column of ones:
+//   i = output n, j = input k (j == in_n: the bias), red = sample b.
+template <class R>
+struct DenseColOnesLoader {  // value = j < ld ? base[row(red) * ld + j] : 1
+    static constexpr bool kRedFast = false;
+    const R* base; size_t ld; const int* gather_base; const int* cursor;
+    __device__ __forceinline__ R operator()(int o, int r) const {
+        if ((size_t)o >= ld) return R(1);
+        const int* gather = resolve_gather(gather_base, cursor);
+        const size_t row = gather ? (size_t)gather[r] : (size_t)r;
+        return base[row * ld + o];
+    }
+};
+
+template <class R>
+struct EpiWeightAndBias {  // dW[n][k] for k < in_n, db[n] for k == in_n; plain store (the batch sum overwrites, Net.inl:259)
+    R* db; R* dW; int in_n;
+    __device__ __forceinline__ void operator()(int n, int k, R acc) const {
+        if (k < in_n) dW[(size_t)n * in_n + k] = acc;
+        else db[n] = acc;
+    }
+};
+
+template <class R>
+struct EpiStoreTimesDeriv {  // input gradient times the previous layer's activation derivative (from its output values)
+    R* out; size_t ld; const R* prev_y; int prev_act;
+    __device__ __forceinline__ void operator()(int i, int j, R acc) const {
+        const size_t o = (size_t)i * ld + j;
+        out[o] = prev_act ? deriv_from_value<R>(prev_act, prev_y[o]) * acc : acc;
+    }
+};
+
+template <class R>
+struct DenseRowCursorLoader {  // DenseRowLoader whose gather slice is addressed through the device-side cursor
+    static constexpr bool kRedFast = true;
+    const R* base; size_t ld; const int* gather_base; const int* cursor;
+    __device__ __forceinline__ R operator()(int o, int r) const {
+        const int* gather = resolve_gather(gather_base, cursor);
+        const size_t row = gather ? (size_t)gather[o] : (size_t)o;
+        return base[row * ld + r];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Partial-sum reduction fused with the SGD update.
+// ---------------------------------------------------------------------------------------------------------------
+struct ReduceSegments {
+    int count;
+    long long end[kMaxSegments];           // exclusive end offset in the flat parameter buffer
+    unsigned char regularised[kMaxSegments];
+    const void* partial[kMaxSegments];     // nullptr: the gradient is already final in the flat gradient buffer
+    int chunks[kMaxSegments];
+    long long stride[kMaxSegments];        // elements between consecutive chunks
+    long long local_off[kMaxSegments];     // offset of the segment's first element inside one chunk
+};
+
+template <class R>
+__global__ void reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads, size_t n, ReduceSegments segs, int do_update,
+                                     R param_scale, R grad_scale, int nontrivial_reg, int* __restrict__ cursor, int advance) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0 && cursor) *cursor += advance;   // every reader of the cursor ran earlier in the stream
+    if (e >= n) return;
+    int s = 0;
+    while (s < segs.count - 1 && (long long)e >= segs.end[s]) ++s;
+    R gsum;
+    if (segs.partial[s]) {
+        const long long begin = s == 0 ? 0 : segs.end[s - 1];
+        const R* part = static_cast<const R*>(segs.partial[s]) + segs.local_off[s] + ((long long)e - begin);
+        gsum = R(0);
+        for (int c = 0; c < segs.chunks[s]; ++c) gsum += part[(long long)c * segs.stride[s]];
+        grads[e] = gsum;
+    } else {
+        gsum = grads[e];
+    }
+    if (do_update) {
+        const bool reg = nontrivial_reg && segs.regularised[s];
+        const R xv = p[e];
+        p[e] = reg ? xv * param_scale + gsum * grad_scale : xv + gsum * grad_scale;
+    }
+}
+
+}  // namespace dlb
+
+// =================================================================================================================
+// Host-side dispatch of the fused first stage.
+// =================================================================================================================
+namespace dlb {
+
+struct ConvPoolPlan {
+    bool ok = false;
+    ConvPoolGeom g{};
+    int KH = 0, KW = 0, fpt = 1, wpl = 1, act = 0, is_max = 1;
+    int fwd_threads = 0, bwd_threads = 0;
+    size_t fwd_smem_elems = 0, bwd_smem_elems = 0;
+    int n_par = 0;
+};
+
+// Which CLayer + PLayer pairs the fused kernels cover: stride 1, 5x5 (1 channel) or 3x3 (1 or 3 channels) filters,
+// at most 32 filters, 2x2 max/min pooling, element-wise activation.  Everything else takes the unfused operators.
+inline ConvPoolPlan plan_conv_pool(const dlb_layer_spec& c, const dlb_layer_spec& p, size_t real_bytes) {
+    ConvPoolPlan pl;
+    if (c.type != DLB_LAYER_CONVOLUTION || p.type != DLB_LAYER_PULL) return pl;
+    if (c.stride_h != 1 || c.stride_w != 1 || c.activation == DLB_ACT_SOFTMAX) return pl;
+    if (p.pool_type != DLB_POOL_MAX && p.pool_type != DLB_POOL_MIN) return pl;
+    if (p.win_h != 2 || p.win_w != 2) return pl;
+    const bool k55 = c.win_h == 5 && c.win_w == 5 && c.in_c == 1;
+    const bool k33 = c.win_h == 3 && c.win_w == 3 && (c.in_c == 1 || c.in_c == 3);
+    if (!k55 && !k33) return pl;
+    if (c.out_c > 32) return pl;
+    ConvPoolGeom& g = pl.g;
+    g.C = c.in_c; g.H = c.in_h; g.W = c.in_w; g.F = c.out_c; g.ph = c.pad_h; g.pw = c.pad_w;
+    g.OH = conv_out_size(g.H, c.win_h, g.ph, 1); g.OW = conv_out_size(g.W, c.win_w, g.pw, 1);
+    g.POH = conv_out_size(g.OH, 2, 0, 2); g.POW = conv_out_size(g.OW, 2, 0, 2);
+    g.Hp = g.H + 2 * g.ph; g.Wp = g.W + 2 * g.pw; g.K = g.C * c.win_h * c.win_w; g.NPOS = g.POH * g.POW;
+    if (g.POH < 1 || g.POW < 1 || g.NPOS > 256) return pl;
+    pl.KH = c.win_h; pl.KW = c.win_w; pl.act = c.activation; pl.is_max = p.pool_type == DLB_POOL_MAX;
+    for (int fpt : {8, 5, 4, 2, 1})
+        if (g.F % fpt == 0 && (long)g.NPOS * (g.F / fpt) <= 1024) { pl.fpt = fpt; break; }
+    if ((long)g.NPOS * ceil_div(g.F, pl.fpt) > 1024) return pl;
+    pl.fwd_threads = ceil_div(g.NPOS * ceil_div(g.F, pl.fpt), 32) * 32;
+    pl.bwd_threads = 32 * g.F;
+    const int need_wpl = ceil_div(g.NPOS, 32);
+    pl.wpl = need_wpl <= 1 ? 1 : need_wpl <= 2 ? 2 : need_wpl <= 5 ? 5 : 8;
+    pl.fwd_smem_elems = (size_t)g.F * g.K + (size_t)g.F * g.OH * g.OW + (size_t)g.C * g.Hp * g.Wp;
+    pl.bwd_smem_elems = (size_t)g.C * g.Hp * g.Wp;
+    if (pl.fwd_smem_elems * real_bytes > 200 * 1024) return pl;
+    pl.n_par = g.F * g.OH * g.OW + g.F * g.K;
+    pl.ok = true;
+    return pl;
+}
+
+template <class R, int KH, int KW>
+void conv_pool_forward_fpt(cudaStream_t st, const ConvPoolPlan& pl, int grid, const R* x, const int* gather_base, const int* cursor,
+                           const R* bias, const R* filt, R* pooled, int* map, int B) {
+    const size_t smem = pl.fwd_smem_elems * sizeof(R);
+    const dim3 gd((unsigned)grid), bd((unsigned)pl.fwd_threads);
+#define DLB_CPF(FPT)                                                                                                           \
+    DLB_LAUNCH_SMEM((conv_pool_forward_kernel<R, KH, KW, 2, 2, FPT>), gd, bd, smem, st, x, gather_base, cursor, bias, filt, pooled, \
+                    map, B, pl.g, pl.act, pl.is_max)
+    switch (pl.fpt) {
+    case 8: DLB_CPF(8); break;
+    case 5: DLB_CPF(5); break;
+    case 4: DLB_CPF(4); break;
+    case 2: DLB_CPF(2); break;
+    default: DLB_CPF(1); break;
+    }
+#undef DLB_CPF
+}
+
+template <class R>
+void conv_pool_forward(cudaStream_t st, const ConvPoolPlan& pl, int grid, const R* x, const int* gather_base, const int* cursor,
+                       const R* bias, const R* filt, R* pooled, int* map, int B) {
+    TagScope tag_("conv_pool_fwd");
+    if (pl.KH == 5) conv_pool_forward_fpt<R, 5, 5>(st, pl, grid, x, gather_base, cursor, bias, filt, pooled, map, B);
+    else conv_pool_forward_fpt<R, 3, 3>(st, pl, grid, x, gather_base, cursor, bias, filt, pooled, map, B);
+}
+
+template <class R, int C, int KH, int KW>
+void conv_pool_backward_wpl(cudaStream_t st, const ConvPoolPlan& pl, int grid, const R* x, const int* gather_base, const int* cursor,
+                            const R* dpool, const int* map, const R* pooled, R* partial, int B) {
+    const size_t smem = pl.bwd_smem_elems * sizeof(R);
+    const dim3 gd((unsigned)grid), bd((unsigned)pl.bwd_threads);
+#define DLB_CPB(WPL)                                                                                                            \
+    DLB_LAUNCH_SMEM((conv_pool_backward_kernel<R, C, KH, KW, 2, 2, WPL>), gd, bd, smem, st, x, gather_base, cursor, dpool, map,  \
+                    pooled, partial, B, pl.g, pl.act, pl.n_par)
+    switch (pl.wpl) {
+    case 1: DLB_CPB(1); break;
+    case 2: DLB_CPB(2); break;
+    case 5: DLB_CPB(5); break;
+    default: DLB_CPB(8); break;
+    }
+#undef DLB_CPB
+}
+
+template <class R>
+void conv_pool_backward(cudaStream_t st, const ConvPoolPlan& pl, int grid, const R* x, const int* gather_base, const int* cursor,
+                        const R* dpool, const int* map, const R* pooled, R* partial, int B) {
+    TagScope tag_("conv_pool_bwd");
+    if (pl.KH == 5) conv_pool_backward_wpl<R, 1, 5, 5>(st, pl, grid, x, gather_base, cursor, dpool, map, pooled, partial, B);
+    else if (pl.g.C == 1) conv_pool_backward_wpl<R, 1, 3, 3>(st, pl, grid, x, gather_base, cursor, dpool, map, pooled, partial, B);
+    else conv_pool_backward_wpl<R, 3, 3, 3>(st, pl, grid, x, gather_base, cursor, dpool, map, pooled, partial, B);
+}
+
+}  // namespace dlb

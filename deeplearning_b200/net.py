@@ -258,6 +258,14 @@ class Net:
     def layer_param_offset(self, l: int) -> int:
         return int(self.lib.dlb_net_layer_param_offset(self._handle(), l))
 
+    def describe_plan(self) -> str:
+        buf = C.create_string_buffer(512)
+        _capi.check(self.lib.dlb_net_describe_plan(self._handle(), buf, len(buf)))
+        return buf.value.decode()
+
+    def enable_graphs(self, on: bool) -> None:
+        _capi.check(self.lib.dlb_net_enable_graphs(self._handle(), 1 if on else 0))
+
     # ---- parameters (GpuDC::from_host / to_host) ----------------------------------------------------------------
     def set_params(self, flat) -> None:
         p = np.ascontiguousarray(flat, self.dtype).ravel()

@@ -138,6 +138,11 @@ DLB_API int dlb_net_learn(dlb_net* net, int64_t batch_size, int64_t epochs, doub
 DLB_API int dlb_net_train_steps(dlb_net* net, int64_t batch_size, int64_t n_steps, double learning_rate, int cost_id, double lambda,
                                 int64_t* items_out);
 
+/* Which execution plan learn / train_steps / step_* use for this net: "fused: ..." (fused.cuh) or "unfused: ...". */
+DLB_API int dlb_net_describe_plan(dlb_net* net, char* buf, int64_t cap);
+/* CUDA-graph replay of the step on the resident-data path (on by default); off = every step launches its kernels. */
+DLB_API int dlb_net_enable_graphs(dlb_net* net, int on);
+
 /* One mini-batch step on explicit item indices of the resident data set (host int64 indices, n of them). */
 DLB_API int dlb_net_step_indices(dlb_net* net, const int64_t* indices, int64_t n, double learning_rate, int cost_id, double reg_factor);
 

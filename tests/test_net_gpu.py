@@ -154,3 +154,39 @@ def test_argument_errors_are_loud():
         net.set_params(np.zeros(5, np.float32))
     with pytest.raises(dl.DlbError):
         net.learn(np.zeros((3, 4)), np.zeros((2, 3)), 1, 1, 0.1, dl.CostFunctionId.SQUARED_ERROR)
+
+
+def test_plans():
+    """LeNet and the MLP take the fused path; nets outside its grammar take the generic operators."""
+    assert dl.lenet("f32").describe_plan().startswith("fused: conv_pool(5x5")
+    assert dl.Net([H.to_dl_spec(s) for s in MINI_MLP], real="f64").describe_plan().startswith("fused:")
+    assert dl.Net([H.to_dl_spec(s) for s in MINI_LENET], real="f32").describe_plan().startswith("fused: conv_pool(3x3")
+    assert dl.Net([H.to_dl_spec(s) for s in FIXTURE_NET], real="f32").describe_plan().startswith("unfused")
+    assert dl.Net([H.to_dl_spec(s) for s in AVG_NET], real="f32").describe_plan().startswith("unfused")
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_train_steps_equals_learn_and_graph_replay_is_exact(real):
+    """train_steps (resumable) walks the same epoch sequence as learn; replaying the captured CUDA graph of the step
+    gives bit-identical parameters to launching the kernels one by one."""
+    specs, cost = NETS["mini_lenet"]
+    x, y = None, None
+    results = []
+    for mode in ("learn", "steps", "steps_nograph"):
+        orc, gpu = H.make_pair(specs, real, seed=51)
+        if x is None:
+            x, y = H.synthetic_batch(orc, 64, real, seed=52, lo=0.0, hi=1.0)
+        gpu.reset_random_generator(9)
+        if mode == "learn":
+            gpu.learn(x, y, 8, 3, 0.05, dl.CostFunctionId(cost), 0.2)
+        else:
+            gpu.set_dataset(x, y)
+            gpu.enable_graphs(mode == "steps")
+            assert gpu.train_steps(8, 10, 0.05, dl.CostFunctionId(cost), 0.2) == 80
+            assert gpu.train_steps(8, 14, 0.05, dl.CostFunctionId(cost), 0.2) == 112
+        results.append(gpu.get_params())
+    assert np.array_equal(results[0], results[1]), "train_steps differs from learn"
+    assert np.array_equal(results[1], results[2]), "graph replay differs from eager launches"
+    perms = dl.shuffle_sequence(9, 64, 3)
+    orc.learn(x, y, 8, 3, 0.05, cost, 0.2, threads=1, perms=perms)
+    H.assert_close("parameters", results[0], orc.get_params(), real, rtol_mult=20)

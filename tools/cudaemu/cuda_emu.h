@@ -171,6 +171,18 @@ inline void run_block(void (*body)(void*), void* arg) {
     block() = nullptr;
 }
 
+inline std::vector<double>& dyn_smem_storage() { static std::vector<double> v; return v; }
+inline void* dyn_smem() { return dyn_smem_storage().data(); }
+
+template <class K, class... A>
+void launch(K kernel, dim3 grid, dim3 blk, A... args);
+
+template <class K, class... A>
+void launch_smem(K kernel, dim3 grid, dim3 blk, size_t smem, A... args) {
+    dyn_smem_storage().assign(smem / sizeof(double) + 2, 0.0);
+    launch(kernel, grid, blk, args...);
+}
+
 template <class K, class... A>
 void launch(K kernel, dim3 grid, dim3 blk, A... args) {
     grid_dim() = grid; block_dim() = blk;
