@@ -104,7 +104,7 @@ class ClockSampler:
 # algorithmic bytes per launch of each operator tag (DESIGN.md "Roofline accounting")
 # ------------------------------------------------------------------------------------------------------------------
 def algorithmic_bytes(net, key: str, batch: int, sz: int) -> float | None:
-    layer_s, tag, kernel = key.split(":")
+    layer_s, tag, kernel = key.split(":", 2)
     l = int(layer_s)
     L = net.layers_count()
     P = net.param_count
@@ -119,6 +119,18 @@ def algorithmic_bytes(net, key: str, batch: int, sz: int) -> float | None:
     spec = net._specs[l]
     bias_n = out_n if spec.type != 3 else 0
     weight_n = n_par - bias_n
+    if tag == "reduce_update":
+        return 3.0 * P * sz     # gradient in, parameter in, parameter out (partial sums are overhead of the split)
+    if tag == "conv_pool_fwd":   # fused CLayer + PLayer forward: input, pooled output, index map, parameters
+        o1 = net.layer_out_size(l + 1)
+        return batch * (in_n * sz + o1 * sz + o1 * 4) + n_par * sz
+    if tag == "conv_pool_bwd":   # pooled gradient, index map, pooled values, input; bias + filter gradient out
+        o1 = net.layer_out_size(l + 1)
+        return batch * (o1 * sz + o1 * 4 + o1 * sz + in_n * sz) + n_par * sz
+    if tag == "head":            # x, reference, g, dx
+        return batch * (in_n + 2 * out_n + in_n) * sz + n_par * sz
+    if tag == "head_dW":
+        return batch * (in_n + out_n) * sz + n_par * sz
     if kernel == "gemm_finalize_kernel":
         return None          # partial-sum traffic is overhead of the split, not algorithmic
     if tag in ("conv_fwd", "full_fwd"):

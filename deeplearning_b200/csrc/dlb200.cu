@@ -14,6 +14,7 @@
 #include <numeric>
 #include <random>
 #include <ranges>
+#include <type_traits>
 #include <vector>
 
 #ifndef DLB_CUDA_EMU
@@ -22,6 +23,7 @@
 
 #include "../../include/dlb200.h"
 #include "fused.cuh"
+#include "tc_gemm.cuh"
 
 namespace dlb {
 
@@ -48,6 +50,8 @@ void timing_begin(cudaStream_t stream, const char* kernel_text) {
     std::string k(kernel_text);
     const size_t lt = k.find('<');
     if (lt != std::string::npos) k = k.substr(0, lt);
+    const size_t ns = k.rfind("::");
+    if (ns != std::string::npos) k = k.substr(ns + 2);
     while (!k.empty() && (k.front() == '(' || k.front() == ' ')) k.erase(k.begin());
     while (!k.empty() && (k.back() == ')' || k.back() == ' ')) k.pop_back();
     t.key = std::to_string(g_tag_layer) + ":" + g_tag + ":" + k;
@@ -252,6 +256,7 @@ struct dlb_net {
     virtual void eval_host(const void* x, int64_t n, int32_t* classes, void* outputs) = 0;
     virtual std::string describe_plan() = 0;
     virtual void enable_graphs(bool on) = 0;
+    virtual void enable_tensor_cores(bool on) = 0;
 };
 
 namespace {
@@ -302,6 +307,7 @@ struct NetT final : dlb_net {
     std::vector<StepGraph> step_graphs;
     const void* ws_stamp = nullptr;   // the context scratch the captured graphs point into
     bool graphs_enabled = true;
+    bool use_tensor_cores = true;     // fp32 NLayer contractions on tcgen05 (3xTF32); off = FMA path (gemm.cuh)
     void drop_graphs() {
 #ifndef DLB_CUDA_EMU
         for (auto& g : step_graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
@@ -542,6 +548,16 @@ struct NetT final : dlb_net {
             g_tag_layer = l;
             TagScope tag_("full_fwd");
             const R* bias = params + Y.param_off;
+#ifndef DLB_CUDA_EMU
+            if constexpr (std::is_same_v<R, float>) {
+                if (use_tensor_cores) {   // y = act(X W^T + b): both operands reduction-contiguous
+                    const TcOperand A{l == 0 ? x : out[(size_t)l - 1], (long long)Y.in_n, 0, l == 0 ? gather_base : nullptr, l == 0 ? cursor : nullptr, -1};
+                    const TcOperand Bo{bias + Y.bias_n, (long long)Y.in_n, 0, nullptr, nullptr, -1};
+                    tc_gemm(st, B, (int)Y.out_n, (int)Y.in_n, A, Bo, EpiFullForward<float>{out[(size_t)l], nullptr, bias, (int)Y.out_n, Y.s.activation}, lc.ws);
+                    continue;
+                }
+            }
+#endif
             if (l == 0)
                 gemm<R>(st, B, (int)Y.out_n, (int)Y.in_n, DenseRowCursorLoader<R>{x, (size_t)Y.in_n, gather_base, cursor},
                         DenseRowLoader<R>{bias + Y.bias_n, (size_t)Y.in_n, nullptr},
@@ -586,6 +602,31 @@ struct NetT final : dlb_net {
             g_tag_layer = l;
             const R* gl = in_grad[(size_t)l + 1];
             R* db = grads + Y.param_off;
+            bool done_tc = false;
+#ifndef DLB_CUDA_EMU
+            if constexpr (std::is_same_v<R, float>) {
+                if (use_tensor_cores) {
+                    {   // dW[n][k] = sum_b g[b][n] x[b][k], db[n] = sum_b g[b][n] (column of ones): both operands outer-contiguous
+                        TagScope tag_("full_dW");
+                        const TcOperand A{gl, (long long)Y.out_n, 1, nullptr, nullptr, -1};
+                        const TcOperand Bo{l == 0 ? x : out[(size_t)l - 1], (long long)Y.in_n, 1, l == 0 ? gather_base : nullptr,
+                                           l == 0 ? cursor : nullptr, (int)Y.in_n};
+                        tc_gemm(st, (int)Y.out_n, (int)Y.in_n + 1, B, A, Bo, EpiWeightAndBias<float>{db, db + Y.bias_n, (int)Y.in_n}, lc.ws);
+                    }
+                    if (l > 0) {   // dx[b][k] = sum_n g[b][n] W[n][k]: A reduction-contiguous, B (= W) outer-contiguous
+                        TagScope tag_("full_dX");
+                        const auto& Pv = layers[(size_t)l - 1];
+                        const int prev_act = Pv.s.type == DLB_LAYER_FULL ? Pv.s.activation : 0;
+                        const TcOperand A{gl, (long long)Y.out_n, 0, nullptr, nullptr, -1};
+                        const TcOperand Bo{params + Y.param_off + Y.bias_n, (long long)Y.in_n, 1, nullptr, nullptr, -1};
+                        tc_gemm(st, B, (int)Y.in_n, (int)Y.out_n, A, Bo,
+                                EpiStoreTimesDeriv<float>{in_grad[(size_t)l], (size_t)Y.in_n, out[(size_t)l - 1], prev_act}, lc.ws);
+                    }
+                    done_tc = true;
+                }
+            }
+#endif
+            if (done_tc) continue;
             {
                 TagScope tag_("full_dW");
                 if (l == 0)
@@ -891,6 +932,7 @@ struct NetT final : dlb_net {
         return d;
     }
     void enable_graphs(bool on) override { graphs_enabled = on; if (!on) drop_graphs(); }
+    void enable_tensor_cores(bool on) override { use_tensor_cores = on; drop_graphs(); }
 
     void eval_host(const void* x, int64_t n, int32_t* classes, void* outputs) override {
         DLB_REQUIRE(x && n >= 0, "Invalid input.");
@@ -1123,6 +1165,33 @@ int dlb_net_eval_host(dlb_net* net, const void* x, int64_t n, int32_t* classes, 
 int dlb_net_describe_plan(dlb_net* net, char* buf, int64_t cap) {
     return guarded([&] { DLB_REQUIRE(net && buf && cap > 0, "null argument"); std::snprintf(buf, (size_t)cap, "%s", net->describe_plan().c_str()); });
 }
+int dlb_net_enable_tensor_cores(dlb_net* net, int on) { return guarded([&] { DLB_REQUIRE(net, "null net"); net->enable_tensor_cores(on != 0); }); }
+
+// C[M][N] = sum_k A(m, k) * B(n, k) in fp32.  a_transposed / b_transposed: the operand is stored [K][M] / [K][N]
+// (leading dimension lda / ldb) instead of [M][K] / [N][K].  use_tensor_cores: tcgen05 3xTF32 (tc_gemm.cuh) or FMA.
+int dlb_matmul_f32(dlb_context* ctx, int M, int N, int K, const float* A, int64_t lda, int a_transposed, const float* B, int64_t ldb,
+                   int b_transposed, float* C, int use_tensor_cores) {
+    return guarded([&] {
+        DLB_REQUIRE(ctx && A && B && C && M > 0 && N > 0 && K > 0, "Incompatible matrix-vector dimensionality");
+        use_device(ctx); ensure_op_ws(ctx);
+        TagScope tag_("matmul");
+        if (use_tensor_cores) {
+#ifdef DLB_CUDA_EMU
+            throw std::runtime_error("tensor cores are not available");
+#else
+            tc_gemm(ctx->stream, M, N, K, TcOperand{A, lda, a_transposed ? 1 : 0, nullptr, nullptr, -1},
+                    TcOperand{B, ldb, b_transposed ? 1 : 0, nullptr, nullptr, -1}, EpiStore<float>{C, (size_t)N}, ctx->ws);
+#endif
+        } else {
+            auto run = [&](auto al, auto bl) { gemm<float>(ctx->stream, M, N, K, al, bl, EpiStore<float>{C, (size_t)N}, ctx->ws); };
+            if (!a_transposed && !b_transposed) run(DenseRowLoader<float>{A, (size_t)lda, nullptr}, DenseRowLoader<float>{B, (size_t)ldb, nullptr});
+            else if (!a_transposed && b_transposed) run(DenseRowLoader<float>{A, (size_t)lda, nullptr}, DenseColLoader<float>{B, (size_t)ldb, nullptr});
+            else if (a_transposed && !b_transposed) run(DenseColLoader<float>{A, (size_t)lda, nullptr}, DenseRowLoader<float>{B, (size_t)ldb, nullptr});
+            else run(DenseColLoader<float>{A, (size_t)lda, nullptr}, DenseColLoader<float>{B, (size_t)ldb, nullptr});
+        }
+    });
+}
+
 int dlb_net_enable_graphs(dlb_net* net, int on) { return guarded([&] { DLB_REQUIRE(net, "null net"); net->enable_graphs(on != 0); }); }
 
 int dlb_net_train_steps(dlb_net* net, int64_t batch, int64_t n_steps, double lr, int cost, double lambda, int64_t* items_out) {

@@ -137,8 +137,8 @@ __global__ void conv_pool_forward_kernel(const R* __restrict__ x, const int* __r
 // the K = C*KH*KW filter-gradient accumulators and the PH*PW bias-gradient accumulators of each of its windows, all in
 // registers across the CTA's samples.  partial layout per CTA = the layer's flat parameter layout [bias | filters].
 // ---------------------------------------------------------------------------------------------------------------
-template <class R, int C, int KH, int KW, int PH, int PW, int WPL>
-__global__ void conv_pool_backward_kernel(const R* __restrict__ x, const int* __restrict__ gather_base, const int* __restrict__ cursor,
+template <class R, int C, int KH, int KW, int PH, int PW, int WPL, int FMAX>
+__global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_kernel(const R* __restrict__ x, const int* __restrict__ gather_base, const int* __restrict__ cursor,
                                           const R* __restrict__ dpool, const int* __restrict__ map, const R* __restrict__ pooled,
                                           R* __restrict__ partial, int B, ConvPoolGeom g, int act, int n_par) {
     DLB_DYNAMIC_SMEM(R, x_s);
@@ -475,9 +475,16 @@ void conv_pool_backward_wpl(cudaStream_t st, const ConvPoolPlan& pl, int grid, c
                             const R* dpool, const int* map, const R* pooled, R* partial, int B) {
     const size_t smem = pl.bwd_smem_elems * sizeof(R);
     const dim3 gd((unsigned)grid), bd((unsigned)pl.bwd_threads);
-#define DLB_CPB(WPL)                                                                                                            \
-    DLB_LAUNCH_SMEM((conv_pool_backward_kernel<R, C, KH, KW, 2, 2, WPL>), gd, bd, smem, st, x, gather_base, cursor, dpool, map,  \
-                    pooled, partial, B, pl.g, pl.act, pl.n_par)
+    // FMAX bounds the block size (one warp per filter) so that ptxas knows the register budget per thread.
+#define DLB_CPB2(WPL, FMAX)                                                                                                     \
+    DLB_LAUNCH_SMEM((conv_pool_backward_kernel<R, C, KH, KW, 2, 2, WPL, FMAX>), gd, bd, smem, st, x, gather_base, cursor, dpool, \
+                    map, pooled, partial, B, pl.g, pl.act, pl.n_par)
+#define DLB_CPB(WPL)                                          \
+    do {                                                      \
+        if (pl.g.F <= 8) DLB_CPB2(WPL, 8);                    \
+        else if (pl.g.F <= 20) DLB_CPB2(WPL, 20);             \
+        else DLB_CPB2(WPL, 32);                               \
+    } while (0)
     switch (pl.wpl) {
     case 1: DLB_CPB(1); break;
     case 2: DLB_CPB(2); break;
@@ -485,6 +492,7 @@ void conv_pool_backward_wpl(cudaStream_t st, const ConvPoolPlan& pl, int grid, c
     default: DLB_CPB(8); break;
     }
 #undef DLB_CPB
+#undef DLB_CPB2
 }
 
 template <class R>

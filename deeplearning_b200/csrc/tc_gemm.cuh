@@ -1,0 +1,296 @@
+// tc_gemm.cuh — fp32 contraction  C[i][j] = sum_r A(i, r) * B(j, r)  on the 5th-generation tensor cores (tcgen05 / UMMA,
+// sm_100a) at fp32 accuracy: every fp32 operand is split into a TF32 "hi" part and an fp32 remainder "lo"
+// (x = hi + lo exactly), and three kind::tf32 MMAs per k-step (lo*hi, hi*lo, hi*hi) accumulate into the same fp32
+// accumulator in tensor memory (the classic 3xTF32 scheme; the dropped lo*lo term is O(2^-22) relative).  This is how
+// "tensor cores in the reference's Real precision" is met for Real = float: plain TF32 (10-bit mantissa) cannot hold
+// the 1e-5 parity bar over K = 2880, and tcgen05 has no IEEE fp32 operand kind.  Real = double stays on the FMA path
+// (gemm.cuh): tcgen05 has no fp64 kind.
+//
+// Structure of one CTA (one 128 x BN output tile, one split of the reduction):
+//   warps 0-3  producers: global -> registers (coalesced along the operand's contiguous index, optional row gather,
+//              optional implicit column of ones) -> hi/lo split -> shared memory in the canonical K-major SWIZZLE_128B
+//              UMMA layout (row = 32 fp32 = 128 B; 16-byte chunk c of row r stored at chunk c ^ (r & 7)); the same warps
+//              run the epilogue at the end (tcgen05.ld of their 32 TMEM lanes -> epilogue functor -> global)
+//   warp 4     lane 0 issues the MMAs (tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = BN, K = 8 per instruction),
+//              tcgen05.commit releases the shared-memory stage / signals the epilogue; the warp owns the TMEM allocation
+//   mbarrier ring of kStages stages: full[s] (128 producer arrivals) / empty[s] (1 tcgen05.commit arrival).
+// Operands that are not K-contiguous in memory (W^T, G^T, X^T of the backward contractions) are transposed on the fly by
+// the producers, so all three NLayer contractions (NLayer.inl:131-171) use the same K-major MMA.
+#pragma once
+
+#include "gemm.cuh"
+
+namespace dlb {
+
+// How an operand tile is fetched: value(outer, red) =
+//   kRedContig   : base[row(outer) * ld + red]      (gather applies to outer)
+//   kOuterContig : base[row(red)   * ld + outer]    (gather applies to red); outer == ones_col yields 1
+struct TcOperand {
+    const float* base;
+    long long ld;
+    int outer_contig;          // 0: kRedContig, 1: kOuterContig
+    const int* gather_base;    // optional row gather (device int32), addressed through *cursor when cursor != nullptr
+    const int* cursor;
+    int ones_col;              // outer index that reads as 1 (bias folded into the contraction); -1: none
+};
+
+#ifndef DLB_CUDA_EMU
+
+namespace tc {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32, kStages = 3;
+constexpr int kTileBytes = kBM * kBK * 4;                  // 16 KiB: one hi or lo tile of either operand
+constexpr int kStageBytes = 4 * kTileBytes;                // A_hi, A_lo, B_hi, B_lo
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 160;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol error becomes a trap (launch failure) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (long long spin = 0; !ok; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1LL << 26)) __trap();
+    }
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start address
+// >> 4 in bits [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B >> 4 in [32,46) (distance between
+// 8-row groups), descriptor version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 @ bit 4), A = B = TF32 (2 @ bits 7 and 10), both
+// operands K-major (bits 15, 16 = 0), N >> 3 @ bit 17, M >> 4 @ bit 24.
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, unsigned char* lo_tile, int row, int chunk) {
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+    const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
+    *reinterpret_cast<float4*>(hi_tile + off) = h;
+    *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+// Fills one 128 x 32 operand tile (rows = outer index o0.., columns = reduction index r0..) as hi and lo tiles.
+__device__ __forceinline__ void produce_tile(const TcOperand& op, int o0, int o_end, int r0, int r_end,
+                                             unsigned char* hi_tile, unsigned char* lo_tile, int t) {
+    const int* gather = op.gather_base ? op.gather_base + (op.cursor ? *op.cursor : 0) : nullptr;
+    if (!op.outer_contig) {
+        // 8 threads per row read one 16-byte chunk each: 4 rows x 128 B per warp-wide load
+        const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int q = t + 128 * i;
+            const int row = q >> 3, c = q & 7;
+            const int o = o0 + row, r = r0 + 4 * c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o < o_end && r < r_end) {
+                const long long grow = gather ? (long long)gather[o] : (long long)o;
+                const float* p = op.base + grow * op.ld + r;
+                if (vec && r + 3 < r_end) {
+                    v = *reinterpret_cast<const float4*>(p);
+                } else {
+                    v.x = p[0];
+                    if (r + 1 < r_end) v.y = p[1];
+                    if (r + 2 < r_end) v.z = p[2];
+                    if (r + 3 < r_end) v.w = p[3];
+                }
+            }
+            split_store(v, hi_tile, lo_tile, row, c);
+        }
+    } else {
+        // thread t owns tile row t (outer index o0 + t): 32 coalesced scalar loads (consecutive threads, consecutive o)
+        const int o = o0 + t;
+        const bool valid_o = o < o_end;
+        const bool ones = valid_o && o == op.ones_col;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + 4 * c + j;
+                float x = 0.f;
+                if (valid_o && r < r_end) {
+                    if (ones) x = 1.f;
+                    else {
+                        const long long grow = gather ? (long long)gather[r] : (long long)r;
+                        x = op.base[grow * op.ld + o];
+                    }
+                }
+                e[j] = x;
+            }
+            split_store(make_float4(e[0], e[1], e[2], e[3]), hi_tile, lo_tile, t, c);
+        }
+    }
+}
+
+template <class EP>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(int M, int N, int K, int k_per_split, TcOperand a, TcOperand b, EP ep, float* __restrict__ partials) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);   // full[kStages], empty[kStages], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int i0 = blockIdx.y * kBM, j0 = blockIdx.x * kBN;
+    const int kb = blockIdx.z * k_per_split;
+    const int ke = min(K, kb + k_per_split);
+    const int n_kblocks = (ke - kb + kBK - 1) / kBK;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bars[s]), 128); mbar_init(smem_u32(&bars[kStages + s]), 1); }
+        mbar_init(smem_u32(&bars[2 * kStages]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {   // the MMA warp owns the tensor-memory allocation: kBN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kBN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ---------------- producers ----------------
+        for (int it = 0; it < n_kblocks; ++it) {
+            const int s = it % kStages;
+            const uint32_t phase = (it / kStages) & 1;
+            mbar_wait(smem_u32(&bars[kStages + s]), phase ^ 1);     // stage free (first pass: returns at once)
+            unsigned char* st = smem + s * kStageBytes;
+            const int r0 = kb + it * kBK;
+            produce_tile(a, i0, M, r0, ke, st, st + kTileBytes, tid);
+            produce_tile(b, j0, N, r0, ke, st + 2 * kTileBytes, st + 3 * kTileBytes, tid);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (UMMA) reads
+            mbar_arrive(smem_u32(&bars[s]));
+        }
+        // ---------------- epilogue (same warps): TMEM lanes 32*warp .. 32*warp+31 ----------------
+        mbar_wait(smem_u32(&bars[2 * kStages]), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int gi = i0 + warp * 32 + lane;
+        const bool split = gridDim.z > 1;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kBN; c0 += 32) {
+            if (j0 + c0 >= N) break;                                  // warp-uniform
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (gi < M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int gj = j0 + c0 + j;
+                    if (gj >= N) break;
+                    const float acc = __uint_as_float(v[j]);
+                    if (split) partials[((size_t)blockIdx.z * M + gi) * N + gj] = acc;
+                    else ep(gi, gj, acc);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(kBM, kBN);
+            uint32_t accumulate = 0;
+            for (int it = 0; it < n_kblocks; ++it) {
+                const int s = it % kStages;
+                const uint32_t phase = (it / kStages) & 1;
+                mbar_wait(smem_u32(&bars[s]), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(smem + s * kStageBytes);
+                const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + kTileBytes);
+                const uint64_t b_hi = make_desc(st + 2 * kTileBytes), b_lo = make_desc(st + 3 * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 8; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // +32 bytes per k-step inside the 128-byte swizzle row
+                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, accumulate);
+                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                    accumulate = 1u;
+                }
+                umma_commit(smem_u32(&bars[kStages + s]));          // frees the stage when these MMAs have read it
+            }
+            umma_commit(smem_u32(&bars[2 * kStages]));              // accumulator complete -> epilogue
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kBN) : "memory");
+    }
+}
+
+}  // namespace tc
+
+// Host launcher.  Falls back to nothing: callers decide (by Real type and shape) whether to use this or gemm<R>.
+template <class EP>
+void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcOperand& b, EP ep, const GemmWorkspace& ws) {
+    if (M <= 0 || N <= 0) return;
+    const long tiles = (long)ceil_div(M, tc::kBM) * ceil_div(N, tc::kBN);
+    const int kblocks = ceil_div(K > 0 ? K : 1, tc::kBK);
+    int splits = 1;
+    if (tiles < kNumSMs && kblocks > 2) {
+        splits = (int)ceil_div<long>(kNumSMs, tiles);
+        if (splits > kblocks / 2) splits = kblocks / 2;              // at least two k-blocks per split
+        const size_t per_split = (size_t)M * N * sizeof(float);
+        const size_t max_by_ws = per_split ? ws.bytes / per_split : 0;
+        if ((size_t)splits > max_by_ws) splits = (int)max_by_ws;
+        if (splits < 1) splits = 1;
+    }
+    int k_per_split = ceil_div(kblocks, splits) * tc::kBK;
+    splits = ceil_div(K > 0 ? K : 1, k_per_split);
+    const dim3 grid(ceil_div(N, tc::kBN), ceil_div(M, tc::kBM), splits);
+    float* partials = static_cast<float*>(ws.ptr);
+    DLB_LAUNCH_SMEM((tc::tc_gemm_kernel<EP>), grid, dim3(tc::kThreads), (size_t)tc::kSmemBytes, st, M, N, K, k_per_split, a, b, ep, partials);
+    if (splits > 1) {
+        const size_t total = (size_t)M * N;
+        DLB_LAUNCH((gemm_finalize_kernel<float, EP>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), st,
+                   (const float*)partials, splits, M, N, ep);
+    }
+}
+
+#endif  // !DLB_CUDA_EMU
+
+}  // namespace dlb

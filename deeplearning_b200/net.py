@@ -263,6 +263,9 @@ class Net:
         _capi.check(self.lib.dlb_net_describe_plan(self._handle(), buf, len(buf)))
         return buf.value.decode()
 
+    def enable_tensor_cores(self, on: bool) -> None:
+        _capi.check(self.lib.dlb_net_enable_tensor_cores(self._handle(), 1 if on else 0))
+
     def enable_graphs(self, on: bool) -> None:
         _capi.check(self.lib.dlb_net_enable_graphs(self._handle(), 1 if on else 0))
 

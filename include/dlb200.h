@@ -143,6 +143,16 @@ DLB_API int dlb_net_describe_plan(dlb_net* net, char* buf, int64_t cap);
 /* CUDA-graph replay of the step on the resident-data path (on by default); off = every step launches its kernels. */
 DLB_API int dlb_net_enable_graphs(dlb_net* net, int on);
 
+/* fp32 NLayer contractions of the fused path on the tcgen05 tensor cores with 3xTF32 operand splitting (on by default
+ * for Real = float); off = the FMA path.  Real = double always uses the FMA path (tcgen05 has no fp64 kind). */
+DLB_API int dlb_net_enable_tensor_cores(dlb_net* net, int on);
+
+/* Dense fp32 contraction C[M][N] = sum_k A(m,k) * B(n,k) (replaces CudaMatrix::mul_add / transpose_mul /
+ * vector_col_times_vector_row style products, CudaMatrix.cu:227-498, for whole batches).  a_transposed / b_transposed:
+ * the operand is stored [K][M] / [K][N] with leading dimension lda / ldb.  use_tensor_cores selects tcgen05 (3xTF32). */
+DLB_API int dlb_matmul_f32(dlb_context* ctx, int M, int N, int K, const float* A, int64_t lda, int a_transposed, const float* B,
+                           int64_t ldb, int b_transposed, float* C, int use_tensor_cores);
+
 /* One mini-batch step on explicit item indices of the resident data set (host int64 indices, n of them). */
 DLB_API int dlb_net_step_indices(dlb_net* net, const int64_t* indices, int64_t n, double learning_rate, int cost_id, double reg_factor);
 
