@@ -365,11 +365,25 @@ def main():
         bps = step_bytes_per_sample(net, batch, sz)
         line["step_roofline"] = {"bytes_per_sample": bps, "roofline_samples_per_s": peak * 1e9 / bps, "frac": value / (peak * 1e9 / bps)}
 
-        # the data-parallel workload's per-GPU share on one GPU, for reading the scaling series
+        # the data-parallel workload's per-GPU share on one GPU, for reading the scaling series; with its own kernel table
         net.train_steps(8192, 3, LR, cost_id, LAMBDA)
         ctx.synchronize()
         e0.record(); it = net.train_steps(8192, 16, LR, cost_id, LAMBDA); e1.record()
-        line["config5_on_1_gpu"] = {"global_batch": 8192, "value": it / (e0.elapsed_ms(e1) / 1e3), "unit": "samples/s"}
+        big = {"global_batch": 8192, "value": it / (e0.elapsed_ms(e1) / 1e3), "unit": "samples/s"}
+        dl.timing_enable(True)
+        net.train_steps(8192, 8, LR, cost_id, LAMBDA)
+        rep = dl.timing_report()
+        dl.timing_enable(False)
+        tot = sum(v[1] for v in rep.values()) or 1.0
+        big["kernels"] = []
+        for k, (n, t) in sorted(rep.items(), key=lambda kv: -kv[1][1])[:10]:
+            ab = algorithmic_bytes(net, k, 8192, sz)
+            us = 1e3 * t / n
+            big["kernels"].append({"kernel": k, "us_per_launch": us, "share": t / tot, "gbs": (ab / (us * 1e-6) / 1e9) if ab else None,
+                                   "frac_of_hbm_peak": (ab / (us * 1e-6) / 1e9 / peak) if ab else None})
+        bps8 = step_bytes_per_sample(net, 8192, sz)
+        big["step_roofline_frac"] = big["value"] / (peak * 1e9 / bps8)
+        line["config5_on_1_gpu"] = big
 
         r = run_reference(args.real, 256, 64, 2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],

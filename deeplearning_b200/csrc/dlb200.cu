@@ -679,9 +679,13 @@ struct NetT final : dlb_net {
         const R grad_norm = static_cast<R>(1) / static_cast<R>(batch_items);
         g_tag_layer = -1;
         TagScope tag_("reduce_update");
-        DLB_LAUNCH((reduce_update_kernel<R>), dim3((unsigned)ceil_div<size_t>((size_t)n_params, 256)), dim3(256), ctx->stream, params, grads,
-                   (size_t)n_params, rs, do_update ? 1 : 0, static_cast<R>(1) + reg * l_rate, l_rate * grad_norm,
-                   reg > static_cast<R>(0) ? 1 : 0, advance ? d_cursor : (int*)nullptr, advance);
+        long long n_partial = 0;
+        for (int i = 0; i < rs.count; ++i)
+            if (rs.partial[i]) n_partial += rs.end[i] - (i == 0 ? 0 : rs.end[i - 1]);
+        const int partial_blocks = (int)ceil_div<long long>(n_partial, 16);
+        DLB_LAUNCH((reduce_update_kernel<R>), dim3((unsigned)(partial_blocks + ceil_div<size_t>((size_t)n_params, 256))), dim3(256), ctx->stream,
+                   params, grads, (size_t)n_params, rs, partial_blocks, n_partial, do_update ? 1 : 0, static_cast<R>(1) + reg * l_rate,
+                   l_rate * grad_norm, reg > static_cast<R>(0) ? 1 : 0, advance ? d_cursor : (int*)nullptr, advance);
     }
 
     void allreduce_gradient() {
@@ -697,7 +701,8 @@ struct NetT final : dlb_net {
     void update(double lr, double reg_factor, int64_t batch_items, int advance = 0) {
         if (advance) {   // keep the device-side cursor in step (the unfused path reads its gather slice from the host-computed pointer)
             ReduceSegments none{}; none.count = 1; none.end[0] = 0;
-            DLB_LAUNCH((reduce_update_kernel<R>), dim3(1), dim3(32), ctx->stream, params, grads, (size_t)0, none, 0, R(0), R(0), 0, d_cursor, advance);
+            DLB_LAUNCH((reduce_update_kernel<R>), dim3(1), dim3(256), ctx->stream, params, grads, (size_t)0, none, 0, (long long)0, 0, R(0), R(0), 0,
+                       d_cursor, advance);
         }
         const R l_rate = -static_cast<R>(lr);
         const R reg = static_cast<R>(reg_factor);

@@ -49,20 +49,18 @@ __device__ __forceinline__ const int* resolve_gather(const int* gather_base, con
 // Convolution (stride 1) + untied bias + activation + PH x PW max/min pooling.
 // One CTA walks over samples; a thread owns one pooled position and FPT filters: it keeps the (KH+PH-1)x(KW+PW-1)
 // input patch in registers and reads the filter taps as shared-memory broadcasts.
-// smem: filters [F][K] | bias [F][OH][OW] | zero-padded input [C][Hp][Wp]
+// smem: filters [F][K] | zero-padded input [C][Hp][Wp]; the untied bias is read through the read-only path
 // ---------------------------------------------------------------------------------------------------------------
-template <class R, int KH, int KW, int PH, int PW, int FPT>
-__global__ void conv_pool_forward_kernel(const R* __restrict__ x, const int* __restrict__ gather_base, const int* __restrict__ cursor,
+template <class R, int KH, int KW, int PH, int PW, int FPT, int TMAX>
+__global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __restrict__ x, const int* __restrict__ gather_base, const int* __restrict__ cursor,
                                          const R* __restrict__ bias, const R* __restrict__ filt, R* __restrict__ pooled,
                                          int* __restrict__ map, int B, ConvPoolGeom g, int act, int is_max) {
     DLB_DYNAMIC_SMEM(R, smem);
     R* filt_s = smem;
-    R* bias_s = filt_s + g.F * g.K;
-    R* x_s = bias_s + g.F * g.OH * g.OW;
+    R* x_s = filt_s + g.F * g.K;
     const int* gather = resolve_gather(gather_base, cursor);
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < g.F * g.K; i += nt) filt_s[i] = filt[i];
-    for (int i = tid; i < g.F * g.OH * g.OW; i += nt) bias_s[i] = bias[i];
     for (int i = tid; i < g.C * g.Hp * g.Wp; i += nt) x_s[i] = R(0);   // the border stays zero (padding)
     __syncthreads();
 
@@ -72,12 +70,39 @@ __global__ void conv_pool_forward_kernel(const R* __restrict__ x, const int* __r
     const int HW = g.H * g.W;
     constexpr int PR = KH + PH - 1, PC = KW + PW - 1;
 
+    // The next sample's input is fetched into registers (XPT values per thread) while the current one is computed.
+    constexpr int XPT = 4;
+    const int n_in = g.C * HW;
+    const bool prefetch = n_in <= XPT * nt;
+    R xr[XPT];
+    auto fetch = [&](int b) {
+        const R* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
+#pragma unroll
+        for (int j = 0; j < XPT; ++j) { const int i = tid + j * nt; xr[j] = i < n_in ? __ldg(xs + i) : R(0); }
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int j = 0; j < XPT; ++j) {
+            const int i = tid + j * nt;
+            if (i < n_in) {
+                const int c = i / HW, r = i - c * HW;
+                const int yy = r / g.W, xx = r - yy * g.W;
+                x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xr[j];
+            }
+        }
+    };
+    if (prefetch && (int)blockIdx.x < B) fetch(blockIdx.x);
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        const R* xs = x + (size_t)(gather ? gather[b] : b) * g.C * HW;
-        for (int i = tid; i < g.C * HW; i += nt) {
-            const int c = i / HW, r = i - c * HW;
-            const int yy = r / g.W, xx = r - yy * g.W;
-            x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xs[i];
+        if (prefetch) {
+            stage();
+            if (b + (int)gridDim.x < B) fetch(b + gridDim.x);
+        } else {
+            const R* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
+            for (int i = tid; i < n_in; i += nt) {
+                const int c = i / HW, r = i - c * HW;
+                const int yy = r / g.W, xx = r - yy * g.W;
+                x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xs[i];
+            }
         }
         __syncthreads();
         if (active) {
@@ -120,7 +145,7 @@ __global__ void conv_pool_forward_kernel(const R* __restrict__ x, const int* __r
                     for (int dx = 0; dx < PW; ++dx) {
                         const int id = (f * g.OH + py * PH + dy) * g.OW + px * PW + dx;
                         R d;
-                        const R v = apply_activation<R>(act, acc[fi][dy * PW + dx] + bias_s[id], d);
+                        const R v = apply_activation<R>(act, acc[fi][dy * PW + dx] + __ldg(bias + id), d);   // untied bias: L1/L2 resident
                         if (is_max ? (best < v) : (best > v)) { best = v; best_id = id; }
                     }
                 const size_t o = ((size_t)b * g.F + f) * g.NPOS + pos;
@@ -159,22 +184,60 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_kernel(const 
 #pragma unroll
         for (int q = 0; q < PH * PW; ++q) db[wi][q] = R(0);
 
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        const R* xs = x + (size_t)(gather ? gather[b] : b) * C * HW;
-        for (int i = tid; i < C * HW; i += nt) {
-            const int c = i / HW, r = i - c * HW;
-            const int yy = r / g.W, xx = r - yy * g.W;
-            x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xs[i];
+    // Per-sample operands are fetched one sample ahead into registers: the lane's WPL windows (index map, pooled value,
+    // pooled gradient) and the thread's share of the input image.
+    constexpr int XPT = 2;
+    const int n_in = C * HW;
+    const bool prefetch = n_in <= XPT * nt;
+    R xr[XPT];
+    int wm[WPL]; R wp[WPL], wd[WPL];
+    auto fetch = [&](int b) {
+        const R* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
+        if (prefetch) {
+#pragma unroll
+            for (int j = 0; j < XPT; ++j) { const int i = tid + j * nt; xr[j] = i < n_in ? __ldg(xs + i) : R(0); }
         }
+#pragma unroll
+        for (int wi = 0; wi < WPL; ++wi) {
+            const int win = lane + 32 * wi;
+            wm[wi] = -1; wp[wi] = R(0); wd[wi] = R(0);
+            if (win < g.NPOS) {
+                const size_t o = ((size_t)b * g.F + f) * g.NPOS + win;
+                wm[wi] = __ldg(map + o); wp[wi] = __ldg(pooled + o); wd[wi] = __ldg(dpool + o);
+            }
+        }
+    };
+    if ((int)blockIdx.x < B) fetch(blockIdx.x);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        if (prefetch) {
+#pragma unroll
+            for (int j = 0; j < XPT; ++j) {
+                const int i = tid + j * nt;
+                if (i < n_in) {
+                    const int c = i / HW, r = i - c * HW;
+                    const int yy = r / g.W, xx = r - yy * g.W;
+                    x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xr[j];
+                }
+            }
+        } else {
+            const R* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
+            for (int i = tid; i < n_in; i += nt) {
+                const int c = i / HW, r = i - c * HW;
+                const int yy = r / g.W, xx = r - yy * g.W;
+                x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xs[i];
+            }
+        }
+        int cm[WPL]; R cg[WPL];
+#pragma unroll
+        for (int wi = 0; wi < WPL; ++wi) { cm[wi] = wm[wi]; cg[wi] = deriv_from_value<R>(act, wp[wi]) * wd[wi]; }
+        if (b + (int)gridDim.x < B) fetch(b + gridDim.x);
         __syncthreads();
 #pragma unroll
         for (int wi = 0; wi < WPL; ++wi) {
             const int win = lane + 32 * wi;
-            if (win >= g.NPOS) continue;
-            const size_t o = ((size_t)b * g.F + f) * g.NPOS + win;
-            const int m = map[o];
-            if (m < 0) continue;
-            const R gval = deriv_from_value<R>(act, pooled[o]) * dpool[o];
+            const int m = cm[wi];
+            if (win >= g.NPOS || m < 0) continue;
+            const R gval = cg[wi];
             const int rem = m - f * g.OH * g.OW;
             const int oy = rem / g.OW, ox = rem - oy * g.OW;
             const int py = win / g.POW, px = win - py * g.POW;
@@ -369,22 +432,51 @@ struct ReduceSegments {
     long long local_off[kMaxSegments];     // offset of the segment's first element inside one chunk
 };
 
+// Blocks [0, partial_blocks) own the elements whose gradient arrives as per-CTA / per-chunk partial sums: 16 elements
+// per block, 16 threads per element, each thread adds every 16th partial (independent loads in flight), then one
+// thread adds the 16 sub-sums in a fixed order - deterministic, and ~chunks/16 dependent steps instead of `chunks`.
+// The remaining blocks own 256 elements each whose gradient is already final in `grads`.
 template <class R>
-__global__ void reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads, size_t n, ReduceSegments segs, int do_update,
-                                     R param_scale, R grad_scale, int nontrivial_reg, int* __restrict__ cursor, int advance) {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e == 0 && cursor) *cursor += advance;   // every reader of the cursor ran earlier in the stream
-    if (e >= n) return;
-    int s = 0;
-    while (s < segs.count - 1 && (long long)e >= segs.end[s]) ++s;
-    R gsum;
-    if (segs.partial[s]) {
-        const long long begin = s == 0 ? 0 : segs.end[s - 1];
-        const R* part = static_cast<const R*>(segs.partial[s]) + segs.local_off[s] + ((long long)e - begin);
+__global__ void reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads, size_t n, ReduceSegments segs, int partial_blocks,
+                                     long long n_partial_elems, int do_update, R param_scale, R grad_scale, int nontrivial_reg,
+                                     int* __restrict__ cursor, int advance) {
+    __shared__ R sub[16][17];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && cursor) *cursor += advance;   // every reader of the cursor ran earlier in the stream
+    long long e; R gsum; int s = 0; bool active;
+    if ((int)blockIdx.x < partial_blocks) {
+        // the partial elements are enumerated segment by segment in flat order
+        const int el = threadIdx.x & 15, part = threadIdx.x >> 4;
+        long long idx = (long long)blockIdx.x * 16 + el;
+        active = idx < n_partial_elems;
+        e = 0;
+        if (active) {
+            long long begin = 0;
+            for (s = 0; s < segs.count; ++s) {
+                begin = s == 0 ? 0 : segs.end[s - 1];
+                if (!segs.partial[s]) continue;
+                const long long len = segs.end[s] - begin;
+                if (idx < len) break;
+                idx -= len;
+            }
+            e = begin + idx;
+            const R* part_ptr = static_cast<const R*>(segs.partial[s]) + segs.local_off[s] + idx;
+            R a = R(0);
+            for (int c = part; c < segs.chunks[s]; c += 16) a += part_ptr[(long long)c * segs.stride[s]];
+            sub[el][part] = a;
+        } else {
+            sub[el][part] = R(0);
+        }
+        __syncthreads();
+        if (part != 0 || !active) return;
         gsum = R(0);
-        for (int c = 0; c < segs.chunks[s]; ++c) gsum += part[(long long)c * segs.stride[s]];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) gsum += sub[el][q];
         grads[e] = gsum;
     } else {
+        e = (long long)(blockIdx.x - partial_blocks) * blockDim.x + threadIdx.x;
+        if (e >= (long long)n) return;
+        while (s < segs.count - 1 && e >= segs.end[s]) ++s;
+        if (segs.partial[s]) return;     // owned by a partial block
         gsum = grads[e];
     }
     if (do_update) {
@@ -436,7 +528,7 @@ inline ConvPoolPlan plan_conv_pool(const dlb_layer_spec& c, const dlb_layer_spec
     pl.bwd_threads = 32 * g.F;
     const int need_wpl = ceil_div(g.NPOS, 32);
     pl.wpl = need_wpl <= 1 ? 1 : need_wpl <= 2 ? 2 : need_wpl <= 5 ? 5 : 8;
-    pl.fwd_smem_elems = (size_t)g.F * g.K + (size_t)g.F * g.OH * g.OW + (size_t)g.C * g.Hp * g.Wp;
+    pl.fwd_smem_elems = (size_t)g.F * g.K + (size_t)g.C * g.Hp * g.Wp;
     pl.bwd_smem_elems = (size_t)g.C * g.Hp * g.Wp;
     if (pl.fwd_smem_elems * real_bytes > 200 * 1024) return pl;
     pl.n_par = g.F * g.OH * g.OW + g.F * g.K;
@@ -449,9 +541,15 @@ void conv_pool_forward_fpt(cudaStream_t st, const ConvPoolPlan& pl, int grid, co
                            const R* bias, const R* filt, R* pooled, int* map, int B) {
     const size_t smem = pl.fwd_smem_elems * sizeof(R);
     const dim3 gd((unsigned)grid), bd((unsigned)pl.fwd_threads);
-#define DLB_CPF(FPT)                                                                                                           \
-    DLB_LAUNCH_SMEM((conv_pool_forward_kernel<R, KH, KW, 2, 2, FPT>), gd, bd, smem, st, x, gather_base, cursor, bias, filt, pooled, \
-                    map, B, pl.g, pl.act, pl.is_max)
+#define DLB_CPF2(FPT, TMAX)                                                                                                    \
+    DLB_LAUNCH_SMEM((conv_pool_forward_kernel<R, KH, KW, 2, 2, FPT, TMAX>), gd, bd, smem, st, x, gather_base, cursor, bias, filt,   \
+                    pooled, map, B, pl.g, pl.act, pl.is_max)
+#define DLB_CPF(FPT)                                          \
+    do {                                                      \
+        if (pl.fwd_threads <= 256) DLB_CPF2(FPT, 256);        \
+        else if (pl.fwd_threads <= 640) DLB_CPF2(FPT, 640);   \
+        else DLB_CPF2(FPT, 1024);                             \
+    } while (0)
     switch (pl.fpt) {
     case 8: DLB_CPF(8); break;
     case 5: DLB_CPF(5); break;
@@ -460,6 +558,7 @@ void conv_pool_forward_fpt(cudaStream_t st, const ConvPoolPlan& pl, int grid, co
     default: DLB_CPF(1); break;
     }
 #undef DLB_CPF
+#undef DLB_CPF2
 }
 
 template <class R>

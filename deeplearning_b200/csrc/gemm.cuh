@@ -91,9 +91,17 @@ __global__ void gemm_finalize_kernel(const R* __restrict__ partials, int splits,
     const size_t total = (size_t)M * N;
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
-    R s = R(0);
-    for (int z = 0; z < splits; ++z) s += partials[(size_t)z * total + e];
-    ep((int)(e / N), (int)(e % N), s);
+    // fixed association (four interleaved running sums, then a fixed combine): deterministic, four loads in flight
+    R s0 = R(0), s1 = R(0), s2 = R(0), s3 = R(0);
+    int z = 0;
+    for (; z + 3 < splits; z += 4) {
+        s0 += partials[(size_t)z * total + e];
+        s1 += partials[(size_t)(z + 1) * total + e];
+        s2 += partials[(size_t)(z + 2) * total + e];
+        s3 += partials[(size_t)(z + 3) * total + e];
+    }
+    for (; z < splits; ++z) s0 += partials[(size_t)z * total + e];
+    ep((int)(e / N), (int)(e % N), (s0 + s1) + (s2 + s3));
 }
 
 struct GemmWorkspace {

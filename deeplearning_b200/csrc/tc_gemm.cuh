@@ -102,12 +102,14 @@ __device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, un
     *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
 
-// Fills one 128 x 32 operand tile (rows = outer index o0.., columns = reduction index r0..) as hi and lo tiles.
-__device__ __forceinline__ void produce_tile(const TcOperand& op, int o0, int o_end, int r0, int r_end,
-                                             unsigned char* hi_tile, unsigned char* lo_tile, int t) {
+// One 128 x 32 operand tile (rows = outer index o0.., columns = reduction index r0..) is moved in two phases so that all
+// of a thread's global loads are in flight together: load_tile fills 8 x 16 bytes of registers (no shared-memory store
+// in between - the compiler must not serialise load/use pairs), store_tile splits them into the hi and lo tiles.
+//   reduction-contiguous operand: register i holds chunk (row = (t + 128 i) >> 3, c = (t + 128 i) & 7)
+//   outer-contiguous operand    : thread t owns tile row t; register c holds its chunk c (transposed on the fly)
+__device__ __forceinline__ void load_tile(const TcOperand& op, int o0, int o_end, int r0, int r_end, int t, float4 (&reg)[8]) {
     const int* gather = op.gather_base ? op.gather_base + (op.cursor ? *op.cursor : 0) : nullptr;
     if (!op.outer_contig) {
-        // 8 threads per row read one 16-byte chunk each: 4 rows x 128 B per warp-wide load
         const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -119,18 +121,17 @@ __device__ __forceinline__ void produce_tile(const TcOperand& op, int o0, int o_
                 const long long grow = gather ? (long long)gather[o] : (long long)o;
                 const float* p = op.base + grow * op.ld + r;
                 if (vec && r + 3 < r_end) {
-                    v = *reinterpret_cast<const float4*>(p);
+                    v = __ldg(reinterpret_cast<const float4*>(p));
                 } else {
-                    v.x = p[0];
-                    if (r + 1 < r_end) v.y = p[1];
-                    if (r + 2 < r_end) v.z = p[2];
-                    if (r + 3 < r_end) v.w = p[3];
+                    v.x = __ldg(p);
+                    if (r + 1 < r_end) v.y = __ldg(p + 1);
+                    if (r + 2 < r_end) v.z = __ldg(p + 2);
+                    if (r + 3 < r_end) v.w = __ldg(p + 3);
                 }
             }
-            split_store(v, hi_tile, lo_tile, row, c);
+            reg[i] = v;
         }
     } else {
-        // thread t owns tile row t (outer index o0 + t): 32 coalesced scalar loads (consecutive threads, consecutive o)
         const int o = o0 + t;
         const bool valid_o = o < o_end;
         const bool ones = valid_o && o == op.ones_col;
@@ -145,13 +146,21 @@ __device__ __forceinline__ void produce_tile(const TcOperand& op, int o0, int o_
                     if (ones) x = 1.f;
                     else {
                         const long long grow = gather ? (long long)gather[r] : (long long)r;
-                        x = op.base[grow * op.ld + o];
+                        x = __ldg(op.base + grow * op.ld + o);
                     }
                 }
                 e[j] = x;
             }
-            split_store(make_float4(e[0], e[1], e[2], e[3]), hi_tile, lo_tile, t, c);
+            reg[c] = make_float4(e[0], e[1], e[2], e[3]);
         }
+    }
+}
+
+__device__ __forceinline__ void store_tile(const TcOperand& op, int t, const float4 (&reg)[8], unsigned char* hi_tile, unsigned char* lo_tile) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (!op.outer_contig) { const int q = t + 128 * i; split_store(reg[i], hi_tile, lo_tile, q >> 3, q & 7); }
+        else split_store(reg[i], hi_tile, lo_tile, t, i);
     }
 }
 
@@ -184,15 +193,21 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, TcOperand a, TcOperand b, E
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // ---------------- producers ----------------
+        // ---------------- producers: register double buffering, the next k-block's loads fly during this one's stores/MMAs ----
+        float4 ra[8], rb[8];
+        if (n_kblocks > 0) { load_tile(a, i0, M, kb, ke, tid, ra); load_tile(b, j0, N, kb, ke, tid, rb); }
         for (int it = 0; it < n_kblocks; ++it) {
             const int s = it % kStages;
             const uint32_t phase = (it / kStages) & 1;
             mbar_wait(smem_u32(&bars[kStages + s]), phase ^ 1);     // stage free (first pass: returns at once)
             unsigned char* st = smem + s * kStageBytes;
-            const int r0 = kb + it * kBK;
-            produce_tile(a, i0, M, r0, ke, st, st + kTileBytes, tid);
-            produce_tile(b, j0, N, r0, ke, st + 2 * kTileBytes, st + 3 * kTileBytes, tid);
+            store_tile(a, tid, ra, st, st + kTileBytes);
+            store_tile(b, tid, rb, st + 2 * kTileBytes, st + 3 * kTileBytes);
+            if (it + 1 < n_kblocks) {
+                const int r0 = kb + (it + 1) * kBK;
+                load_tile(a, i0, M, r0, ke, tid, ra);
+                load_tile(b, j0, N, r0, ke, tid, rb);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (UMMA) reads
             mbar_arrive(smem_u32(&bars[s]));
         }
@@ -273,7 +288,8 @@ void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcO
     int splits = 1;
     if (tiles < kNumSMs && kblocks > 2) {
         splits = (int)ceil_div<long>(kNumSMs, tiles);
-        if (splits > kblocks / 2) splits = kblocks / 2;              // at least two k-blocks per split
+        if (splits > kblocks / 3) splits = kblocks / 3 > 0 ? kblocks / 3 : 1;   // at least three k-blocks per split (fills the ring)
+        if (splits > 24) splits = 24;                                        // bounded partial-sum traffic
         const size_t per_split = (size_t)M * N * sizeof(float);
         const size_t max_by_ws = per_split ? ws.bytes / per_split : 0;
         if ((size_t)splits > max_by_ws) splits = (int)max_by_ws;

@@ -219,3 +219,4 @@ using std::isinf;
 using std::isnan;
 using std::max;
 using std::min;
+template <class T> inline T __ldg(const T* p) { return *p; }

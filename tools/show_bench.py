@@ -10,5 +10,10 @@ if "roofline" in d:
     for k in d.get("kernels", []):
         print("  %-52s n/step %.1f %8.2f us share %.3f GB/s %s" % (k["kernel"], k["launches_per_step"], k["us_per_launch"], k["share"],
                                                                    None if k["gbs"] is None else round(k["gbs"])))
-    print(" cfg5@1gpu", d.get("config5_on_1_gpu"), " cpu", d.get("cpu_baseline", {}).get("value"), d.get("cpu_baseline", {}).get("cores"))
+    c5 = d.get("config5_on_1_gpu", {})
+    for k in c5.get("kernels", []):
+        print("  [B=8192] %-44s %9.2f us share %.3f GB/s %s frac %s" % (k["kernel"], k["us_per_launch"], k["share"],
+              None if k["gbs"] is None else round(k["gbs"]), None if k["frac_of_hbm_peak"] is None else round(k["frac_of_hbm_peak"], 3)))
+    c5 = {k: v for k, v in c5.items() if k != "kernels"}
+    print(" cfg5@1gpu", c5, " cpu", d.get("cpu_baseline", {}).get("value"), d.get("cpu_baseline", {}).get("cores"))
 print(" clocks", d.get("clocks"))
