@@ -107,52 +107,70 @@ __device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, un
 // in between - the compiler must not serialise load/use pairs), store_tile splits them into the hi and lo tiles.
 //   reduction-contiguous operand: register i holds chunk (row = (t + 128 i) >> 3, c = (t + 128 i) & 7)
 //   outer-contiguous operand    : thread t owns tile row t; register c holds its chunk c (transposed on the fly)
+// Branch-free on purpose: every address is clamped into the operand and every load is issued unconditionally, the value
+// is zeroed / replaced afterwards.  (With the loads inside conditional regions ptxas serialises them - one exposed DRAM
+// latency per element instead of per tile; measured 47 us per k-block before, see profiles/.)
 __device__ __forceinline__ void load_tile(const TcOperand& op, int o0, int o_end, int r0, int r_end, int t, float4 (&reg)[8]) {
     const int* gather = op.gather_base ? op.gather_base + (op.cursor ? *op.cursor : 0) : nullptr;
     if (!op.outer_contig) {
-        const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0);
+        const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0) && (((r_end - r0) & 3) == 0 || r0 + kBK <= r_end);
+        if (vec) {
+            long long grow[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int q = t + 128 * i;
-            const int row = q >> 3, c = q & 7;
-            const int o = o0 + row, r = r0 + 4 * c;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (o < o_end && r < r_end) {
-                const long long grow = gather ? (long long)gather[o] : (long long)o;
-                const float* p = op.base + grow * op.ld + r;
-                if (vec && r + 3 < r_end) {
-                    v = __ldg(reinterpret_cast<const float4*>(p));
-                } else {
-                    v.x = __ldg(p);
-                    if (r + 1 < r_end) v.y = __ldg(p + 1);
-                    if (r + 2 < r_end) v.z = __ldg(p + 2);
-                    if (r + 3 < r_end) v.w = __ldg(p + 3);
-                }
+            for (int i = 0; i < 8; ++i) {
+                const int o = min(o0 + ((t + 128 * i) >> 3), o_end - 1);
+                grow[i] = gather ? (long long)__ldg(gather + o) : (long long)o;
             }
-            reg[i] = v;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = t + 128 * i;
+                const int r = r0 + 4 * (q & 7);
+                const int rc = min(r, r_end - 4);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(op.base + grow[i] * op.ld + rc));
+                const bool ok = (o0 + (q >> 3) < o_end) && (r < r_end);
+                reg[i] = ok ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = t + 128 * i;
+                const int o = o0 + (q >> 3), r = r0 + 4 * (q & 7);
+                const int oc = min(o, o_end - 1);
+                const long long grow = gather ? (long long)__ldg(gather + oc) : (long long)oc;
+                const float* p = op.base + grow * op.ld;
+                float e[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float x = __ldg(p + min(r + j, r_end - 1));
+                    e[j] = (o < o_end && r + j < r_end) ? x : 0.f;
+                }
+                reg[i] = make_float4(e[0], e[1], e[2], e[3]);
+            }
         }
     } else {
         const int o = o0 + t;
         const bool valid_o = o < o_end;
         const bool ones = valid_o && o == op.ones_col;
+        const int oc = min(min(o, o_end - 1), (int)op.ld - 1);     // the column of ones lies outside the stored rows
+        const float* col = op.base + oc;
+        long long grow[32];
+        if (gather) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float e[4];
+            for (int i = 0; i < 32; ++i) grow[i] = (long long)__ldg(gather + min(r0 + i, r_end - 1));
+        } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = r0 + 4 * c + j;
-                float x = 0.f;
-                if (valid_o && r < r_end) {
-                    if (ones) x = 1.f;
-                    else {
-                        const long long grow = gather ? (long long)gather[r] : (long long)r;
-                        x = __ldg(op.base + grow * op.ld + o);
-                    }
-                }
-                e[j] = x;
-            }
-            reg[c] = make_float4(e[0], e[1], e[2], e[3]);
+            for (int i = 0; i < 32; ++i) grow[i] = (long long)min(r0 + i, r_end - 1);
         }
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = __ldg(col + grow[i] * op.ld);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const bool ok = valid_o && (r0 + i < r_end);
+            e[i] = ok ? (ones ? 1.f : e[i]) : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) reg[c] = make_float4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
     }
 }
 
