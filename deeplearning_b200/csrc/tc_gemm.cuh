@@ -7,13 +7,14 @@
 // (gemm.cuh): tcgen05 has no fp64 kind.
 //
 // Structure of one CTA (one 128 x BN output tile, one split of the reduction):
-//   warps 0-3  producers: global -> registers (coalesced along the operand's contiguous index, optional row gather,
-//              optional implicit column of ones) -> hi/lo split -> shared memory in the canonical K-major SWIZZLE_128B
-//              UMMA layout (row = 32 fp32 = 128 B; 16-byte chunk c of row r stored at chunk c ^ (r & 7)); the same warps
-//              run the epilogue at the end (tcgen05.ld of their 32 TMEM lanes -> epilogue functor -> global)
+//   warps 0-3  producers: cp.async global -> shared raw fp32 tiles (3-deep ring, ~96 KB in flight per SM; coalesced along
+//              the operand's contiguous index, optional row gather, zero fill, optional implicit column of ones), already
+//              in the canonical K-major SWIZZLE_128B UMMA layout (row = 32 fp32 = 128 B; 16-byte chunk c of row r stored
+//              at chunk c ^ (r & 7)); then raw -> hi/lo split into the 2-stage operand ring; the same warps run the
+//              epilogue at the end (tcgen05.ld of their 32 TMEM lanes -> epilogue functor -> global)
 //   warp 4     lane 0 issues the MMAs (tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = BN, K = 8 per instruction),
 //              tcgen05.commit releases the shared-memory stage / signals the epilogue; the warp owns the TMEM allocation
-//   mbarrier ring of kStages stages: full[s] (128 producer arrivals) / empty[s] (1 tcgen05.commit arrival).
+//   mbarrier ring of kStages operand stages: full[s] (128 producer arrivals) / empty[s] (1 tcgen05.commit arrival).
 // Operands that are not K-contiguous in memory (W^T, G^T, X^T of the backward contractions) are transposed on the fly by
 // the producers, so all three NLayer contractions (NLayer.inl:131-171) use the same K-major MMA.
 #pragma once
@@ -38,10 +39,13 @@ struct TcOperand {
 
 namespace tc {
 
-constexpr int kBM = 128, kBN = 128, kBK = 32, kStages = 3;
-constexpr int kTileBytes = kBM * kBK * 4;                  // 16 KiB: one hi or lo tile of either operand
+constexpr int kBM = 128, kBN = 128, kBK = 32;
+constexpr int kStages = 2;                                 // hi/lo operand stages consumed by the tensor core
+constexpr int kRaw = 3;                                    // raw fp32 stages filled by cp.async (the prefetch depth)
+constexpr int kTileBytes = kBM * kBK * 4;                  // 16 KiB: one raw, hi or lo tile of either operand
 constexpr int kStageBytes = 4 * kTileBytes;                // A_hi, A_lo, B_hi, B_lo
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kRawBytes = 2 * kTileBytes;                  // A_raw, B_raw
+constexpr int kSmemBytes = kStages * kStageBytes + kRaw * kRawBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 constexpr int kThreads = 160;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,68 +95,77 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, unsigned char* lo_tile, int row, int chunk) {
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-    const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
-    *reinterpret_cast<float4*>(hi_tile + off) = h;
-    *reinterpret_cast<float4*>(lo_tile + off) = l;
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Byte offset of 16-byte chunk c of tile row `row` in the K-major SWIZZLE_128B layout.
+__device__ __forceinline__ int chunk_off(int row, int c) { return row * 128 + ((c ^ (row & 7)) << 4); }
+
+// Producer thread t owns a fixed set of 8 chunks of every operand tile - it both copies and transforms exactly those, so
+// the producers need no barrier among themselves (only the 128-arrival `full` mbarrier towards the MMA warp):
+//   reduction-contiguous operand: chunks q = t + 128 i  (row q >> 3, chunk q & 7): one 16-byte cp.async each
+//   outer-contiguous operand    : all 8 chunks of tile row t, filled by 32 4-byte cp.async (transposed on the fly)
+// Out-of-range elements are zero-filled by cp.async's src-size operand (addresses are clamped into the operand).
+struct TileOwner {
+    long long grow[8];   // reduction-contiguous: stored row of each owned chunk (gather resolved once per CTA)
+};
+
+__device__ __forceinline__ void owner_init(const TcOperand& op, int o0, int o_end, int t, TileOwner& w) {
+    if (op.outer_contig) return;
+    const int* gather = op.gather_base ? op.gather_base + (op.cursor ? *op.cursor : 0) : nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int o = min(o0 + ((t + 128 * i) >> 3), o_end - 1);
+        w.grow[i] = gather ? (long long)__ldg(gather + o) : (long long)o;
+    }
 }
 
-// One 128 x 32 operand tile (rows = outer index o0.., columns = reduction index r0..) is moved in two phases so that all
-// of a thread's global loads are in flight together: load_tile fills 8 x 16 bytes of registers (no shared-memory store
-// in between - the compiler must not serialise load/use pairs), store_tile splits them into the hi and lo tiles.
-//   reduction-contiguous operand: register i holds chunk (row = (t + 128 i) >> 3, c = (t + 128 i) & 7)
-//   outer-contiguous operand    : thread t owns tile row t; register c holds its chunk c (transposed on the fly)
-// Branch-free on purpose: every address is clamped into the operand and every load is issued unconditionally, the value
-// is zeroed / replaced afterwards.  (With the loads inside conditional regions ptxas serialises them - one exposed DRAM
-// latency per element instead of per tile; measured 47 us per k-block before, see profiles/.)
-__device__ __forceinline__ void load_tile(const TcOperand& op, int o0, int o_end, int r0, int r_end, int t, float4 (&reg)[8]) {
-    const int* gather = op.gather_base ? op.gather_base + (op.cursor ? *op.cursor : 0) : nullptr;
+__device__ __forceinline__ void issue_tile(const TcOperand& op, const TileOwner& w, int o0, int o_end, int r0, int r_end, int t,
+                                           unsigned char* raw_tile) {
+    const uint32_t raw = smem_u32(raw_tile);
     if (!op.outer_contig) {
         const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0) && (((r_end - r0) & 3) == 0 || r0 + kBK <= r_end);
         if (vec) {
-            long long grow[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int o = min(o0 + ((t + 128 * i) >> 3), o_end - 1);
-                grow[i] = gather ? (long long)__ldg(gather + o) : (long long)o;
-            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int q = t + 128 * i;
-                const int r = r0 + 4 * (q & 7);
-                const int rc = min(r, r_end - 4);
-                const float4 v = __ldg(reinterpret_cast<const float4*>(op.base + grow[i] * op.ld + rc));
-                const bool ok = (o0 + (q >> 3) < o_end) && (r < r_end);
-                reg[i] = ok ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int row = q >> 3, c = q & 7;
+                const int r = r0 + 4 * c;
+                const bool ok = (o0 + row < o_end) && (r < r_end);
+                cp_async_16(raw + chunk_off(row, c), op.base + w.grow[i] * op.ld + min(r, r_end - 4), ok ? 16u : 0u);
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int q = t + 128 * i;
-                const int o = o0 + (q >> 3), r = r0 + 4 * (q & 7);
-                const int oc = min(o, o_end - 1);
-                const long long grow = gather ? (long long)__ldg(gather + oc) : (long long)oc;
-                const float* p = op.base + grow * op.ld;
-                float e[4];
+                const int row = q >> 3, c = q & 7;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float x = __ldg(p + min(r + j, r_end - 1));
-                    e[j] = (o < o_end && r + j < r_end) ? x : 0.f;
+                    const int r = r0 + 4 * c + j;
+                    const bool ok = (o0 + row < o_end) && (r < r_end);
+                    cp_async_4(raw + chunk_off(row, c) + 4 * j, op.base + w.grow[i] * op.ld + min(r, r_end - 1), ok ? 4u : 0u);
                 }
-                reg[i] = make_float4(e[0], e[1], e[2], e[3]);
             }
         }
     } else {
+        const int* gather = op.gather_base ? op.gather_base + (op.cursor ? *op.cursor : 0) : nullptr;
         const int o = o0 + t;
         const bool valid_o = o < o_end;
         const bool ones = valid_o && o == op.ones_col;
         const int oc = min(min(o, o_end - 1), (int)op.ld - 1);     // the column of ones lies outside the stored rows
         const float* col = op.base + oc;
+        if (ones) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                *reinterpret_cast<float*>(raw_tile + chunk_off(t, i >> 2) + 4 * (i & 3)) = (r0 + i < r_end) ? 1.f : 0.f;
+            return;
+        }
         long long grow[32];
         if (gather) {
 #pragma unroll
@@ -161,24 +174,26 @@ __device__ __forceinline__ void load_tile(const TcOperand& op, int o0, int o_end
 #pragma unroll
             for (int i = 0; i < 32; ++i) grow[i] = (long long)min(r0 + i, r_end - 1);
         }
-        float e[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = __ldg(col + grow[i] * op.ld);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const bool ok = valid_o && (r0 + i < r_end);
-            e[i] = ok ? (ones ? 1.f : e[i]) : 0.f;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) reg[c] = make_float4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+        for (int i = 0; i < 32; ++i)
+            cp_async_4(raw + chunk_off(t, i >> 2) + 4 * (i & 3), col + grow[i] * op.ld, (valid_o && r0 + i < r_end) ? 4u : 0u);
     }
 }
 
-__device__ __forceinline__ void store_tile(const TcOperand& op, int t, const float4 (&reg)[8], unsigned char* hi_tile, unsigned char* lo_tile) {
+// raw fp32 chunk -> hi (TF32-representable) and lo (remainder) chunks at the same offsets of the hi / lo tiles
+__device__ __forceinline__ void transform_tile(const TcOperand& op, int t, const unsigned char* raw_tile, unsigned char* hi_tile, unsigned char* lo_tile) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        if (!op.outer_contig) { const int q = t + 128 * i; split_store(reg[i], hi_tile, lo_tile, q >> 3, q & 7); }
-        else split_store(reg[i], hi_tile, lo_tile, t, i);
+        const int q = t + 128 * i;
+        const int off = op.outer_contig ? chunk_off(t, i) : chunk_off(q >> 3, q & 7);
+        const float4 v = *reinterpret_cast<const float4*>(raw_tile + off);
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+        *reinterpret_cast<float4*>(hi_tile + off) = h;
+        *reinterpret_cast<float4*>(lo_tile + off) = l;
     }
 }
 
@@ -187,7 +202,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(int M, int N, int K, int k_per_split, TcOperand a, TcOperand b, EP ep, float* __restrict__ partials) {
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);   // full[kStages], empty[kStages], tmem_full
+    unsigned char* raw_ring = smem + kStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_ring + kRaw * kRawBytes);    // full[kStages], empty[kStages], tmem_full
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -211,21 +227,35 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, TcOperand a, TcOperand b, E
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // ---------------- producers: register double buffering, the next k-block's loads fly during this one's stores/MMAs ----
-        float4 ra[8], rb[8];
-        if (n_kblocks > 0) { load_tile(a, i0, M, kb, ke, tid, ra); load_tile(b, j0, N, kb, ke, tid, rb); }
+        // ---------------- producers: cp.async ring (kRaw - 1 k-blocks in flight beyond the current), then hi/lo transform ----
+        TileOwner wa, wb;
+        owner_init(a, i0, M, tid, wa);
+        owner_init(b, j0, N, tid, wb);
+#pragma unroll
+        for (int p = 0; p < kRaw - 1; ++p) {
+            if (p < n_kblocks) {
+                unsigned char* raw = raw_ring + p * kRawBytes;
+                issue_tile(a, wa, i0, M, kb + p * kBK, ke, tid, raw);
+                issue_tile(b, wb, j0, N, kb + p * kBK, ke, tid, raw + kTileBytes);
+            }
+            cp_async_commit();
+        }
         for (int it = 0; it < n_kblocks; ++it) {
+            const int nxt = it + kRaw - 1;
+            if (nxt < n_kblocks) {   // refills the raw slot this thread finished transforming in the previous iteration
+                unsigned char* raw = raw_ring + (nxt % kRaw) * kRawBytes;
+                issue_tile(a, wa, i0, M, kb + nxt * kBK, ke, tid, raw);
+                issue_tile(b, wb, j0, N, kb + nxt * kBK, ke, tid, raw + kTileBytes);
+            }
+            cp_async_commit();
+            cp_async_wait<kRaw - 1>();                              // this thread's copies of k-block `it` have landed
             const int s = it % kStages;
             const uint32_t phase = (it / kStages) & 1;
-            mbar_wait(smem_u32(&bars[kStages + s]), phase ^ 1);     // stage free (first pass: returns at once)
+            mbar_wait(smem_u32(&bars[kStages + s]), phase ^ 1);     // hi/lo stage free (first pass: returns at once)
+            const unsigned char* raw = raw_ring + (it % kRaw) * kRawBytes;
             unsigned char* st = smem + s * kStageBytes;
-            store_tile(a, tid, ra, st, st + kTileBytes);
-            store_tile(b, tid, rb, st + 2 * kTileBytes, st + 3 * kTileBytes);
-            if (it + 1 < n_kblocks) {
-                const int r0 = kb + (it + 1) * kBK;
-                load_tile(a, i0, M, r0, ke, tid, ra);
-                load_tile(b, j0, N, r0, ke, tid, rb);
-            }
+            transform_tile(a, tid, raw, st, st + kTileBytes);
+            transform_tile(b, tid, raw + kTileBytes, st + 2 * kTileBytes, st + 3 * kTileBytes);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (UMMA) reads
             mbar_arrive(smem_u32(&bars[s]));
         }
