@@ -154,46 +154,72 @@ __device__ __forceinline__ void issue_tile(const TcOperand& op, const TileOwner&
             }
         }
     } else {
+        // raw layout of an outer-contiguous operand: plain [32 reduction rows][128 outer] fp32 (512 B per row), copied as 16-byte
+        // chunks along the contiguous (outer) index; transform_tile transposes it into the K-major tiles
         const int* gather = op.gather_base ? op.gather_base + (op.cursor ? *op.cursor : 0) : nullptr;
-        const int o = o0 + t;
-        const bool valid_o = o < o_end;
-        const bool ones = valid_o && o == op.ones_col;
-        const int oc = min(min(o, o_end - 1), (int)op.ld - 1);     // the column of ones lies outside the stored rows
-        const float* col = op.base + oc;
-        if (ones) {
+        const int o_lim = min(o_end, (int)op.ld);                   // the column of ones (o == ld) is synthesised in transform_tile
+        const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0);
+        if (vec) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                *reinterpret_cast<float*>(raw_tile + chunk_off(t, i >> 2) + 4 * (i & 3)) = (r0 + i < r_end) ? 1.f : 0.f;
-            return;
-        }
-        long long grow[32];
-        if (gather) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) grow[i] = (long long)__ldg(gather + min(r0 + i, r_end - 1));
+            for (int i = 0; i < 8; ++i) {
+                const int q = t + 128 * i;
+                const int k = q >> 5, oc = (q & 31) * 4;
+                const int r = min(r0 + k, r_end - 1);
+                const long long grow = gather ? (long long)__ldg(gather + r) : (long long)r;
+                const int o = o0 + oc;
+                int n_ok = (r0 + k < r_end) ? min(4, o_lim - o) : 0;
+                n_ok = n_ok < 0 ? 0 : n_ok;
+                cp_async_16(raw + (k * 128 + oc) * 4, op.base + grow * op.ld + min(o, (int)op.ld - 4), (uint32_t)(4 * n_ok));
+            }
         } else {
+            const int o = o0 + t;
+            const int oc = min(min(o, o_end - 1), (int)op.ld - 1);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) grow[i] = (long long)min(r0 + i, r_end - 1);
+            for (int k = 0; k < 32; ++k) {
+                const int r = min(r0 + k, r_end - 1);
+                const long long grow = gather ? (long long)__ldg(gather + r) : (long long)r;
+                cp_async_4(raw + (k * 128 + t) * 4, op.base + grow * op.ld + oc, (o < o_lim && r0 + k < r_end) ? 4u : 0u);
+            }
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-            cp_async_4(raw + chunk_off(t, i >> 2) + 4 * (i & 3), col + grow[i] * op.ld, (valid_o && r0 + i < r_end) ? 4u : 0u);
     }
 }
 
 // raw fp32 chunk -> hi (TF32-representable) and lo (remainder) chunks at the same offsets of the hi / lo tiles
-__device__ __forceinline__ void transform_tile(const TcOperand& op, int t, const unsigned char* raw_tile, unsigned char* hi_tile, unsigned char* lo_tile) {
+__device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, unsigned char* lo_tile, int off) {
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi_tile + off) = h;
+    *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+__device__ __forceinline__ void transform_tile(const TcOperand& op, int o0, int o_end, int r0, int r_end, int t,
+                                               const unsigned char* raw_tile, unsigned char* hi_tile, unsigned char* lo_tile) {
+    if (!op.outer_contig) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int q = t + 128 * i;
-        const int off = op.outer_contig ? chunk_off(t, i) : chunk_off(q >> 3, q & 7);
-        const float4 v = *reinterpret_cast<const float4*>(raw_tile + off);
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-        *reinterpret_cast<float4*>(hi_tile + off) = h;
-        *reinterpret_cast<float4*>(lo_tile + off) = l;
+        for (int i = 0; i < 8; ++i) {
+            const int q = t + 128 * i;
+            const int off = chunk_off(q >> 3, q & 7);
+            split_store(*reinterpret_cast<const float4*>(raw_tile + off), hi_tile, lo_tile, off);
+        }
+    } else {
+        // thread t produces tile row t (outer index o0 + t): column t of the raw [k][o] block (conflict-free: lanes read
+        // consecutive words), or the implicit column of ones
+        const float* raw = reinterpret_cast<const float*>(raw_tile);
+        const bool ones = (o0 + t < o_end) && (o0 + t == op.ones_col);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float4 v;
+            if (ones) {
+                v = make_float4(r0 + 4 * c < r_end ? 1.f : 0.f, r0 + 4 * c + 1 < r_end ? 1.f : 0.f,
+                                r0 + 4 * c + 2 < r_end ? 1.f : 0.f, r0 + 4 * c + 3 < r_end ? 1.f : 0.f);
+            } else {
+                v = make_float4(raw[(4 * c) * 128 + t], raw[(4 * c + 1) * 128 + t], raw[(4 * c + 2) * 128 + t], raw[(4 * c + 3) * 128 + t]);
+            }
+            split_store(v, hi_tile, lo_tile, chunk_off(t, c));
+        }
     }
 }
 
@@ -241,28 +267,31 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, TcOperand a, TcOperand b, E
             cp_async_commit();
         }
         for (int it = 0; it < n_kblocks; ++it) {
+            cp_async_wait<kRaw - 2>();                              // this thread's copies of k-block `it` have landed
+            // every producer's copies of k-block `it` have landed, and every producer is done reading the slot refilled next
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             const int nxt = it + kRaw - 1;
-            if (nxt < n_kblocks) {   // refills the raw slot this thread finished transforming in the previous iteration
-                unsigned char* raw = raw_ring + (nxt % kRaw) * kRawBytes;
-                issue_tile(a, wa, i0, M, kb + nxt * kBK, ke, tid, raw);
-                issue_tile(b, wb, j0, N, kb + nxt * kBK, ke, tid, raw + kTileBytes);
+            if (nxt < n_kblocks) {
+                unsigned char* rawn = raw_ring + (nxt % kRaw) * kRawBytes;
+                issue_tile(a, wa, i0, M, kb + nxt * kBK, ke, tid, rawn);
+                issue_tile(b, wb, j0, N, kb + nxt * kBK, ke, tid, rawn + kTileBytes);
             }
             cp_async_commit();
-            cp_async_wait<kRaw - 1>();                              // this thread's copies of k-block `it` have landed
             const int s = it % kStages;
             const uint32_t phase = (it / kStages) & 1;
             mbar_wait(smem_u32(&bars[kStages + s]), phase ^ 1);     // hi/lo stage free (first pass: returns at once)
             const unsigned char* raw = raw_ring + (it % kRaw) * kRawBytes;
             unsigned char* st = smem + s * kStageBytes;
-            transform_tile(a, tid, raw, st, st + kTileBytes);
-            transform_tile(b, tid, raw + kTileBytes, st + 2 * kTileBytes, st + 3 * kTileBytes);
+            const int r0 = kb + it * kBK;
+            transform_tile(a, i0, M, r0, ke, tid, raw, st, st + kTileBytes);
+            transform_tile(b, j0, N, r0, ke, tid, raw + kTileBytes, st + 2 * kTileBytes, st + 3 * kTileBytes);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (UMMA) reads
             mbar_arrive(smem_u32(&bars[s]));
         }
+        cp_async_wait<0>();
         // ---------------- epilogue (same warps): TMEM lanes 32*warp .. 32*warp+31 ----------------
         mbar_wait(smem_u32(&bars[2 * kStages]), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int gi = i0 + warp * 32 + lane;
         const bool split = gridDim.z > 1;
 #pragma unroll 1
         for (int c0 = 0; c0 < kBN; c0 += 32) {
@@ -279,16 +308,24 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, TcOperand a, TcOperand b, E
                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (gi < M) {
+            // 32 x 32 block: lane = row in registers -> shared (padded) -> lane = column, so that every warp-wide access of the
+            // epilogue (stores, bias / previous-activation loads) covers 128 contiguous bytes
+            float* tile = reinterpret_cast<float*>(raw_ring) + warp * (32 * 33);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int gj = j0 + c0 + j;
-                    if (gj >= N) break;
-                    const float acc = __uint_as_float(v[j]);
-                    if (split) partials[((size_t)blockIdx.z * M + gi) * N + gj] = acc;
-                    else ep(gi, gj, acc);
+            for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            const int gj = j0 + c0 + lane;
+            if (gj < N) {
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    const int gr = i0 + warp * 32 + r;
+                    if (gr >= M) break;
+                    const float acc = tile[r * 33 + lane];
+                    if (split) partials[((size_t)blockIdx.z * M + gr) * N + gj] = acc;
+                    else ep(gr, gj, acc);
                 }
             }
+            __syncwarp();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
