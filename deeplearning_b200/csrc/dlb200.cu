@@ -305,6 +305,13 @@ struct NetT final : dlb_net {
 #endif
     };
     std::vector<StepGraph> step_graphs;
+    // Side streams: after the head kernel the step forks - the head's and every hidden NLayer's weight gradient run beside
+    // the input-gradient -> conv-backward chain - and joins again before the reduce/update.  Inside a CUDA-graph capture
+    // the same event fork/join becomes parallel graph branches.
+    cudaStream_t side_head = nullptr, side_dw = nullptr;
+    std::vector<cudaEvent_t> fork_events;
+    GemmWorkspace ws_side;            // split-partial scratch of the weight-gradient contractions on side_dw
+    bool overlap_enabled = true;
     const void* ws_stamp = nullptr;   // the context scratch the captured graphs point into
     bool graphs_enabled = true;
     bool use_tensor_cores = true;     // fp32 NLayer contractions on tcgen05 (3xTF32); off = FMA path (gemm.cuh)
@@ -340,6 +347,16 @@ struct NetT final : dlb_net {
         d_cursor = dev_alloc<int>(1);
         DLB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(int), ctx->stream));
         build_plan();
+#ifndef DLB_CUDA_EMU
+        if (plan.ok) {
+            DLB_CUDA(cudaStreamCreateWithFlags(&side_head, cudaStreamNonBlocking));
+            DLB_CUDA(cudaStreamCreateWithFlags(&side_dw, cudaStreamNonBlocking));
+            fork_events.resize((size_t)L() + 4);
+            for (auto& e : fork_events) DLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ws_side.bytes = 64u << 20;
+            DLB_CUDA(cudaMalloc(&ws_side.ptr, ws_side.bytes));
+        }
+#endif
     }
 
     // Which nets take the fused path:  [CLayer + PLayer(max|min) covered by plan_conv_pool]  NLayer*  NLayer(head)
@@ -374,6 +391,12 @@ struct NetT final : dlb_net {
         free_workspace();
         dev_free(params); dev_free(grads); dev_free(cost_dev); dev_free(perm_dev);
         drop_graphs();
+#ifndef DLB_CUDA_EMU
+        if (side_head) { cudaStreamSynchronize(side_head); cudaStreamDestroy(side_head); }
+        if (side_dw) { cudaStreamSynchronize(side_dw); cudaStreamDestroy(side_dw); }
+        for (auto& e : fork_events) cudaEventDestroy(e);
+        if (ws_side.ptr) cudaFree(ws_side.ptr);
+#endif
         dev_free(cp_partial); dev_free(head_partial); dev_free(d_cursor);
         if (own_data) { dev_free(data_x); dev_free(data_y); }
 #ifndef DLB_CUDA_EMU
@@ -533,6 +556,12 @@ struct NetT final : dlb_net {
         const LaunchCtx lc = ctx->lc();
         cudaStream_t st = ctx->stream;
         const int Ln = L();
+#ifndef DLB_CUDA_EMU
+        const bool fork = overlap_enabled && side_head != nullptr && !g_timing_on;
+#else
+        const bool fork = false;
+#endif
+        bool forked_dw = false;
         int l = 0;
         if (plan.has_cp) {
             g_tag_layer = 0;
@@ -592,7 +621,15 @@ struct NetT final : dlb_net {
                 TagScope tag_("head_dW");
                 head_chunks = (int)ceil_div(B, kHeadChunk);
                 const int total = (int)Y.out_n * (int)(Y.in_n + 1);
-                DLB_LAUNCH((batch_outer_partial_kernel<R>), dim3((unsigned)ceil_div(total, 128), (unsigned)head_chunks), dim3(128), st,
+                cudaStream_t hs = st;
+#ifndef DLB_CUDA_EMU
+                if (fork) {
+                    DLB_CUDA(cudaEventRecord(fork_events[(size_t)Ln], st));
+                    DLB_CUDA(cudaStreamWaitEvent(side_head, fork_events[(size_t)Ln], 0));
+                    hs = side_head;
+                }
+#endif
+                DLB_LAUNCH((batch_outer_partial_kernel<R>), dim3((unsigned)ceil_div(total, 128), (unsigned)head_chunks), dim3(128), hs,
                            (const R*)in_grad[(size_t)Ln], (const R*)out[(size_t)h - 1], head_partial, B, (int)Y.out_n, (int)Y.in_n, kHeadChunk);
             }
         }
@@ -603,7 +640,15 @@ struct NetT final : dlb_net {
             const R* gl = in_grad[(size_t)l + 1];
             R* db = grads + Y.param_off;
             bool done_tc = false;
+            // the weight gradient of this layer only needs g_l: it runs on the side stream while the main stream goes on with dX
+            cudaStream_t ws_stream = st;
+            GemmWorkspace ws_for_dw = lc.ws;
 #ifndef DLB_CUDA_EMU
+            if (fork) {
+                DLB_CUDA(cudaEventRecord(fork_events[(size_t)l], st));
+                DLB_CUDA(cudaStreamWaitEvent(side_dw, fork_events[(size_t)l], 0));
+                ws_stream = side_dw; ws_for_dw = ws_side; forked_dw = true;
+            }
             if constexpr (std::is_same_v<R, float>) {
                 if (use_tensor_cores) {
                     {   // dW[n][k] = sum_b g[b][n] x[b][k], db[n] = sum_b g[b][n] (column of ones): both operands outer-contiguous
@@ -611,7 +656,7 @@ struct NetT final : dlb_net {
                         const TcOperand A{gl, (long long)Y.out_n, 1, nullptr, nullptr, -1};
                         const TcOperand Bo{l == 0 ? x : out[(size_t)l - 1], (long long)Y.in_n, 1, l == 0 ? gather_base : nullptr,
                                            l == 0 ? cursor : nullptr, (int)Y.in_n};
-                        tc_gemm(st, (int)Y.out_n, (int)Y.in_n + 1, B, A, Bo, EpiWeightAndBias<float>{db, db + Y.bias_n, (int)Y.in_n}, lc.ws);
+                        tc_gemm(ws_stream, (int)Y.out_n, (int)Y.in_n + 1, B, A, Bo, EpiWeightAndBias<float>{db, db + Y.bias_n, (int)Y.in_n}, ws_for_dw);
                     }
                     if (l > 0) {   // dx[b][k] = sum_n g[b][n] W[n][k]: A reduction-contiguous, B (= W) outer-contiguous
                         TagScope tag_("full_dX");
@@ -630,12 +675,12 @@ struct NetT final : dlb_net {
             {
                 TagScope tag_("full_dW");
                 if (l == 0)
-                    gemm<R>(st, (int)Y.out_n, (int)Y.in_n + 1, B, DenseColLoader<R>{gl, (size_t)Y.out_n, nullptr},
-                            DenseColOnesLoader<R>{x, (size_t)Y.in_n, gather_base, cursor}, EpiWeightAndBias<R>{db, db + Y.bias_n, (int)Y.in_n}, lc.ws);
+                    gemm<R>(ws_stream, (int)Y.out_n, (int)Y.in_n + 1, B, DenseColLoader<R>{gl, (size_t)Y.out_n, nullptr},
+                            DenseColOnesLoader<R>{x, (size_t)Y.in_n, gather_base, cursor}, EpiWeightAndBias<R>{db, db + Y.bias_n, (int)Y.in_n}, ws_for_dw);
                 else
-                    gemm<R>(st, (int)Y.out_n, (int)Y.in_n + 1, B, DenseColLoader<R>{gl, (size_t)Y.out_n, nullptr},
+                    gemm<R>(ws_stream, (int)Y.out_n, (int)Y.in_n + 1, B, DenseColLoader<R>{gl, (size_t)Y.out_n, nullptr},
                             DenseColOnesLoader<R>{out[(size_t)l - 1], (size_t)Y.in_n, nullptr, nullptr},
-                            EpiWeightAndBias<R>{db, db + Y.bias_n, (int)Y.in_n}, lc.ws);
+                            EpiWeightAndBias<R>{db, db + Y.bias_n, (int)Y.in_n}, ws_for_dw);
             }
             if (l > 0) {
                 TagScope tag_("full_dX");
@@ -653,6 +698,17 @@ struct NetT final : dlb_net {
                 DLB_CUDA(cudaMemsetAsync(cp_partial + (size_t)grid * plan.cp.n_par, 0, (size_t)(cp_grid - grid) * plan.cp.n_par * sizeof(R), st));
             conv_pool_backward<R>(st, plan.cp, grid, x, gather_base, cursor, (const R*)in_grad[2], (const int*)imap[1], (const R*)out[1], cp_partial, B);
         }
+#ifndef DLB_CUDA_EMU
+        if (fork) {   // join: the reduce/update that follows reads every gradient
+            DLB_CUDA(cudaEventRecord(fork_events[(size_t)Ln + 1], side_head));
+            DLB_CUDA(cudaStreamWaitEvent(st, fork_events[(size_t)Ln + 1], 0));
+            if (forked_dw) {
+                DLB_CUDA(cudaEventRecord(fork_events[(size_t)Ln + 2], side_dw));
+                DLB_CUDA(cudaStreamWaitEvent(st, fork_events[(size_t)Ln + 2], 0));
+            }
+        }
+#endif
+        (void)forked_dw;
         last_B = B;
     }
 
