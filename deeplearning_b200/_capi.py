@@ -54,7 +54,7 @@ SYMBOLS = [
     "dlb_net_write_gradient", "dlb_net_eval_host", "dlb_nccl_get_unique_id", "dlb_net_set_distributed",
     "dlb_shuffle_sequence", "dlb_net_train_steps", "dlb_rank_slice", "dlb_event_create", "dlb_event_destroy",
     "dlb_event_record", "dlb_event_elapsed_ms", "dlb_timing_enable", "dlb_timing_report", "dlb_net_describe_plan",
-    "dlb_net_enable_graphs", "dlb_net_enable_tensor_cores", "dlb_matmul_f32",
+    "dlb_net_enable_graphs", "dlb_net_enable_tensor_cores", "dlb_matmul_f32", "dlb_net_step_host_async",
 ]
 
 
@@ -98,6 +98,7 @@ def load() -> C.CDLL:
     lib.dlb_net_learn.argtypes = [vp, i64, i64, dbl, i32, dbl, vp, vp]
     lib.dlb_net_step_indices.argtypes = [vp, vp, i64, dbl, i32, dbl]
     lib.dlb_net_step_host.argtypes = [vp, vp, vp, i64, dbl, i32, dbl, C.POINTER(dbl)]
+    lib.dlb_net_step_host_async.argtypes = [vp, vp, vp, i64, dbl, i32, dbl, vp]
     lib.dlb_net_forward_backward_host.argtypes = [vp, vp, vp, i64, i32, dbl]
     lib.dlb_net_read.argtypes = [vp, i32, i32, vp, i64]
     lib.dlb_net_write_gradient.argtypes = [vp, vp]

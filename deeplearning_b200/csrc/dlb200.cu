@@ -249,7 +249,7 @@ struct dlb_net {
     virtual void learn(int64_t batch, int64_t epochs, double lr, int cost, double lambda, dlb_epoch_callback cb, void* user) = 0;
     virtual int64_t train_steps(int64_t batch, int64_t n_steps, double lr, int cost, double lambda) = 0;
     virtual void step_indices(const int64_t* idx, int64_t n, double lr, int cost, double reg_factor) = 0;
-    virtual void step_host(const void* x, const void* y, int64_t n, double lr, int cost, double reg_factor, double* cost_out) = 0;
+    virtual void step_host(const void* x, const void* y, int64_t n, double lr, int cost, double reg_factor, double* cost_out, bool sync) = 0;
     virtual void forward_backward_host(const void* x, const void* y, int64_t n, int cost, double scale) = 0;
     virtual void read(int what, int layer, void* dst, int64_t bytes) = 0;
     virtual void write_gradient(const void* src) = 0;
@@ -295,8 +295,10 @@ struct NetT final : dlb_net {
     // CUDA graphs of the whole step, one per distinct (share, batch, hyper-parameters): the per-step launch sequence is
     // identical for every batch of an epoch because the batch position lives in d_cursor on the device.
     struct StepKey {
-        int64_t mine, global; double lr, reg; int cost;
-        bool operator==(const StepKey& o) const { return mine == o.mine && global == o.global && lr == o.lr && reg == o.reg && cost == o.cost; }
+        int64_t mine, global; double lr, reg; int cost; const void* x; int flags;
+        bool operator==(const StepKey& o) const {
+            return mine == o.mine && global == o.global && lr == o.lr && reg == o.reg && cost == o.cost && x == o.x && flags == o.flags;
+        }
     };
     struct StepGraph {
         StepKey key{}; int seen = 0; long long launches = 0;
@@ -305,12 +307,53 @@ struct NetT final : dlb_net {
 #endif
     };
     std::vector<StepGraph> step_graphs;
+
+    // Runs `body` (a fixed launch sequence on fixed buffers) eagerly the first time a key is seen (this also sets kernel
+    // attributes), captures it into a CUDA graph the second time, and replays the graph from then on.
+    template <class F>
+    void run_graphed(const StepKey& key, F&& body) {
+#ifndef DLB_CUDA_EMU
+        if (ws_stamp == ctx->ws.ptr && !g_timing_on && graphs_enabled) {
+            StepGraph* sg = nullptr;
+            for (auto& g : step_graphs) if (g.key == key) { sg = &g; break; }
+            if (!sg) { if (step_graphs.size() >= 16) drop_graphs(); step_graphs.push_back(StepGraph{}); sg = &step_graphs.back(); sg->key = key; }
+            if (sg->exec) {
+                DLB_CUDA(cudaGraphLaunch(sg->exec, ctx->stream));
+                g_launch_count.fetch_add(sg->launches, std::memory_order_relaxed);
+                last_B = (int)key.mine;
+                return;
+            }
+            if (sg->seen++ >= 1) {
+                const long long before = g_launch_count.load();
+                DLB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                try { body(); } catch (...) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(ctx->stream, &junk); if (junk) cudaGraphDestroy(junk); throw; }
+                DLB_CUDA(cudaStreamEndCapture(ctx->stream, &sg->graph));
+                sg->launches = g_launch_count.load() - before;
+                g_launch_count.store(before);
+                DLB_CUDA(cudaGraphInstantiate(&sg->exec, sg->graph, 0));
+                DLB_CUDA(cudaGraphLaunch(sg->exec, ctx->stream));
+                g_launch_count.fetch_add(sg->launches, std::memory_order_relaxed);
+                return;
+            }
+        }
+        ws_stamp = ctx->ws.ptr;
+#endif
+        body();
+    }
+
     // Side streams: after the head kernel the step forks - the head's and every hidden NLayer's weight gradient run beside
     // the input-gradient -> conv-backward chain - and joins again before the reduce/update.  Inside a CUDA-graph capture
     // the same event fork/join becomes parallel graph branches.
     cudaStream_t side_head = nullptr, side_dw = nullptr;
     std::vector<cudaEvent_t> fork_events;
     GemmWorkspace ws_side;            // split-partial scratch of the weight-gradient contractions on side_dw
+    // Host-buffer steps (dlb_net_step_host*): the next batch is copied on its own stream into the other half of a double
+    // buffer while the current step computes.
+    cudaStream_t side_copy = nullptr;
+    R* hstage_x[2] = {nullptr, nullptr}; R* hstage_y[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    bool hbuf_used[2] = {false, false};
+    int hbuf = 0; int64_t hcap = 0;
     bool overlap_enabled = true;
     const void* ws_stamp = nullptr;   // the context scratch the captured graphs point into
     bool graphs_enabled = true;
@@ -356,6 +399,11 @@ struct NetT final : dlb_net {
             ws_side.bytes = 64u << 20;
             DLB_CUDA(cudaMalloc(&ws_side.ptr, ws_side.bytes));
         }
+        DLB_CUDA(cudaStreamCreateWithFlags(&side_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            DLB_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+            DLB_CUDA(cudaEventCreateWithFlags(&ev_consumed[i], cudaEventDisableTiming));
+        }
 #endif
     }
 
@@ -396,7 +444,10 @@ struct NetT final : dlb_net {
         if (side_dw) { cudaStreamSynchronize(side_dw); cudaStreamDestroy(side_dw); }
         for (auto& e : fork_events) cudaEventDestroy(e);
         if (ws_side.ptr) cudaFree(ws_side.ptr);
+        if (side_copy) { cudaStreamSynchronize(side_copy); cudaStreamDestroy(side_copy); }
+        for (int i = 0; i < 2; ++i) { if (ev_copied[i]) cudaEventDestroy(ev_copied[i]); if (ev_consumed[i]) cudaEventDestroy(ev_consumed[i]); }
 #endif
+        for (int i = 0; i < 2; ++i) { dev_free(hstage_x[i]); dev_free(hstage_y[i]); }
         dev_free(cp_partial); dev_free(head_partial); dev_free(d_cursor);
         if (own_data) { dev_free(data_x); dev_free(data_y); }
 #ifndef DLB_CUDA_EMU
@@ -785,35 +836,8 @@ struct NetT final : dlb_net {
                     update(lr, reg_factor, global, advance);
                 }
             };
-#ifndef DLB_CUDA_EMU
-            // Only the resident-data path (cursor-relative gather on fixed buffers) replays a graph; the first occurrence of a
-            // key runs eagerly (it also sets kernel attributes), the second is captured, later ones are one cudaGraphLaunch.
-            if (cursor && x == data_x && ws_stamp == ctx->ws.ptr && !g_timing_on && graphs_enabled) {
-                const StepKey key{mine, global, lr, reg_factor, cost};
-                StepGraph* sg = nullptr;
-                for (auto& g : step_graphs) if (g.key == key) { sg = &g; break; }
-                if (!sg) { if (step_graphs.size() >= 16) drop_graphs(); step_graphs.push_back(StepGraph{}); sg = &step_graphs.back(); sg->key = key; }
-                if (sg->exec) {
-                    DLB_CUDA(cudaGraphLaunch(sg->exec, ctx->stream));
-                    g_launch_count.fetch_add(sg->launches, std::memory_order_relaxed);
-                    last_B = (int)mine;
-                    return;
-                }
-                if (sg->seen++ >= 1) {
-                    const long long before = g_launch_count.load();
-                    DLB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-                    try { body(); } catch (...) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(ctx->stream, &junk); if (junk) cudaGraphDestroy(junk); throw; }
-                    DLB_CUDA(cudaStreamEndCapture(ctx->stream, &sg->graph));
-                    sg->launches = g_launch_count.load() - before;
-                    g_launch_count.store(before);
-                    DLB_CUDA(cudaGraphInstantiate(&sg->exec, sg->graph, 0));
-                    DLB_CUDA(cudaGraphLaunch(sg->exec, ctx->stream));
-                    g_launch_count.fetch_add(sg->launches, std::memory_order_relaxed);
-                    return;
-                }
-            }
-            ws_stamp = ctx->ws.ptr;
-#endif
+            // Only paths whose buffers are fixed replay a graph: the resident-data path (cursor-relative gather).
+            if (cursor && x == data_x) { run_graphed(StepKey{mine, global, lr, reg_factor, cost, x, 0}, body); return; }
             body();
             return;
         }
@@ -924,29 +948,67 @@ struct NetT final : dlb_net {
         if (y) DLB_CUDA(cudaMemcpyAsync(stage_y, y, (size_t)n * (size_t)outN() * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
     }
 
-    void step_host(const void* x, const void* y, int64_t n, double lr, int cost, double reg_factor, double* cost_out) override {
+    // One step on host buffers.  The copy of this batch runs on the copy stream into the half of the staging double buffer
+    // that the step before the previous one used, so it overlaps the previous step's kernels; the step itself (a CUDA graph
+    // per buffer half on the fused path) and the device->host copy of the batch cost are enqueued on the main stream.
+    // sync == false leaves everything in flight (dlb_net_step_host_async); the caller synchronises the context.
+    void step_host(const void* x, const void* y, int64_t n, double lr, int cost, double reg_factor, double* cost_out, bool sync) override {
         DLB_REQUIRE(x && y && n > 0, "Invalid input.");
         use_device(ctx);
-        stage_host_batch(x, y, n);
-        if (plan.ok) train_forward_backward((int)n, stage_x, stage_y, nullptr, nullptr, cost);
-        else forward_backward((int)n, stage_x, stage_y, nullptr, cost, R(0));
-        if (cost_out) {
-            g_tag_layer = L();
-            TagScope tag_("cost_sum");
-            DLB_LAUNCH((cost_sum_kernel<R>), dim3(1), dim3(256), ctx->stream, (const R*)out[(size_t)L() - 1], (const R*)stage_y,
-                       (const int*)nullptr, (int)n, (int)outN(), cost, cost_dev);
-        }
-        if (plan.ok && world <= 1) {
-            train_reduce_update(true, lr, reg_factor, n, 0);
-        } else {
-            if (plan.ok) train_reduce_update(false, lr, reg_factor, n, 0);
-            allreduce_gradient();
-            update(lr, reg_factor, n * world);
-        }
-        if (cost_out) {
-            DLB_CUDA(cudaMemcpyAsync(cost_out, cost_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ensure_capacity(n);
+        if (n > hcap) {
             DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+#ifndef DLB_CUDA_EMU
+            DLB_CUDA(cudaStreamSynchronize(side_copy));
+#endif
+            drop_graphs();
+            for (int i = 0; i < 2; ++i) {
+                dev_free(hstage_x[i]); dev_free(hstage_y[i]);
+                hstage_x[i] = dev_alloc<R>((size_t)n * (size_t)in0());
+                hstage_y[i] = dev_alloc<R>((size_t)n * (size_t)outN());
+                hbuf_used[i] = false;
+            }
+            hcap = n;
         }
+        const int buf = hbuf; hbuf ^= 1;
+        R* sx = hstage_x[buf]; R* sy = hstage_y[buf];
+        cudaStream_t cs = ctx->stream;
+#ifndef DLB_CUDA_EMU
+        cs = side_copy;
+        if (hbuf_used[buf]) DLB_CUDA(cudaStreamWaitEvent(cs, ev_consumed[buf], 0));   // the step that last read this half is done
+#endif
+        DLB_CUDA(cudaMemcpyAsync(sx, x, (size_t)n * (size_t)in0() * sizeof(R), cudaMemcpyHostToDevice, cs));
+        DLB_CUDA(cudaMemcpyAsync(sy, y, (size_t)n * (size_t)outN() * sizeof(R), cudaMemcpyHostToDevice, cs));
+#ifndef DLB_CUDA_EMU
+        DLB_CUDA(cudaEventRecord(ev_copied[buf], cs));
+        DLB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied[buf], 0));
+#endif
+        const bool want_cost = cost_out != nullptr;
+        auto body = [&] {
+            if (plan.ok) train_forward_backward((int)n, sx, sy, nullptr, nullptr, cost);
+            else forward_backward((int)n, sx, sy, nullptr, cost, R(0));
+            if (want_cost) {
+                g_tag_layer = L();
+                TagScope tag_("cost_sum");
+                DLB_LAUNCH((cost_sum_kernel<R>), dim3(1), dim3(256), ctx->stream, (const R*)out[(size_t)L() - 1], (const R*)sy,
+                           (const int*)nullptr, (int)n, (int)outN(), cost, cost_dev);
+            }
+            if (plan.ok && world <= 1) {
+                train_reduce_update(true, lr, reg_factor, n, 0);
+            } else {
+                if (plan.ok) train_reduce_update(false, lr, reg_factor, n, 0);
+                allreduce_gradient();
+                update(lr, reg_factor, n * world);
+            }
+        };
+        if (plan.ok) run_graphed(StepKey{n, n * world, lr, reg_factor, cost, sx, want_cost ? 1 : 2}, body);
+        else body();
+#ifndef DLB_CUDA_EMU
+        DLB_CUDA(cudaEventRecord(ev_consumed[buf], ctx->stream));
+        hbuf_used[buf] = true;
+#endif
+        if (cost_out) DLB_CUDA(cudaMemcpyAsync(cost_out, cost_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (sync) DLB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
 
     void forward_backward_host(const void* x, const void* y, int64_t n, int cost, double scale) override {
@@ -1210,7 +1272,10 @@ int dlb_net_step_indices(dlb_net* net, const int64_t* idx, int64_t n, double lr,
     return guarded([&] { DLB_REQUIRE(net, "null net"); net->step_indices(idx, n, lr, cost, reg_factor); });
 }
 int dlb_net_step_host(dlb_net* net, const void* x, const void* y, int64_t n, double lr, int cost, double reg_factor, double* cost_out) {
-    return guarded([&] { DLB_REQUIRE(net, "null net"); net->step_host(x, y, n, lr, cost, reg_factor, cost_out); });
+    return guarded([&] { DLB_REQUIRE(net, "null net"); net->step_host(x, y, n, lr, cost, reg_factor, cost_out, true); });
+}
+int dlb_net_step_host_async(dlb_net* net, const void* x, const void* y, int64_t n, double lr, int cost, double reg_factor, double* cost_out) {
+    return guarded([&] { DLB_REQUIRE(net, "null net"); net->step_host(x, y, n, lr, cost, reg_factor, cost_out, false); });
 }
 int dlb_net_forward_backward_host(dlb_net* net, const void* x, const void* y, int64_t n, int cost, double scale) {
     return guarded([&] { DLB_REQUIRE(net, "null net"); net->forward_backward_host(x, y, n, cost, scale); });

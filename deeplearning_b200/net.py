@@ -358,6 +358,14 @@ class Net:
                                                int(cost_func_id), float(reg_factor), C.byref(cost) if want_cost else None))
         return cost.value if want_cost else None
 
+    def step_host_async(self, inputs: np.ndarray, refs: np.ndarray, learning_rate: float, cost_func_id: CostFunctionId,
+                        reg_factor: float = 0.0, cost_slot: Optional[np.ndarray] = None) -> None:
+        """Enqueue one mini-batch step on host buffers without waiting: the copy of this batch overlaps the previous step.
+        cost_slot: a one-element float64 array in pinned memory that receives the batch cost; valid after ctx.synchronize()."""
+        _capi.check(self.lib.dlb_net_step_host_async(self._handle(), inputs.ctypes.data, refs.ctypes.data, inputs.shape[0],
+                                                     float(learning_rate), int(cost_func_id), float(reg_factor),
+                                                     cost_slot.ctypes.data if cost_slot is not None else None))
+
     def forward_backward(self, inputs, refs, cost_func_id: CostFunctionId, scale: float = 0.0) -> int:
         x = self._as_items(inputs, self.layer_in_size(0))
         y = self._as_items(refs, self.layer_out_size(self.layers_count() - 1))

@@ -162,6 +162,13 @@ DLB_API int dlb_net_step_indices(dlb_net* net, const int64_t* indices, int64_t n
 DLB_API int dlb_net_step_host(dlb_net* net, const void* inputs, const void* refs, int64_t n, double learning_rate, int cost_id,
                               double reg_factor, double* cost_out);
 
+/* The same step without the final synchronisation: the host->device copy of this batch (on a copy stream, into the other
+ * half of a staging double buffer), the step and the device->host copy of its cost into *cost_out (pinned memory) are
+ * left in flight, so that consecutive calls overlap copy and compute.  The host buffers must stay valid and unchanged until
+ * dlb_context_synchronize(); *cost_out is defined after it. */
+DLB_API int dlb_net_step_host_async(dlb_net* net, const void* inputs, const void* refs, int64_t n, double learning_rate, int cost_id,
+                                    double reg_factor, double* cost_out);
+
 /* Forward + cost derivative + backward on a host batch WITHOUT the update; the traces stay on the device for
  * dlb_net_read.  `scale` is applied to the previous content of the gradient buffer (gradient_scale_factor). */
 DLB_API int dlb_net_forward_backward_host(dlb_net* net, const void* inputs, const void* refs, int64_t n, int cost_id, double scale);

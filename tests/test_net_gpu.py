@@ -190,3 +190,29 @@ def test_train_steps_equals_learn_and_graph_replay_is_exact(real):
     perms = dl.shuffle_sequence(9, 64, 3)
     orc.learn(x, y, 8, 3, 0.05, cost, 0.2, threads=1, perms=perms)
     H.assert_close("parameters", results[0], orc.get_params(), real, rtol_mult=20)
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_async_host_steps_equal_sync_host_steps(real):
+    """dlb_net_step_host_async (copy of step i+1 overlapped with step i, graph replay per staging half) must give the
+    same parameters and the same per-step costs as the synchronous calls."""
+    specs, cost = NETS["mini_lenet"]
+    orc, gpu_a = H.make_pair(specs, real, seed=61)
+    _, gpu_s = H.make_pair(specs, real, seed=61)
+    n, steps = 16, 9
+    batches = [H.synthetic_batch(orc, n, real, seed=70 + i, lo=0.0, hi=1.0) for i in range(steps)]
+    hx = dl.pinned_array((steps, n, orc.in_sizes[0]), gpu_a.dtype); hy = dl.pinned_array((steps, n, orc.out_sizes[-1]), gpu_a.dtype)
+    for i, (x, y) in enumerate(batches):
+        hx[i] = x; hy[i] = y
+    costs = dl.pinned_array((steps,), np.float64)
+    costs[:] = -1
+    for i in range(steps):
+        gpu_a.step_host_async(hx[i], hy[i], 0.05, dl.CostFunctionId(cost), 0.01, costs[i:i + 1])
+    gpu_a.ctx.synchronize()
+    sync_costs = [gpu_s.step_host(hx[i], hy[i], 0.05, dl.CostFunctionId(cost), 0.01) for i in range(steps)]
+    assert np.array_equal(gpu_a.get_params(), gpu_s.get_params())
+    assert np.allclose(costs, sync_costs, rtol=1e-12)
+    perm = np.arange(n, dtype=np.int64)[None, :]
+    for x, y in batches:   # oracle: one learn call per batch with reg_factor = lambda / n
+        orc.learn(x, y, n, 1, 0.05, cost, 0.01 * n, threads=1, perms=perm)
+    H.assert_close("parameters after 9 host steps", gpu_a.get_params(), orc.get_params(), real, rtol_mult=20)
