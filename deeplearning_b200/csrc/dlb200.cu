@@ -617,7 +617,7 @@ struct NetT final : dlb_net {
         if (plan.has_cp) {
             g_tag_layer = 0;
             const auto& Y = layers[0];
-            const int grid = std::min(B, 2 * kNumSMs);
+            const int grid = std::min((int)ceil_div(B, plan.cp.spc), kNumSMs);
             conv_pool_forward<R>(st, plan.cp, grid, x, gather_base, cursor, params + Y.param_off, params + Y.param_off + Y.bias_n,
                                  out[1], imap[1], B);
             l = 2;

@@ -46,77 +46,124 @@ __device__ __forceinline__ const int* resolve_gather(const int* gather_base, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Convolution (stride 1) + untied bias + activation + PH x PW max/min pooling.
-// One CTA walks over samples; a thread owns one pooled position and FPT filters: it keeps the (KH+PH-1)x(KW+PW-1)
-// input patch in registers and reads the filter taps as shared-memory broadcasts.
-// smem: filters [F][K] | zero-padded input [C][Hp][Wp]; the untied bias is read through the read-only path
+// Convolution (stride 1) + untied bias + activation + 2 x 2 max/min pooling.
+// One CTA walks over groups of `spc` samples.  A thread owns PP horizontally adjacent pooled positions and FPT filters of
+// one sample: it keeps the (KH+1) x (KW+2*PP-1) input patch in registers, reads every filter tap once (shared-memory
+// broadcast) for its 4*PP convolution outputs, and reads the untied bias through the read-only path.  The activation and
+// the pooling operator are compile-time in the epilogue (one uniform switch per sample, no per-element branches).
+// smem: filters [F][K] | `spc` zero-padded input images [C][Hp][Wp]
 // ---------------------------------------------------------------------------------------------------------------
-template <class R, int KH, int KW, int PH, int PW, int FPT, int TMAX>
-__global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __restrict__ x, const int* __restrict__ gather_base, const int* __restrict__ cursor,
-                                         const R* __restrict__ bias, const R* __restrict__ filt, R* __restrict__ pooled,
-                                         int* __restrict__ map, int B, ConvPoolGeom g, int act, int is_max) {
+template <class R, int ACT> __device__ __forceinline__ R activation_ct(R z) {
+    if (ACT == DLB_ACT_SIGMOID) return R(1) / (R(1) + dl_exp<R>(-z));
+    if (ACT == DLB_ACT_TANH) return dl_tanh<R>(z);
+    if (ACT == DLB_ACT_RELU) return z > R(0) ? z : R(0);
+    return z;
+}
+
+template <class R, int FPT, int PP, int ACT, bool IS_MAX>
+__device__ __forceinline__ void conv_pool_epilogue(const R (&acc)[FPT][2][2 * PP], const R* __restrict__ bias, R* __restrict__ pooled,
+                                                   int* __restrict__ map, const ConvPoolGeom& g, int fs, int py, int pxg, size_t b) {
+#pragma unroll
+    for (int fi = 0; fi < FPT; ++fi) {
+        const int f = fs * FPT + fi;
+        if (f >= g.F) continue;
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {
+            const int px = pxg * PP + pp;
+            if (px >= g.POW) continue;
+            R best = IS_MAX ? -real_limits<R>::max() : real_limits<R>::max();
+            int best_id = -1;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int id = (f * g.OH + py * 2 + dy) * g.OW + px * 2 + dx;
+                    const R v = activation_ct<R, ACT>(acc[fi][dy][pp * 2 + dx] + __ldg(bias + id));
+                    if (IS_MAX ? (best < v) : (best > v)) { best = v; best_id = id; }   // strict: the first wins ties
+                }
+            const size_t o = (b * g.F + f) * g.NPOS + py * g.POW + px;
+            pooled[o] = best;
+            map[o] = best_id;
+        }
+    }
+}
+
+template <class R, int KH, int KW, int FPT, int PP, int TMAX>
+__global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __restrict__ x, const int* __restrict__ gather_base,
+                                                                    const int* __restrict__ cursor, const R* __restrict__ bias,
+                                                                    const R* __restrict__ filt, R* __restrict__ pooled, int* __restrict__ map,
+                                                                    int B, ConvPoolGeom g, int act, int is_max, int spc, int tps) {
     DLB_DYNAMIC_SMEM(R, smem);
     R* filt_s = smem;
-    R* x_s = filt_s + g.F * g.K;
+    const int img = g.C * g.Hp * g.Wp;
+    R* x_all = filt_s + g.F * g.K;
     const int* gather = resolve_gather(gather_base, cursor);
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < g.F * g.K; i += nt) filt_s[i] = filt[i];
-    for (int i = tid; i < g.C * g.Hp * g.Wp; i += nt) x_s[i] = R(0);   // the border stays zero (padding)
+    for (int i = tid; i < spc * img; i += nt) x_all[i] = R(0);   // the borders stay zero (padding)
     __syncthreads();
 
-    const int fs = tid / g.NPOS, pos = tid - fs * g.NPOS;
-    const bool active = fs * FPT < g.F;
-    const int py = pos / g.POW, px = pos - py * g.POW;
-    const int HW = g.H * g.W;
-    constexpr int PR = KH + PH - 1, PC = KW + PW - 1;
+    const int slot = tid / tps, lt = tid - slot * tps;
+    const int PGW = (g.POW + PP - 1) / PP, NPG = g.POH * PGW;
+    const int fs = lt / NPG, pg = lt - fs * NPG;
+    const int py = pg / PGW, pxg = pg - py * PGW;
+    const bool active = slot < spc && fs * FPT < g.F;
+    const R* x_s = x_all + (slot < spc ? slot : 0) * img;
+    const int HW = g.H * g.W, n_in = g.C * HW;
+    constexpr int PR = KH + 1, PC = KW + 2 * PP - 1;
 
-    // The next sample's input is fetched into registers (XPT values per thread) while the current one is computed.
+    // The next group's inputs are fetched into registers while the current group is computed.
     constexpr int XPT = 4;
-    const int n_in = g.C * HW;
-    const bool prefetch = n_in <= XPT * nt;
+    const int n_all = spc * n_in;
+    const bool prefetch = n_all <= XPT * nt;
     R xr[XPT];
-    auto fetch = [&](int b) {
-        const R* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
-#pragma unroll
-        for (int j = 0; j < XPT; ++j) { const int i = tid + j * nt; xr[j] = i < n_in ? __ldg(xs + i) : R(0); }
-    };
-    auto stage = [&]() {
+    auto fetch = [&](int b0) {
 #pragma unroll
         for (int j = 0; j < XPT; ++j) {
             const int i = tid + j * nt;
-            if (i < n_in) {
-                const int c = i / HW, r = i - c * HW;
-                const int yy = r / g.W, xx = r - yy * g.W;
-                x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xr[j];
-            }
+            const int sm = i / n_in, e = i - sm * n_in;
+            const int b = b0 + sm;
+            xr[j] = (i < n_all && b < B) ? __ldg(x + (size_t)(gather ? gather[b] : b) * n_in + e) : R(0);
         }
     };
-    if (prefetch && (int)blockIdx.x < B) fetch(blockIdx.x);
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    auto stage_one = [&](int i, R v) {
+        const int sm = i / n_in, e = i - sm * n_in;
+        const int c = e / HW, r = e - c * HW;
+        const int yy = r / g.W, xx = r - yy * g.W;
+        x_all[sm * img + (c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = v;
+    };
+    const int stride = gridDim.x * spc;
+    if (prefetch && (int)blockIdx.x * spc < B) fetch(blockIdx.x * spc);
+    for (int b0 = blockIdx.x * spc; b0 < B; b0 += stride) {
         if (prefetch) {
-            stage();
-            if (b + (int)gridDim.x < B) fetch(b + gridDim.x);
+#pragma unroll
+            for (int j = 0; j < XPT; ++j) { const int i = tid + j * nt; if (i < n_all) stage_one(i, xr[j]); }
+            if (b0 + stride < B) fetch(b0 + stride);
         } else {
-            const R* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
-            for (int i = tid; i < n_in; i += nt) {
-                const int c = i / HW, r = i - c * HW;
-                const int yy = r / g.W, xx = r - yy * g.W;
-                x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xs[i];
+            for (int i = tid; i < n_all; i += nt) {
+                const int b = b0 + i / n_in;
+                stage_one(i, b < B ? x[(size_t)(gather ? gather[b] : b) * n_in + (i % n_in)] : R(0));
             }
         }
         __syncthreads();
-        if (active) {
-            R acc[FPT][PH * PW];
+        const int b = b0 + slot;
+        if (active && b < B) {
+            R acc[FPT][2][2 * PP];
 #pragma unroll
             for (int fi = 0; fi < FPT; ++fi)
 #pragma unroll
-                for (int q = 0; q < PH * PW; ++q) acc[fi][q] = R(0);
+                for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                    for (int q = 0; q < 2 * PP; ++q) acc[fi][dy][q] = R(0);
             for (int c = 0; c < g.C; ++c) {
                 R p[PR][PC];
 #pragma unroll
                 for (int r = 0; r < PR; ++r)
 #pragma unroll
-                    for (int s = 0; s < PC; ++s) p[r][s] = x_s[(c * g.Hp + py * PH + r) * g.Wp + px * PW + s];
+                    for (int q = 0; q < PC; ++q) {
+                        const int col = pxg * (2 * PP) + q;
+                        p[r][q] = col < g.Wp ? x_s[(c * g.Hp + py * 2 + r) * g.Wp + col] : R(0);
+                    }
 #pragma unroll
                 for (int fi = 0; fi < FPT; ++fi) {
                     const int f = fs * FPT + fi;
@@ -127,31 +174,24 @@ __global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __r
                         for (int kx = 0; kx < KW; ++kx) {
                             const R wv = w[ky * KW + kx];
 #pragma unroll
-                            for (int dy = 0; dy < PH; ++dy)
+                            for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                                for (int dx = 0; dx < PW; ++dx) acc[fi][dy * PW + dx] += p[dy + ky][dx + kx] * wv;
+                                for (int q = 0; q < 2 * PP; ++q) acc[fi][dy][q] += p[dy + ky][q + kx] * wv;
                         }
                 }
             }
-#pragma unroll
-            for (int fi = 0; fi < FPT; ++fi) {
-                const int f = fs * FPT + fi;
-                if (f >= g.F) continue;
-                R best = is_max ? -real_limits<R>::max() : real_limits<R>::max();
-                int best_id = -1;
-#pragma unroll
-                for (int dy = 0; dy < PH; ++dy)
-#pragma unroll
-                    for (int dx = 0; dx < PW; ++dx) {
-                        const int id = (f * g.OH + py * PH + dy) * g.OW + px * PW + dx;
-                        R d;
-                        const R v = apply_activation<R>(act, acc[fi][dy * PW + dx] + __ldg(bias + id), d);   // untied bias: L1/L2 resident
-                        if (is_max ? (best < v) : (best > v)) { best = v; best_id = id; }
-                    }
-                const size_t o = ((size_t)b * g.F + f) * g.NPOS + pos;
-                pooled[o] = best;
-                map[o] = best_id;
+#define DLB_EPI(ACT)                                                                                               \
+            do {                                                                                                       \
+                if (is_max) conv_pool_epilogue<R, FPT, PP, ACT, true>(acc, bias, pooled, map, g, fs, py, pxg, (size_t)b);  \
+                else conv_pool_epilogue<R, FPT, PP, ACT, false>(acc, bias, pooled, map, g, fs, py, pxg, (size_t)b);        \
+            } while (0)
+            switch (act) {
+            case DLB_ACT_RELU: DLB_EPI(DLB_ACT_RELU); break;
+            case DLB_ACT_SIGMOID: DLB_EPI(DLB_ACT_SIGMOID); break;
+            case DLB_ACT_TANH: DLB_EPI(DLB_ACT_TANH); break;
+            default: DLB_EPI(DLB_ACT_LINEAR); break;
             }
+#undef DLB_EPI
         }
         __syncthreads();
     }
@@ -497,6 +537,7 @@ struct ConvPoolPlan {
     bool ok = false;
     ConvPoolGeom g{};
     int KH = 0, KW = 0, fpt = 1, wpl = 1, act = 0, is_max = 1;
+    int pp = 1, spc = 1, tps = 0;     // forward: pooled positions per thread, samples per CTA iteration, threads per sample
     int fwd_threads = 0, bwd_threads = 0;
     size_t fwd_smem_elems = 0, bwd_smem_elems = 0;
     int n_par = 0;
@@ -521,14 +562,19 @@ inline ConvPoolPlan plan_conv_pool(const dlb_layer_spec& c, const dlb_layer_spec
     g.Hp = g.H + 2 * g.ph; g.Wp = g.W + 2 * g.pw; g.K = g.C * c.win_h * c.win_w; g.NPOS = g.POH * g.POW;
     if (g.POH < 1 || g.POW < 1 || g.NPOS > 256) return pl;
     pl.KH = c.win_h; pl.KW = c.win_w; pl.act = c.activation; pl.is_max = p.pool_type == DLB_POOL_MAX;
+    pl.pp = g.POW >= 2 ? 2 : 1;
+    const int npg = g.POH * ceil_div(g.POW, pl.pp);
+    pl.fpt = 1;
     for (int fpt : {8, 5, 4, 2, 1})
-        if (g.F % fpt == 0 && (long)g.NPOS * (g.F / fpt) <= 1024) { pl.fpt = fpt; break; }
-    if ((long)g.NPOS * ceil_div(g.F, pl.fpt) > 1024) return pl;
-    pl.fwd_threads = ceil_div(g.NPOS * ceil_div(g.F, pl.fpt), 32) * 32;
+        if (g.F % fpt == 0 && (long)npg * (g.F / fpt) <= 640) { pl.fpt = fpt; break; }
+    pl.tps = npg * ceil_div(g.F, pl.fpt);
+    if (pl.tps > 640) return pl;
+    pl.spc = std::max(1, std::min(4, 640 / pl.tps));
+    pl.fwd_threads = ceil_div(pl.spc * pl.tps, 32) * 32;
     pl.bwd_threads = 32 * g.F;
     const int need_wpl = ceil_div(g.NPOS, 32);
     pl.wpl = need_wpl <= 1 ? 1 : need_wpl <= 2 ? 2 : need_wpl <= 5 ? 5 : 8;
-    pl.fwd_smem_elems = (size_t)g.F * g.K + (size_t)g.C * g.Hp * g.Wp;
+    pl.fwd_smem_elems = (size_t)g.F * g.K + (size_t)pl.spc * g.C * g.Hp * g.Wp;
     pl.bwd_smem_elems = (size_t)g.C * g.Hp * g.Wp;
     if (pl.fwd_smem_elems * real_bytes > 200 * 1024) return pl;
     pl.n_par = g.F * g.OH * g.OW + g.F * g.K;
@@ -541,14 +587,18 @@ void conv_pool_forward_fpt(cudaStream_t st, const ConvPoolPlan& pl, int grid, co
                            const R* bias, const R* filt, R* pooled, int* map, int B) {
     const size_t smem = pl.fwd_smem_elems * sizeof(R);
     const dim3 gd((unsigned)grid), bd((unsigned)pl.fwd_threads);
-#define DLB_CPF2(FPT, TMAX)                                                                                                    \
-    DLB_LAUNCH_SMEM((conv_pool_forward_kernel<R, KH, KW, 2, 2, FPT, TMAX>), gd, bd, smem, st, x, gather_base, cursor, bias, filt,   \
-                    pooled, map, B, pl.g, pl.act, pl.is_max)
-#define DLB_CPF(FPT)                                          \
-    do {                                                      \
-        if (pl.fwd_threads <= 256) DLB_CPF2(FPT, 256);        \
-        else if (pl.fwd_threads <= 640) DLB_CPF2(FPT, 640);   \
-        else DLB_CPF2(FPT, 1024);                             \
+#define DLB_CPF3(FPT, PP, TMAX)                                                                                                  \
+    DLB_LAUNCH_SMEM((conv_pool_forward_kernel<R, KH, KW, FPT, PP, TMAX>), gd, bd, smem, st, x, gather_base, cursor, bias, filt,     \
+                    pooled, map, B, pl.g, pl.act, pl.is_max, pl.spc, pl.tps)
+#define DLB_CPF2(FPT, PP)                                          \
+    do {                                                           \
+        if (pl.fwd_threads <= 320) DLB_CPF3(FPT, PP, 320);         \
+        else DLB_CPF3(FPT, PP, 640);                               \
+    } while (0)
+#define DLB_CPF(FPT)                                 \
+    do {                                             \
+        if (pl.pp == 2) DLB_CPF2(FPT, 2);            \
+        else DLB_CPF2(FPT, 1);                       \
     } while (0)
     switch (pl.fpt) {
     case 8: DLB_CPF(8); break;
@@ -559,6 +609,7 @@ void conv_pool_forward_fpt(cudaStream_t st, const ConvPoolPlan& pl, int grid, co
     }
 #undef DLB_CPF
 #undef DLB_CPF2
+#undef DLB_CPF3
 }
 
 template <class R>
