@@ -53,6 +53,18 @@ __device__ __forceinline__ const int* resolve_gather(const int* gather_base, con
 // the pooling operator are compile-time in the epilogue (one uniform switch per sample, no per-element branches).
 // smem: filters [F][K] | `spc` zero-padded input images [C][Hp][Wp]
 // ---------------------------------------------------------------------------------------------------------------
+// 16-byte shared-memory loads of a run of fp32 / fp64 values (the address must be 16-byte aligned).
+template <int N> __device__ __forceinline__ void lds_vec(const float* p, float (&d)[N], int off) {
+    static_assert(N % 4 == 0, "whole float4 runs");
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) { const float4 v = *reinterpret_cast<const float4*>(p + 4 * i); d[off + 4 * i] = v.x; d[off + 4 * i + 1] = v.y; d[off + 4 * i + 2] = v.z; d[off + 4 * i + 3] = v.w; }
+}
+template <int N> __device__ __forceinline__ void lds_vec(const double* p, double (&d)[N], int off) {
+    static_assert(N % 2 == 0, "whole double2 runs");
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) { const double2 v = *reinterpret_cast<const double2*>(p + 2 * i); d[off + 2 * i] = v.x; d[off + 2 * i + 1] = v.y; }
+}
+
 template <class R, int ACT> __device__ __forceinline__ R activation_ct(R z) {
     if (ACT == DLB_ACT_SIGMOID) return R(1) / (R(1) + dl_exp<R>(-z));
     if (ACT == DLB_ACT_TANH) return dl_tanh<R>(z);
@@ -111,6 +123,8 @@ __global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __r
     const R* x_s = x_all + (slot < spc ? slot : 0) * img;
     const int HW = g.H * g.W, n_in = g.C * HW;
     constexpr int PR = KH + 1, PC = KW + 2 * PP - 1;
+    // whole-vector patch rows need 16-byte aligned row starts: images, rows and the thread's first column
+    const bool vec_rows = PP == 2 && ((g.Wp * sizeof(R)) % 16 == 0) && ((img * sizeof(R)) % 16 == 0) && (((size_t)g.F * g.K * sizeof(R)) % 16 == 0);
 
     // The next group's inputs are fetched into registers while the current group is computed.
     constexpr int XPT = 4;
@@ -156,14 +170,18 @@ __global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __r
 #pragma unroll
                     for (int q = 0; q < 2 * PP; ++q) acc[fi][dy][q] = R(0);
             for (int c = 0; c < g.C; ++c) {
-                R p[PR][PC];
+                constexpr int PCV = (PC + 3) / 4 * 4;   // patch row rounded up to whole 16-byte vectors
+                R p[PR][PCV];
+                const R* prow = x_s + (c * g.Hp + py * 2) * g.Wp + pxg * (2 * PP);
+                if (vec_rows) {   // conflict-free 16-byte loads (lanes read consecutive 16-byte words)
 #pragma unroll
-                for (int r = 0; r < PR; ++r)
+                    for (int r = 0; r < PR; ++r) lds_vec<PCV>(prow + r * g.Wp, p[r], 0);
+                } else {
 #pragma unroll
-                    for (int q = 0; q < PC; ++q) {
-                        const int col = pxg * (2 * PP) + q;
-                        p[r][q] = col < g.Wp ? x_s[(c * g.Hp + py * 2 + r) * g.Wp + col] : R(0);
-                    }
+                    for (int r = 0; r < PR; ++r)
+#pragma unroll
+                        for (int q = 0; q < PC; ++q) p[r][q] = (pxg * (2 * PP) + q < g.Wp) ? prow[r * g.Wp + q] : R(0);
+                }
 #pragma unroll
                 for (int fi = 0; fi < FPT; ++fi) {
                     const int f = fs * FPT + fi;
@@ -285,13 +303,15 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_kernel(const 
 #pragma unroll
             for (int q = 0; q < PH * PW; ++q) db[wi][q] += (q == sel) ? gval : R(0);
             if (gval != R(0)) {   // the reference skips zero factors as well (Tensor.cpp:484-486)
+                const R* base = x_s + oy * g.Wp + ox;
 #pragma unroll
                 for (int c = 0; c < C; ++c)
 #pragma unroll
-                    for (int ky = 0; ky < KH; ++ky)
+                    for (int ky = 0; ky < KH; ++ky) {
+                        const R* row = base + (c * g.Hp + ky) * g.Wp;
 #pragma unroll
-                        for (int kx = 0; kx < KW; ++kx)
-                            dk[(c * KH + ky) * KW + kx] += x_s[(c * g.Hp + oy + ky) * g.Wp + ox + kx] * gval;
+                        for (int kx = 0; kx < KW; ++kx) dk[(c * KH + ky) * KW + kx] += row[kx] * gval;
+                    }
             }
         }
         __syncthreads();
@@ -574,7 +594,7 @@ inline ConvPoolPlan plan_conv_pool(const dlb_layer_spec& c, const dlb_layer_spec
     pl.bwd_threads = 32 * g.F;
     const int need_wpl = ceil_div(g.NPOS, 32);
     pl.wpl = need_wpl <= 1 ? 1 : need_wpl <= 2 ? 2 : need_wpl <= 5 ? 5 : 8;
-    pl.fwd_smem_elems = (size_t)g.F * g.K + (size_t)pl.spc * g.C * g.Hp * g.Wp;
+    pl.fwd_smem_elems = (size_t)g.F * g.K + (size_t)pl.spc * g.C * g.Hp * g.Wp + 8 /*vector over-read of the last patch row*/;
     pl.bwd_smem_elems = (size_t)g.C * g.Hp * g.Wp;
     if (pl.fwd_smem_elems * real_bytes > 200 * 1024) return pl;
     pl.n_par = g.F * g.OH * g.OW + g.F * g.K;
@@ -593,6 +613,7 @@ void conv_pool_forward_fpt(cudaStream_t st, const ConvPoolPlan& pl, int grid, co
 #define DLB_CPF2(FPT, PP)                                          \
     do {                                                           \
         if (pl.fwd_threads <= 320) DLB_CPF3(FPT, PP, 320);         \
+        else if (pl.fwd_threads <= 576) DLB_CPF3(FPT, PP, 576);    \
         else DLB_CPF3(FPT, PP, 640);                               \
     } while (0)
 #define DLB_CPF(FPT)                                 \
