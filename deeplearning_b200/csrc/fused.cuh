@@ -123,8 +123,11 @@ __global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __r
     const R* x_s = x_all + (slot < spc ? slot : 0) * img;
     const int HW = g.H * g.W, n_in = g.C * HW;
     constexpr int PR = KH + 1, PC = KW + 2 * PP - 1;
-    // whole-vector patch rows need 16-byte aligned row starts: images, rows and the thread's first column
-    const bool vec_rows = PP == 2 && ((g.Wp * sizeof(R)) % 16 == 0) && ((img * sizeof(R)) % 16 == 0) && (((size_t)g.F * g.K * sizeof(R)) % 16 == 0);
+    // Whole-vector (16-byte) patch rows are conflict-free but cost registers: measured on B200 the kernel then spills
+    // (96-register cap at 576 threads) and is slower (325 vs 284 us at B=8192), so the scalar rows stay the default.
+    constexpr bool kVectorRows = false;
+    const bool vec_rows = kVectorRows && PP == 2 && ((g.Wp * sizeof(R)) % 16 == 0) && ((img * sizeof(R)) % 16 == 0) &&
+                          (((size_t)g.F * g.K * sizeof(R)) % 16 == 0);
 
     // The next group's inputs are fetched into registers while the current group is computed.
     constexpr int XPT = 4;

@@ -216,3 +216,21 @@ def test_async_host_steps_equal_sync_host_steps(real):
     for x, y in batches:   # oracle: one learn call per batch with reg_factor = lambda / n
         orc.learn(x, y, n, 1, 0.05, cost, 0.01 * n, threads=1, perms=perm)
     H.assert_close("parameters after 9 host steps", gpu_a.get_params(), orc.get_params(), real, rtol_mult=20)
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_cifar_deep_net_matches_oracle(real):
+    """BASELINE configs[2] (3 conv+pool stages on 3x32x32, ReLU, L2) at a small batch: layer traces of the unfused
+    operators and two regularised training steps (generic path: the net is outside the fused grammar)."""
+    specs = ob.cifar_specs()
+    orc, gpu = H.make_pair(specs, real, seed=81)
+    assert gpu.describe_plan().startswith("unfused")
+    x, y = H.synthetic_batch(orc, 3, real, seed=82, lo=0.0, hi=1.0)
+    compare_traces(orc, gpu, x, y, ob.CROSS_ENTROPY, real)
+    gpu.set_dataset(x, y)
+    perm = np.array([[2, 0, 1], [1, 2, 0]], np.int64)
+    orc.learn(x, y, 3, 2, 0.05, ob.CROSS_ENTROPY, 0.3, threads=1, perms=perm)
+    for e in range(2):
+        gpu.step_indices(perm[e], 0.05, dl.CostFunctionId.CROSS_ENTROPY, reg_factor=0.3 / 3)
+    H.assert_close("cifar parameters after two steps", gpu.get_params(), orc.get_params(), real, rtol_mult=20)
+    assert np.array_equal(gpu.predict(x), orc.eval(x))
