@@ -225,8 +225,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--real", default="f32", choices=["f32", "f64"])
     ap.add_argument("--batch", type=int, default=0, help="override the (global) mini-batch size")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="multi-GPU gradient exchange")
     args = ap.parse_args()
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("DLB_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,9 +239,10 @@ def main():
     batch = args.batch or (256 if n_gpus == 1 else 8192)
     workload = ("LeNet-style CNN: CLayer 5x5x20 ReLU -> PLayer max 2x2 -> NLayer 100 ReLU -> NLayer 10 softmax, cross-entropy, "
                 + (f"mini-batch {batch}, 1 B200 (BASELINE configs[1])" if n_gpus == 1 else
-                   f"data-parallel, global mini-batch {batch} sharded over {n_gpus} B200 with NCCL gradient all-reduce (BASELINE configs[4])"))
+                   f"data-parallel, global mini-batch {batch} sharded over {n_gpus} B200, per-step gradient all-reduce (BASELINE configs[4])"))
     config = {"workload": workload, "global_batch": batch, "n_items": N_ITEMS, "lr": LR, "lambda": LAMBDA,
-              "parallelism": f"dp{n_gpus}", "l2_policy": "inputs larger than L2: 65536-item resident data set (205 MB f32), "
+              "parallelism": f"dp{n_gpus}", "collective": ("none" if n_gpus == 1 else
+                                                            "fused peer-memory reduce+update kernel over NVLink" if args.collective == "p2p" else "ncclAllReduce + update kernel"), "l2_policy": "inputs larger than L2: 65536-item resident data set (205 MB f32), "
               "each step gathers a fresh slice of the epoch permutation; no explicit flush"}
     sz = 4 if args.real == "f32" else 8
 
@@ -268,10 +271,14 @@ def main():
     ctx = dl.Context(device=local_rank)
     net = dl.lenet(real=args.real, context=ctx)
     net.init_params(seed=0)
-    if world > 1:
+    if world > 1 and args.collective == "nccl":
         uid = [dl.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         net.set_distributed(rank, world, uid[0])
+    elif world > 1:   # default: fused reduce + update over NVLink peer memory (one kernel per rank, no NCCL on the step)
+        handles = [None] * world
+        dist.all_gather_object(handles, net.p2p_export())
+        net.set_distributed_p2p(rank, world, handles)
     dtype = net.dtype
     x, y = synthetic_data(N_ITEMS, 784, 10, dtype)
     net.set_dataset(x, y)

@@ -257,6 +257,8 @@ struct dlb_net {
     virtual std::string describe_plan() = 0;
     virtual void enable_graphs(bool on) = 0;
     virtual void enable_tensor_cores(bool on) = 0;
+    virtual void p2p_export(void* handle64) = 0;
+    virtual void p2p_connect(int rank, int world, const void* handles) = 0;
 };
 
 namespace {
@@ -354,6 +356,13 @@ struct NetT final : dlb_net {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     bool hbuf_used[2] = {false, false};
     int hbuf = 0; int64_t hcap = 0;
+    // Peer-memory data parallelism (dlb_net_set_distributed_p2p): [publish 0 | publish 1 | flags] in one IPC-shared allocation
+    unsigned char* p2p_region = nullptr; size_t p2p_publish_bytes = 0;
+    std::vector<void*> p2p_peer_regions;      // opened peer mappings (index = rank; own entry = p2p_region)
+    unsigned long long p2p_step = 0;          // host mirror of *d_p2p_step (both advance once per step)
+    unsigned long long* d_p2p_step = nullptr;
+    bool p2p_on = false;
+    R* publish_buf(int parity) { return reinterpret_cast<R*>(p2p_region + (size_t)parity * p2p_publish_bytes); }
     bool overlap_enabled = true;
     const void* ws_stamp = nullptr;   // the context scratch the captured graphs point into
     bool graphs_enabled = true;
@@ -448,6 +457,12 @@ struct NetT final : dlb_net {
         for (int i = 0; i < 2; ++i) { if (ev_copied[i]) cudaEventDestroy(ev_copied[i]); if (ev_consumed[i]) cudaEventDestroy(ev_consumed[i]); }
 #endif
         for (int i = 0; i < 2; ++i) { dev_free(hstage_x[i]); dev_free(hstage_y[i]); }
+#ifndef DLB_CUDA_EMU
+        for (size_t r = 0; r < p2p_peer_regions.size(); ++r)
+            if (p2p_peer_regions[r] && p2p_peer_regions[r] != p2p_region) cudaIpcCloseMemHandle(p2p_peer_regions[r]);
+#endif
+        if (p2p_region) cudaFree(p2p_region);
+        dev_free(d_p2p_step);
         dev_free(cp_partial); dev_free(head_partial); dev_free(d_cursor);
         if (own_data) { dev_free(data_x); dev_free(data_y); }
 #ifndef DLB_CUDA_EMU
@@ -764,7 +779,7 @@ struct NetT final : dlb_net {
     }
 
     // Sums the partial gradients into the flat gradient buffer and (optionally) updates the parameters in the same pass.
-    void train_reduce_update(bool do_update, double lr, double reg_factor, int64_t batch_items, int advance) {
+    void train_reduce_update(bool do_update, double lr, double reg_factor, int64_t batch_items, int advance, bool publish = false) {
         ReduceSegments rs{};
         rs.count = 0;
         for (int l = 0; l < L(); ++l) {
@@ -791,8 +806,38 @@ struct NetT final : dlb_net {
             if (rs.partial[i]) n_partial += rs.end[i] - (i == 0 ? 0 : rs.end[i - 1]);
         const int partial_blocks = (int)ceil_div<long long>(n_partial, 16);
         DLB_LAUNCH((reduce_update_kernel<R>), dim3((unsigned)(partial_blocks + ceil_div<size_t>((size_t)n_params, 256))), dim3(256), ctx->stream,
-                   params, grads, (size_t)n_params, rs, partial_blocks, n_partial, do_update ? 1 : 0, static_cast<R>(1) + reg * l_rate,
+                   params, grads, publish ? publish_buf(0) : (R*)nullptr, p2p_publish_bytes / sizeof(R), (const unsigned long long*)d_p2p_step,
+                   (size_t)n_params, rs, partial_blocks, n_partial, do_update ? 1 : 0, static_cast<R>(1) + reg * l_rate,
                    l_rate * grad_norm, reg > static_cast<R>(0) ? 1 : 0, advance ? d_cursor : (int*)nullptr, advance);
+    }
+
+    // Data-parallel tail of a step whose local gradient sum is (or will be put) in `grads`: peer-memory kernel or NCCL.
+    // local_reduce: for the fused path, runs the partial-sum reduction into the published buffer first.
+    void distributed_finish(bool fused_partials, double lr, double reg_factor, int64_t global, int advance) {
+#ifndef DLB_CUDA_EMU
+        if (p2p_on) {
+            const int parity = (int)(p2p_step & 1);
+            ++p2p_step;
+            if (fused_partials) train_reduce_update(false, lr, reg_factor, global, 0, true);
+            else DLB_CUDA(cudaMemcpyAsync(publish_buf(parity), grads, (size_t)n_params * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
+            PeerTable pt{};
+            for (int r = 0; r < world; ++r) pt.region[r] = static_cast<const unsigned char*>(p2p_peer_regions[(size_t)r]);
+            pt.publish_bytes = p2p_publish_bytes;
+            const R l_rate = -static_cast<R>(lr);
+            const R reg = static_cast<R>(reg_factor);
+            const R grad_norm = static_cast<R>(1) / static_cast<R>(global);
+            g_tag_layer = -1;
+            TagScope tag_("p2p_reduce_update");
+            DLB_LAUNCH((p2p_reduce_update_kernel<R>), dim3(2 * kNumSMs), dim3(256), ctx->stream, params, grads, (size_t)n_params, pt, world, rank,
+                       (const unsigned long long*)d_p2p_step, segs, static_cast<R>(1) + reg * l_rate, l_rate * grad_norm,
+                       reg > static_cast<R>(0) ? 1 : 0, advance ? d_cursor : (int*)nullptr, advance);
+            DLB_LAUNCH((p2p_advance_kernel), dim3(1), dim3(1), ctx->stream, d_p2p_step);
+            return;
+        }
+#endif
+        if (fused_partials) train_reduce_update(false, lr, reg_factor, global, 0);
+        allreduce_gradient();
+        update(lr, reg_factor, global, advance);
     }
 
     void allreduce_gradient() {
@@ -808,8 +853,8 @@ struct NetT final : dlb_net {
     void update(double lr, double reg_factor, int64_t batch_items, int advance = 0) {
         if (advance) {   // keep the device-side cursor in step (the unfused path reads its gather slice from the host-computed pointer)
             ReduceSegments none{}; none.count = 1; none.end[0] = 0;
-            DLB_LAUNCH((reduce_update_kernel<R>), dim3(1), dim3(256), ctx->stream, params, grads, (size_t)0, none, 0, (long long)0, 0, R(0), R(0), 0,
-                       d_cursor, advance);
+            DLB_LAUNCH((reduce_update_kernel<R>), dim3(1), dim3(256), ctx->stream, params, grads, (R*)nullptr, (size_t)0,
+                       (const unsigned long long*)nullptr, (size_t)0, none, 0, (long long)0, 0, R(0), R(0), 0, d_cursor, advance);
         }
         const R l_rate = -static_cast<R>(lr);
         const R reg = static_cast<R>(reg_factor);
@@ -828,16 +873,11 @@ struct NetT final : dlb_net {
             ensure_capacity(mine);
             auto body = [&] {
                 train_forward_backward((int)mine, x, refs, gather_base, cursor, cost);
-                if (world <= 1) {
-                    train_reduce_update(true, lr, reg_factor, global, advance);
-                } else {
-                    train_reduce_update(false, lr, reg_factor, global, 0);
-                    allreduce_gradient();
-                    update(lr, reg_factor, global, advance);
-                }
+                if (world <= 1) train_reduce_update(true, lr, reg_factor, global, advance);
+                else distributed_finish(true, lr, reg_factor, global, advance);
             };
             // Only paths whose buffers are fixed replay a graph: the resident-data path (cursor-relative gather).
-            if (cursor && x == data_x) { run_graphed(StepKey{mine, global, lr, reg_factor, cost, x, 0}, body); return; }
+            if (cursor && x == data_x) { run_graphed(StepKey{mine, global, lr, reg_factor, cost, x, p2p_on ? -1 : 0}, body); return; }
             body();
             return;
         }
@@ -847,8 +887,8 @@ struct NetT final : dlb_net {
         } else {
             DLB_CUDA(cudaMemsetAsync(grads, 0, (size_t)n_params * sizeof(R), ctx->stream));
         }
-        allreduce_gradient();
-        update(lr, reg_factor, global, advance);
+        if (world > 1) distributed_finish(false, lr, reg_factor, global, advance);
+        else update(lr, reg_factor, global, advance);
     }
 
     void rank_slice(int64_t count, int64_t& first, int64_t& mine) const {
@@ -993,13 +1033,9 @@ struct NetT final : dlb_net {
                 DLB_LAUNCH((cost_sum_kernel<R>), dim3(1), dim3(256), ctx->stream, (const R*)out[(size_t)L() - 1], (const R*)sy,
                            (const int*)nullptr, (int)n, (int)outN(), cost, cost_dev);
             }
-            if (plan.ok && world <= 1) {
-                train_reduce_update(true, lr, reg_factor, n, 0);
-            } else {
-                if (plan.ok) train_reduce_update(false, lr, reg_factor, n, 0);
-                allreduce_gradient();
-                update(lr, reg_factor, n * world);
-            }
+            if (world > 1) distributed_finish(plan.ok, lr, reg_factor, n * world, 0);
+            else if (plan.ok) train_reduce_update(true, lr, reg_factor, n, 0);
+            else update(lr, reg_factor, n);
         };
         if (plan.ok) run_graphed(StepKey{n, n * world, lr, reg_factor, cost, sx, want_cost ? 1 : 2}, body);
         else body();
@@ -1056,6 +1092,50 @@ struct NetT final : dlb_net {
     }
     void enable_graphs(bool on) override { graphs_enabled = on; if (!on) drop_graphs(); }
     void enable_tensor_cores(bool on) override { use_tensor_cores = on; drop_graphs(); }
+
+    // Allocates the shared region [publish 0 | publish 1 | flags] and returns its CUDA IPC handle (64 bytes).
+    void p2p_export(void* handle64) override {
+#ifdef DLB_CUDA_EMU
+        (void)handle64; throw std::runtime_error("peer memory is not available");
+#else
+        use_device(ctx);
+        if (!p2p_region) {
+            p2p_publish_bytes = (((size_t)n_params * sizeof(R)) + 255) / 256 * 256;
+            const size_t total = 2 * p2p_publish_bytes + kMaxPeers * sizeof(unsigned long long);
+            DLB_CUDA(cudaMalloc((void**)&p2p_region, total));
+            DLB_CUDA(cudaMemset(p2p_region, 0, total));
+            d_p2p_step = dev_alloc<unsigned long long>(1);
+            DLB_CUDA(cudaMemset(d_p2p_step, 0, sizeof(unsigned long long)));
+        }
+        cudaIpcMemHandle_t h;
+        DLB_CUDA(cudaIpcGetMemHandle(&h, p2p_region));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::memcpy(handle64, &h, sizeof h);
+#endif
+    }
+
+    // handles: world x 64 bytes, index = rank (every rank's p2p_export result, gathered by the launcher's own plumbing).
+    void p2p_connect(int rank_, int world_, const void* handles) override {
+#ifdef DLB_CUDA_EMU
+        (void)rank_; (void)world_; (void)handles; throw std::runtime_error("peer memory is not available");
+#else
+        DLB_REQUIRE(p2p_region, "call dlb_net_p2p_export first");
+        DLB_REQUIRE(world_ >= 1 && world_ <= kMaxPeers && rank_ >= 0 && rank_ < world_ && handles, "Invalid rank / world size");
+        use_device(ctx);
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        drop_graphs();
+        p2p_peer_regions.assign((size_t)world_, nullptr);
+        for (int r = 0; r < world_; ++r) {
+            if (r == rank_) { p2p_peer_regions[(size_t)r] = p2p_region; continue; }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, static_cast<const unsigned char*>(handles) + 64 * (size_t)r, sizeof h);
+            DLB_CUDA(cudaIpcOpenMemHandle(&p2p_peer_regions[(size_t)r], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        rank = rank_; world = world_; p2p_on = world_ > 1; p2p_step = 0;
+        DLB_CUDA(cudaMemset(d_p2p_step, 0, sizeof(unsigned long long)));
+        DLB_CUDA(cudaMemset(p2p_region + 2 * p2p_publish_bytes, 0, kMaxPeers * sizeof(unsigned long long)));
+#endif
+    }
 
     void eval_host(const void* x, int64_t n, int32_t* classes, void* outputs) override {
         DLB_REQUIRE(x && n >= 0, "Invalid input.");
@@ -1412,6 +1492,13 @@ int dlb_net_set_distributed(dlb_net* net, int rank, int world, const void* uniqu
 #endif
         net->rank = rank; net->world = world;
     });
+}
+
+int dlb_net_p2p_export(dlb_net* net, void* handle_out_64_bytes) {
+    return guarded([&] { DLB_REQUIRE(net && handle_out_64_bytes, "null argument"); net->p2p_export(handle_out_64_bytes); });
+}
+int dlb_net_set_distributed_p2p(dlb_net* net, int rank, int world, const void* handles) {
+    return guarded([&] { DLB_REQUIRE(net, "null net"); net->p2p_connect(rank, world, handles); });
 }
 
 int dlb_shuffle_sequence(unsigned seed, int64_t n, int64_t epochs, int64_t* out) {

@@ -500,11 +500,13 @@ struct ReduceSegments {
 // thread adds the 16 sub-sums in a fixed order - deterministic, and ~chunks/16 dependent steps instead of `chunks`.
 // The remaining blocks own 256 elements each whose gradient is already final in `grads`.
 template <class R>
-__global__ void reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads, size_t n, ReduceSegments segs, int partial_blocks,
+__global__ void reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads, R* __restrict__ publish0, size_t publish_stride,
+                                     const unsigned long long* __restrict__ publish_counter, size_t n, ReduceSegments segs, int partial_blocks,
                                      long long n_partial_elems, int do_update, R param_scale, R grad_scale, int nontrivial_reg,
                                      int* __restrict__ cursor, int advance) {
     __shared__ R sub[16][17];
     if (blockIdx.x == 0 && threadIdx.x == 0 && cursor) *cursor += advance;   // every reader of the cursor ran earlier in the stream
+    R* publish = publish0 ? publish0 + (size_t)(*publish_counter & 1) * publish_stride : nullptr;   // the half peers read this step
     long long e; R gsum; int s = 0; bool active;
     if ((int)blockIdx.x < partial_blocks) {
         // the partial elements are enumerated segment by segment in flat order
@@ -535,14 +537,72 @@ __global__ void reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads, s
 #pragma unroll
         for (int q = 0; q < 16; ++q) gsum += sub[el][q];
         grads[e] = gsum;
+        if (publish) publish[e] = gsum;
     } else {
         e = (long long)(blockIdx.x - partial_blocks) * blockDim.x + threadIdx.x;
         if (e >= (long long)n) return;
         while (s < segs.count - 1 && e >= segs.end[s]) ++s;
         if (segs.partial[s]) return;     // owned by a partial block
         gsum = grads[e];
+        if (publish) publish[e] = gsum;
     }
     if (do_update) {
+        const bool reg = nontrivial_reg && segs.regularised[s];
+        const R xv = p[e];
+        p[e] = reg ? xv * param_scale + gsum * grad_scale : xv + gsum * grad_scale;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Data parallelism without NCCL on the step's critical path: ONE kernel per rank that (1) tells every peer "my local
+// gradient sum for step t is published" and waits for theirs (flags in peer memory, written over NVLink), (2) reads all
+// ranks' gradient buffers through peer pointers (NVLink P2P loads), adds them in rank order - so every rank computes the
+// bit-identical total - and (3) applies the SGD update to its own parameters in the same pass (ALayer.inl:97-122).
+// The published buffers are double-buffered by step parity: a rank can only be overwriting the buffer of step t when it
+// is at step t+2, which it cannot reach before every peer has passed the barrier of step t+1, i.e. finished reading
+// step t.  Replaces ncclAllReduce + sgd_update (a 1.2 MB message: latency-bound).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerTable {
+    const unsigned char* region[kMaxPeers];   // peer r's shared region: [publish 0 | publish 1 | flags[world]]
+    size_t publish_bytes;
+};
+
+// The step counter lives on the device so that a captured CUDA graph of the step stays valid from step to step: the
+// publish kernel and the peer kernel read it (parity = which half is published, value + 1 = the barrier ticket) and this
+// one-thread kernel, ordered after them in the stream, advances it.
+__global__ void p2p_advance_kernel(unsigned long long* counter) { *counter += 1; }
+
+template <class R>
+__global__ void p2p_reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads_total, size_t n, PeerTable peers, int world, int rank,
+                                         const unsigned long long* __restrict__ counter, UpdateSegments segs, R param_scale, R grad_scale,
+                                         int nontrivial_reg, int* __restrict__ cursor, int advance) {
+    const unsigned long long t = *counter;
+    const unsigned long long step = t + 1;
+    const size_t half = (size_t)(t & 1) * peers.publish_bytes;
+    // (1) cross-GPU barrier.  The local gradient was written by the previous kernel in this stream, so it is complete.
+    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+        __threadfence_system();
+        volatile unsigned long long* remote =
+            reinterpret_cast<unsigned long long*>(const_cast<unsigned char*>(peers.region[threadIdx.x]) + 2 * peers.publish_bytes) + rank;
+        *remote = step;
+    }
+    if ((int)threadIdx.x < world) {
+        volatile unsigned long long* mine =
+            reinterpret_cast<unsigned long long*>(const_cast<unsigned char*>(peers.region[rank]) + 2 * peers.publish_bytes) + threadIdx.x;
+        long long spin = 0;
+        while (*mine < step) { if (++spin > (1LL << 31)) __trap(); }   // bounded: a lost peer becomes a launch failure, not a hang
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && cursor) *cursor += advance;
+    // (2) + (3)
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        R gsum = R(0);
+        for (int r = 0; r < world; ++r) gsum += reinterpret_cast<const R*>(peers.region[r] + half)[e];   // rank order: identical on every rank
+        grads_total[e] = gsum;
+        int s = 0;
+        while (s < segs.count - 1 && (long long)e >= segs.end[s]) ++s;
         const bool reg = nontrivial_reg && segs.regularised[s];
         const R xv = p[e];
         p[e] = reg ? xv * param_scale + gsum * grad_scale : xv + gsum * grad_scale;

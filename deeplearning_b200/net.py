@@ -423,6 +423,22 @@ class Net:
         _capi.check(self.lib.dlb_net_set_distributed(self._handle(), rank, world_size, buf))
 
 
+def _p2p_export(net: "Net") -> bytes:
+    buf = C.create_string_buffer(64)
+    _capi.check(net.lib.dlb_net_p2p_export(net._handle(), buf))
+    return buf.raw
+
+
+def _p2p_connect(net: "Net", rank: int, world_size: int, handles) -> None:
+    blob = b"".join(handles)
+    assert len(blob) == 64 * world_size
+    _capi.check(net.lib.dlb_net_set_distributed_p2p(net._handle(), rank, world_size, C.create_string_buffer(blob, len(blob))))
+
+
+Net.p2p_export = _p2p_export
+Net.set_distributed_p2p = _p2p_connect
+
+
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _capi.check(_capi.load().dlb_nccl_get_unique_id(buf))

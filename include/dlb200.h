@@ -208,6 +208,14 @@ DLB_API int dlb_event_elapsed_ms(void* start, void* stop, double* ms_out); /* sy
 DLB_API int dlb_timing_enable(int on);
 DLB_API int dlb_timing_report(char* buf, int64_t cap);
 
+/* Data parallelism over NVLink peer memory instead of NCCL: every rank exports the CUDA IPC handle (64 bytes) of its
+ * gradient-exchange region, the launcher gathers the `world` handles (index = rank), every rank connects.  From then on the
+ * step ends with ONE kernel per rank that barriers with its peers through flags in peer memory, sums all ranks' gradients
+ * through peer pointers in rank order (bit-identical on every rank) and applies the update in the same pass.  All ranks
+ * must be on one node with peer access between their devices; call after every rank has called dlb_net_p2p_export. */
+DLB_API int dlb_net_p2p_export(dlb_net* net, void* handle_out_64_bytes);
+DLB_API int dlb_net_set_distributed_p2p(dlb_net* net, int rank, int world_size, const void* handles_world_x_64_bytes);
+
 /* The epoch permutations learn() would draw after reset_random_generator(seed): iota + one shuffle per epoch on
  * the same std::mt19937 (Net.inl:158-171, 223).  Host-only helper for tests and for reference-side callers. */
 DLB_API int dlb_shuffle_sequence(unsigned seed, int64_t n, int64_t epochs, int64_t* out);

@@ -45,13 +45,19 @@ p0 = H.synthetic_params(301130, specs, real, seed=1)
 rng = np.random.default_rng(2)
 x = rng.random((n, 784)).astype(ob.dtype_of(real)); y = ob.one_hot_labels(real, n)
 
+mode = os.environ["DLB_MODE"]
+
 def run(distributed):
     net = dl.Net([H.to_dl_spec(s) for s in specs], real=real, context=dl.Context(rank if distributed else 0))
     net.set_params(p0)
-    if distributed:
+    if distributed and mode == "nccl":
         uid = [dl.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         net.set_distributed(rank, world, uid[0])
+    elif distributed:   # NVLink peer memory: gather every rank's IPC handle
+        handles = [None] * world
+        dist.all_gather_object(handles, net.p2p_export())
+        net.set_distributed_p2p(rank, world, handles)
     net.reset_random_generator(seed)
     net.learn(x, y, batch, epochs, lr, dl.CostFunctionId.CROSS_ENTROPY, lam)
     return net.get_params()
@@ -71,8 +77,9 @@ dist.destroy_process_group()
 
 
 @pytest.mark.skipif(device_count() < 2, reason="needs at least 2 CUDA devices")
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
 @pytest.mark.parametrize("real", ["f32", "f64"])
-def test_two_gpu_learn_matches_single_gpu(tmp_path, real):
+def test_two_gpu_learn_matches_single_gpu(tmp_path, real, mode):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     with socket.socket() as s:
@@ -80,7 +87,7 @@ def test_two_gpu_learn_matches_single_gpu(tmp_path, real):
         port = s.getsockname()[1]
     procs = []
     for rank in range(2):
-        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", DLB_PORT=str(port), DLB_ROOT=ROOT, DLB_REAL=real)
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", DLB_PORT=str(port), DLB_ROOT=ROOT, DLB_REAL=real, DLB_MODE=mode)
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)

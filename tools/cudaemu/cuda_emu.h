@@ -224,3 +224,6 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) double2 { double x, y; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline void __threadfence_system() {}
+inline void __threadfence() {}
+inline void __trap() { std::abort(); }
