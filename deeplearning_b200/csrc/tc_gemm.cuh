@@ -41,12 +41,14 @@ namespace tc {
 
 constexpr int kBM = 128, kBN = 128, kBK = 32;
 constexpr int kStages = 2;                                 // hi/lo operand stages consumed by the tensor core
-constexpr int kRaw = 3;                                    // raw fp32 stages filled by cp.async (the prefetch depth)
+constexpr int kRaw = 2;                                    // raw fp32 stages filled by cp.async (the prefetch depth)
 constexpr int kTileBytes = kBM * kBK * 4;                  // 16 KiB: one raw, hi or lo tile of either operand
 constexpr int kStageBytes = 4 * kTileBytes;                // A_hi, A_lo, B_hi, B_lo
 constexpr int kRawBytes = 2 * kTileBytes;                  // A_raw, B_raw
-constexpr int kSmemBytes = kStages * kStageBytes + kRaw * kRawBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int kThreads = 160;
+constexpr int kEpiBytes = 4 * 32 * 33 * 4;                 // one padded 32 x 32 fp32 staging block per epilogue warp
+constexpr int kSmemBytes = kStages * kStageBytes + kRaw * kRawBytes + kEpiBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 288;                              // 4 producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int kAccCols = 2 * kBN;                          // two fp32 accumulators in tensor memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -223,28 +225,47 @@ __device__ __forceinline__ void transform_tile(const TcOperand& op, int o0, int 
     }
 }
 
+// Decodes a linear tile index into output-tile coordinates and its slice of the reduction.
+struct TileCoord { int i0, j0, kb, ke, nkb, z; };
+__device__ __forceinline__ TileCoord decode_tile(int t, int tiles_m, int tiles_n, int K, int k_per_split) {
+    TileCoord c;
+    const int per_z = tiles_m * tiles_n;
+    c.z = t / per_z;
+    const int rem = t - c.z * per_z;
+    const int mi = rem / tiles_n, ni = rem - mi * tiles_n;
+    c.i0 = mi * kBM; c.j0 = ni * kBN;
+    c.kb = c.z * k_per_split;
+    c.ke = min(K, c.kb + k_per_split);
+    c.nkb = (c.ke - c.kb + kBK - 1) / kBK;
+    return c;
+}
+
+// Persistent kernel: CTA c processes tiles c, c + gridDim.x, ...  Three roles run concurrently on different tiles:
+// producers fill the operand ring for tile j+1 while the MMA lane accumulates tile j+1 into one tensor-memory
+// accumulator and the epilogue warps drain tile j from the other one.
 template <class EP>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_gemm_kernel(int M, int N, int K, int k_per_split, TcOperand a, TcOperand b, EP ep, float* __restrict__ partials) {
+tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, int n_tiles, int n_splits, TcOperand a, TcOperand b, EP ep,
+               float* __restrict__ partials) {
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* raw_ring = smem + kStages * kStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_ring + kRaw * kRawBytes);    // full[kStages], empty[kStages], tmem_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+    float* epi_stage = reinterpret_cast<float*>(raw_ring + kRaw * kRawBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(epi_stage) + kEpiBytes);
+    // bars: full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2]
+    uint64_t* bar_full = bars; uint64_t* bar_empty = bars + kStages;
+    uint64_t* bar_tfull = bars + 2 * kStages; uint64_t* bar_tempty = bars + 2 * kStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int i0 = blockIdx.y * kBM, j0 = blockIdx.x * kBN;
-    const int kb = blockIdx.z * k_per_split;
-    const int ke = min(K, kb + k_per_split);
-    const int n_kblocks = (ke - kb + kBK - 1) / kBK;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bars[s]), 128); mbar_init(smem_u32(&bars[kStages + s]), 1); }
-        mbar_init(smem_u32(&bars[2 * kStages]), 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), 128); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int q = 0; q < 2; ++q) { mbar_init(smem_u32(&bar_tfull[q]), 1); mbar_init(smem_u32(&bar_tempty[q]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {   // the MMA warp owns the tensor-memory allocation: kBN fp32 columns x 128 lanes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kBN) : "memory");
+    if (warp == 4) {   // the MMA warp owns the tensor-memory allocation: two accumulators of kBN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kAccCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -253,112 +274,148 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, TcOperand a, TcOperand b, E
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // ---------------- producers: cp.async ring (kRaw - 1 k-blocks in flight beyond the current), then hi/lo transform ----
-        TileOwner wa, wb;
-        owner_init(a, i0, M, tid, wa);
-        owner_init(b, j0, N, tid, wb);
+        // ---------------- producers: one continuous stream of k-blocks over all of this CTA's tiles ----------------
+        int nt_tile = blockIdx.x;            // tile of the next k-block to issue
+        int nt_k = 0;
+        TileCoord nc{};
+        TileOwner nwa, nwb;
+        auto open_next = [&]() {
+            if (nt_tile < n_tiles) {
+                nc = decode_tile(nt_tile, tiles_m, tiles_n, K, k_per_split);
+                owner_init(a, nc.i0, M, tid, nwa);
+                owner_init(b, nc.j0, N, tid, nwb);
+            }
+        };
+        open_next();
+        long long issued = 0;
+        auto issue_next = [&]() {            // issues one k-block (or nothing at the end of the stream) and commits a group
+            if (nt_tile < n_tiles) {
+                unsigned char* raw = raw_ring + (int)(issued % kRaw) * kRawBytes;
+                const int r0 = nc.kb + nt_k * kBK;
+                issue_tile(a, nwa, nc.i0, M, r0, nc.ke, tid, raw);
+                issue_tile(b, nwb, nc.j0, N, r0, nc.ke, tid, raw + kTileBytes);
+                ++issued;
+                if (++nt_k == nc.nkb) { nt_k = 0; nt_tile += gridDim.x; open_next(); }
+            }
+            cp_async_commit();
+        };
 #pragma unroll
-        for (int p = 0; p < kRaw - 1; ++p) {
-            if (p < n_kblocks) {
-                unsigned char* raw = raw_ring + p * kRawBytes;
-                issue_tile(a, wa, i0, M, kb + p * kBK, ke, tid, raw);
-                issue_tile(b, wb, j0, N, kb + p * kBK, ke, tid, raw + kTileBytes);
+        for (int p = 0; p < kRaw - 1; ++p) issue_next();
+        long long git = 0;                   // k-blocks consumed so far (stage / phase bookkeeping shared with the MMA lane)
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const TileCoord c = decode_tile(t, tiles_m, tiles_n, K, k_per_split);
+            for (int it = 0; it < c.nkb; ++it, ++git) {
+                cp_async_wait<kRaw - 2>();                          // this thread's copies of the current k-block have landed
+                // every producer's copies have landed, and every producer is done reading the raw slot refilled next
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                issue_next();
+                const int s = (int)(git % kStages);
+                const uint32_t phase = (uint32_t)((git / kStages) & 1);
+                mbar_wait(smem_u32(&bar_empty[s]), phase ^ 1);      // hi/lo stage free (first pass: returns at once)
+                const unsigned char* raw = raw_ring + (int)(git % kRaw) * kRawBytes;
+                unsigned char* st = smem + s * kStageBytes;
+                const int r0 = c.kb + it * kBK;
+                transform_tile(a, c.i0, M, r0, c.ke, tid, raw, st, st + kTileBytes);
+                transform_tile(b, c.j0, N, r0, c.ke, tid, raw + kTileBytes, st + 2 * kTileBytes, st + 3 * kTileBytes);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (UMMA) reads
+                mbar_arrive(smem_u32(&bar_full[s]));
             }
-            cp_async_commit();
-        }
-        for (int it = 0; it < n_kblocks; ++it) {
-            cp_async_wait<kRaw - 2>();                              // this thread's copies of k-block `it` have landed
-            // every producer's copies of k-block `it` have landed, and every producer is done reading the slot refilled next
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int nxt = it + kRaw - 1;
-            if (nxt < n_kblocks) {
-                unsigned char* rawn = raw_ring + (nxt % kRaw) * kRawBytes;
-                issue_tile(a, wa, i0, M, kb + nxt * kBK, ke, tid, rawn);
-                issue_tile(b, wb, j0, N, kb + nxt * kBK, ke, tid, rawn + kTileBytes);
-            }
-            cp_async_commit();
-            const int s = it % kStages;
-            const uint32_t phase = (it / kStages) & 1;
-            mbar_wait(smem_u32(&bars[kStages + s]), phase ^ 1);     // hi/lo stage free (first pass: returns at once)
-            const unsigned char* raw = raw_ring + (it % kRaw) * kRawBytes;
-            unsigned char* st = smem + s * kStageBytes;
-            const int r0 = kb + it * kBK;
-            transform_tile(a, i0, M, r0, ke, tid, raw, st, st + kTileBytes);
-            transform_tile(b, j0, N, r0, ke, tid, raw + kTileBytes, st + 2 * kTileBytes, st + 3 * kTileBytes);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (UMMA) reads
-            mbar_arrive(smem_u32(&bars[s]));
         }
         cp_async_wait<0>();
-        // ---------------- epilogue (same warps): TMEM lanes 32*warp .. 32*warp+31 ----------------
-        mbar_wait(smem_u32(&bars[2 * kStages]), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool split = gridDim.z > 1;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kBN; c0 += 32) {
-            if (j0 + c0 >= N) break;                                  // warp-uniform
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // 32 x 32 block: lane = row in registers -> shared (padded) -> lane = column, so that every warp-wide access of the
-            // epilogue (stores, bias / previous-activation loads) covers 128 contiguous bytes
-            float* tile = reinterpret_cast<float*>(raw_ring) + warp * (32 * 33);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
-            __syncwarp();
-            const int gj = j0 + c0 + lane;
-            if (gj < N) {
-#pragma unroll 4
-                for (int r = 0; r < 32; ++r) {
-                    const int gr = i0 + warp * 32 + r;
-                    if (gr >= M) break;
-                    const float acc = tile[r * 33 + lane];
-                    if (split) partials[((size_t)blockIdx.z * M + gr) * N + gj] = acc;
-                    else ep(gr, gj, acc);
-                }
-            }
-            __syncwarp();
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else {
+    } else if (warp == 4) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             const uint32_t idesc = make_idesc(kBM, kBN);
-            uint32_t accumulate = 0;
-            for (int it = 0; it < n_kblocks; ++it) {
-                const int s = it % kStages;
-                const uint32_t phase = (it / kStages) & 1;
-                mbar_wait(smem_u32(&bars[s]), phase);
+            long long git = 0;
+            int j = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+                const TileCoord c = decode_tile(t, tiles_m, tiles_n, K, k_per_split);
+                const int acc = j & 1;
+                mbar_wait(smem_u32(&bar_tempty[acc]), (uint32_t)(((j >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = smem_u32(smem + s * kStageBytes);
-                const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + kTileBytes);
-                const uint64_t b_hi = make_desc(st + 2 * kTileBytes), b_lo = make_desc(st + 3 * kTileBytes);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kBN);
+                uint32_t accumulate = 0;
+                for (int it = 0; it < c.nkb; ++it, ++git) {
+                    const int s = (int)(git % kStages);
+                    const uint32_t phase = (uint32_t)((git / kStages) & 1);
+                    mbar_wait(smem_u32(&bar_full[s]), phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = smem_u32(smem + s * kStageBytes);
+                    const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + kTileBytes);
+                    const uint64_t b_hi = make_desc(st + 2 * kTileBytes), b_lo = make_desc(st + 3 * kTileBytes);
 #pragma unroll
-                for (int k = 0; k < kBK / 8; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // +32 bytes per k-step inside the 128-byte swizzle row
-                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, accumulate);
-                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
-                    accumulate = 1u;
+                    for (int k = 0; k < kBK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // +32 bytes per k-step inside the 128-byte swizzle row
+                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, accumulate);
+                        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                        accumulate = 1u;
+                    }
+                    umma_commit(smem_u32(&bar_empty[s]));           // frees the stage when these MMAs have read it
                 }
-                umma_commit(smem_u32(&bars[kStages + s]));          // frees the stage when these MMAs have read it
+                umma_commit(smem_u32(&bar_tfull[acc]));             // accumulator complete -> epilogue
             }
-            umma_commit(smem_u32(&bars[2 * kStages]));              // accumulator complete -> epilogue
         }
         __syncwarp();
+    } else {
+        // ---------------- epilogue warps 5..8: TMEM lane quadrant = warp % 4 ----------------
+        const int quad = warp & 3;
+        float* tile = epi_stage + (warp - 5) * (32 * 33);
+        const bool split = n_splits > 1;
+        int j = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+            const TileCoord c = decode_tile(t, tiles_m, tiles_n, K, k_per_split);
+            const int acc = j & 1;
+            mbar_wait(smem_u32(&bar_tfull[acc]), (uint32_t)((j >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int n_chunks = min(kBN, N - c.j0 + 31 & ~31) / 32;   // 32-column blocks that hold valid columns
+#pragma unroll 1
+            for (int cc = 0; cc < kBN / 32; ++cc) {
+                const int c0 = cc * 32;
+                if (cc < n_chunks) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kBN + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (cc == n_chunks - 1) {   // last read of this accumulator: hand it back to the MMA lane
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
+                    }
+                    // 32 x 32 block: lane = row in registers -> shared (padded) -> lane = column, so that every warp-wide access
+                    // of the epilogue (stores, bias / previous-activation loads) covers 128 contiguous bytes
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) tile[lane * 33 + q] = __uint_as_float(v[q]);
+                    __syncwarp();
+                    const int gj = c.j0 + c0 + lane;
+                    if (gj < N) {
+#pragma unroll 4
+                        for (int r = 0; r < 32; ++r) {
+                            const int gr = c.i0 + quad * 32 + r;
+                            if (gr >= M) break;
+                            const float accv = tile[r * 33 + lane];
+                            if (split) partials[((size_t)c.z * M + gr) * N + gj] = accv;
+                            else ep(gr, gj, accv);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 4) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kBN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kAccCols) : "memory");
     }
 }
 
@@ -382,9 +439,12 @@ void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcO
     }
     int k_per_split = ceil_div(kblocks, splits) * tc::kBK;
     splits = ceil_div(K > 0 ? K : 1, k_per_split);
-    const dim3 grid(ceil_div(N, tc::kBN), ceil_div(M, tc::kBM), splits);
+    const int tiles_m = ceil_div(M, tc::kBM), tiles_n = ceil_div(N, tc::kBN);
+    const int n_tiles = tiles_m * tiles_n * splits;
+    const dim3 grid((unsigned)std::min(n_tiles, kNumSMs));
     float* partials = static_cast<float*>(ws.ptr);
-    DLB_LAUNCH_SMEM((tc::tc_gemm_kernel<EP>), grid, dim3(tc::kThreads), (size_t)tc::kSmemBytes, st, M, N, K, k_per_split, a, b, ep, partials);
+    DLB_LAUNCH_SMEM((tc::tc_gemm_kernel<EP>), grid, dim3(tc::kThreads), (size_t)tc::kSmemBytes, st, M, N, K, k_per_split, tiles_m, tiles_n,
+                    n_tiles, splits, a, b, ep, partials);
     if (splits > 1) {
         const size_t total = (size_t)M * N;
         DLB_LAUNCH((gemm_finalize_kernel<float, EP>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), st,
