@@ -39,6 +39,7 @@ __device__ __forceinline__ R deriv_from_value(int act, R v) {
 
 struct ConvPoolGeom {
     int C, H, W, F, OH, OW, ph, pw, POH, POW, Hp, Wp, K, NPOS;
+    int bRS, bHO;   // backward kernel's shared-memory image: row stride and offset of the odd-column half (see there)
 };
 
 __device__ __forceinline__ const int* resolve_gather(const int* gather_base, const int* cursor) {
@@ -233,8 +234,18 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_kernel(const 
     const int f = tid / 32, lane = tid % 32;
     const int HW = g.H * g.W;
     constexpr int K = C * KH * KW;
-    for (int i = tid; i < C * g.Hp * g.Wp; i += nt) x_s[i] = R(0);
+    // Shared-memory image layout: every padded row stores its even columns first, then (at +bHO) its odd columns, row stride
+    // bRS.  The lanes of a warp walk consecutive pooled windows, i.e. conv positions two columns apart: in this layout they
+    // read consecutive words (one bank each) instead of every other word, and bRS is chosen on the host so that the window
+    // rows a warp spans fall into disjoint bank ranges.  (ncu before: 62 % of the shared-memory wavefronts were conflicts.)
+    for (int i = tid; i < C * g.Hp * g.bRS; i += nt) x_s[i] = R(0);
     __syncthreads();
+    auto stage_one = [&](int i, R v) {
+        const int c = i / HW, r = i - c * HW;
+        const int yy = r / g.W, xx = r - yy * g.W;
+        const int col = xx + g.pw;
+        x_s[(c * g.Hp + yy + g.ph) * g.bRS + (col & 1) * g.bHO + (col >> 1)] = v;
+    };
 
     R dk[K];
     R db[WPL][PH * PW];
@@ -272,21 +283,10 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_kernel(const 
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         if (prefetch) {
 #pragma unroll
-            for (int j = 0; j < XPT; ++j) {
-                const int i = tid + j * nt;
-                if (i < n_in) {
-                    const int c = i / HW, r = i - c * HW;
-                    const int yy = r / g.W, xx = r - yy * g.W;
-                    x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xr[j];
-                }
-            }
+            for (int j = 0; j < XPT; ++j) { const int i = tid + j * nt; if (i < n_in) stage_one(i, xr[j]); }
         } else {
             const R* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
-            for (int i = tid; i < n_in; i += nt) {
-                const int c = i / HW, r = i - c * HW;
-                const int yy = r / g.W, xx = r - yy * g.W;
-                x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = xs[i];
-            }
+            for (int i = tid; i < n_in; i += nt) stage_one(i, xs[i]);
         }
         int cm[WPL]; R cg[WPL];
 #pragma unroll
@@ -306,14 +306,18 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_kernel(const 
 #pragma unroll
             for (int q = 0; q < PH * PW; ++q) db[wi][q] += (q == sel) ? gval : R(0);
             if (gval != R(0)) {   // the reference skips zero factors as well (Tensor.cpp:484-486)
-                const R* base = x_s + oy * g.Wp + ox;
+                // taps of one row alternate between the two column halves: even taps from pa, odd taps from pb
+                const int par = ox & 1, oxh = ox >> 1;
+                const R* pa = x_s + oy * g.bRS + par * g.bHO + oxh;
+                const R* pb = x_s + oy * g.bRS + (par ? oxh + 1 : g.bHO + oxh);
 #pragma unroll
                 for (int c = 0; c < C; ++c)
 #pragma unroll
                     for (int ky = 0; ky < KH; ++ky) {
-                        const R* row = base + (c * g.Hp + ky) * g.Wp;
+                        const int ro = (c * g.Hp + ky) * g.bRS;
 #pragma unroll
-                        for (int kx = 0; kx < KW; ++kx) dk[(c * KH + ky) * KW + kx] += row[kx] * gval;
+                        for (int kx = 0; kx < KW; ++kx)
+                            dk[(c * KH + ky) * KW + kx] += ((kx & 1) ? pb[ro + (kx >> 1)] : pa[ro + (kx >> 1)]) * gval;
                     }
             }
         }
@@ -658,7 +662,17 @@ inline ConvPoolPlan plan_conv_pool(const dlb_layer_spec& c, const dlb_layer_spec
     const int need_wpl = ceil_div(g.NPOS, 32);
     pl.wpl = need_wpl <= 1 ? 1 : need_wpl <= 2 ? 2 : need_wpl <= 5 ? 5 : 8;
     pl.fwd_smem_elems = (size_t)g.F * g.K + (size_t)pl.spc * g.C * g.Hp * g.Wp + 8 /*vector over-read of the last patch row*/;
-    pl.bwd_smem_elems = (size_t)g.C * g.Hp * g.Wp;
+    {   // backward image layout: even row stride >= padded width whose doubled value lands next to POW modulo the 32 banks
+        const int min_rs = 2 * ceil_div(g.Wp, 2);
+        int best = min_rs, best_score = 1 << 30;
+        for (int rs = min_rs; rs < min_rs + 32; rs += 2) {
+            const int d = ((2 * rs) % 32) - (g.POW % 32);
+            const int score = d >= 0 ? d : 64 + d;      // prefer the smallest gap that does not overlap
+            if (score < best_score) { best_score = score; best = rs; }
+        }
+        g.bRS = best; g.bHO = best / 2;
+    }
+    pl.bwd_smem_elems = (size_t)g.C * g.Hp * g.bRS;
     if (pl.fwd_smem_elems * real_bytes > 200 * 1024) return pl;
     pl.n_par = g.F * g.OH * g.OW + g.F * g.K;
     pl.ok = true;

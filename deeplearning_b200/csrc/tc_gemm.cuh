@@ -427,11 +427,12 @@ void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcO
     if (M <= 0 || N <= 0) return;
     const long tiles = (long)ceil_div(M, tc::kBM) * ceil_div(N, tc::kBN);
     const int kblocks = ceil_div(K > 0 ? K : 1, tc::kBK);
+    // Persistent CTAs (one per SM): split the reduction only as far as the split tiles still fit in ONE wave, so that no
+    // SM gets a second tile while others idle; keep at least three k-blocks per split.
     int splits = 1;
-    if (tiles < kNumSMs && kblocks > 2) {
-        splits = (int)ceil_div<long>(kNumSMs, tiles);
-        if (splits > kblocks / 3) splits = kblocks / 3 > 0 ? kblocks / 3 : 1;   // at least three k-blocks per split (fills the ring)
-        if (splits > 24) splits = 24;                                        // bounded partial-sum traffic
+    if (tiles < kNumSMs && kblocks > 3) {
+        splits = (int)(kNumSMs / tiles);
+        if (splits > kblocks / 3) splits = kblocks / 3;
         const size_t per_split = (size_t)M * N * sizeof(float);
         const size_t max_by_ws = per_split ? ws.bytes / per_split : 0;
         if ((size_t)splits > max_by_ws) splits = (int)max_by_ws;
