@@ -54,18 +54,6 @@ __device__ __forceinline__ const int* resolve_gather(const int* gather_base, con
 // the pooling operator are compile-time in the epilogue (one uniform switch per sample, no per-element branches).
 // smem: filters [F][K] | `spc` zero-padded input images [C][Hp][Wp]
 // ---------------------------------------------------------------------------------------------------------------
-// 16-byte shared-memory loads of a run of fp32 / fp64 values (the address must be 16-byte aligned).
-template <int N> __device__ __forceinline__ void lds_vec(const float* p, float (&d)[N], int off) {
-    static_assert(N % 4 == 0, "whole float4 runs");
-#pragma unroll
-    for (int i = 0; i < N / 4; ++i) { const float4 v = *reinterpret_cast<const float4*>(p + 4 * i); d[off + 4 * i] = v.x; d[off + 4 * i + 1] = v.y; d[off + 4 * i + 2] = v.z; d[off + 4 * i + 3] = v.w; }
-}
-template <int N> __device__ __forceinline__ void lds_vec(const double* p, double (&d)[N], int off) {
-    static_assert(N % 2 == 0, "whole double2 runs");
-#pragma unroll
-    for (int i = 0; i < N / 2; ++i) { const double2 v = *reinterpret_cast<const double2*>(p + 2 * i); d[off + 2 * i] = v.x; d[off + 2 * i + 1] = v.y; }
-}
-
 template <class R, int ACT> __device__ __forceinline__ R activation_ct(R z) {
     if (ACT == DLB_ACT_SIGMOID) return R(1) / (R(1) + dl_exp<R>(-z));
     if (ACT == DLB_ACT_TANH) return dl_tanh<R>(z);
@@ -124,11 +112,8 @@ __global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __r
     const R* x_s = x_all + (slot < spc ? slot : 0) * img;
     const int HW = g.H * g.W, n_in = g.C * HW;
     constexpr int PR = KH + 1, PC = KW + 2 * PP - 1;
-    // Whole-vector (16-byte) patch rows are conflict-free but cost registers: measured on B200 the kernel then spills
-    // (96-register cap at 576 threads) and is slower (325 vs 284 us at B=8192), so the scalar rows stay the default.
-    constexpr bool kVectorRows = false;
-    const bool vec_rows = kVectorRows && PP == 2 && ((g.Wp * sizeof(R)) % 16 == 0) && ((img * sizeof(R)) % 16 == 0) &&
-                          (((size_t)g.F * g.K * sizeof(R)) % 16 == 0);
+    // (16-byte vector loads of the patch rows were tried: conflict-free, but the kernel then spills at the 96-register cap
+    // of 576 threads and is slower - 325 vs 284 us at B=8192 - so the scalar rows stay.)
 
     // The next group's inputs are fetched into registers while the current group is computed.
     constexpr int XPT = 4;
@@ -174,18 +159,14 @@ __global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __r
 #pragma unroll
                     for (int q = 0; q < 2 * PP; ++q) acc[fi][dy][q] = R(0);
             for (int c = 0; c < g.C; ++c) {
-                constexpr int PCV = (PC + 3) / 4 * 4;   // patch row rounded up to whole 16-byte vectors
-                R p[PR][PCV];
-                const R* prow = x_s + (c * g.Hp + py * 2) * g.Wp + pxg * (2 * PP);
-                if (vec_rows) {   // conflict-free 16-byte loads (lanes read consecutive 16-byte words)
+                R p[PR][PC];
 #pragma unroll
-                    for (int r = 0; r < PR; ++r) lds_vec<PCV>(prow + r * g.Wp, p[r], 0);
-                } else {
+                for (int r = 0; r < PR; ++r)
 #pragma unroll
-                    for (int r = 0; r < PR; ++r)
-#pragma unroll
-                        for (int q = 0; q < PC; ++q) p[r][q] = (pxg * (2 * PP) + q < g.Wp) ? prow[r * g.Wp + q] : R(0);
-                }
+                    for (int q = 0; q < PC; ++q) {
+                        const int col = pxg * (2 * PP) + q;
+                        p[r][q] = col < g.Wp ? x_s[(c * g.Hp + py * 2 + r) * g.Wp + col] : R(0);
+                    }
 #pragma unroll
                 for (int fi = 0; fi < FPT; ++fi) {
                     const int f = fs * FPT + fi;
@@ -279,6 +260,15 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_kernel(const 
             }
         }
     };
+    // window geometry of this lane is the same for every sample
+    int wy[WPL], wx[WPL], wbase[WPL];
+#pragma unroll
+    for (int wi = 0; wi < WPL; ++wi) {
+        const int win = lane + 32 * wi;
+        const int py = win / g.POW, px = win - py * g.POW;
+        wy[wi] = py * PH; wx[wi] = px * PW;
+        wbase[wi] = (f * g.OH + wy[wi]) * g.OW + wx[wi];
+    }
     if ((int)blockIdx.x < B) fetch(blockIdx.x);
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         if (prefetch) {
@@ -295,14 +285,14 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_kernel(const 
         __syncthreads();
 #pragma unroll
         for (int wi = 0; wi < WPL; ++wi) {
-            const int win = lane + 32 * wi;
             const int m = cm[wi];
-            if (win >= g.NPOS || m < 0) continue;
+            if (lane + 32 * wi >= g.NPOS || m < 0) continue;
             const R gval = cg[wi];
-            const int rem = m - f * g.OH * g.OW;
-            const int oy = rem / g.OW, ox = rem - oy * g.OW;
-            const int py = win / g.POW, px = win - py * g.POW;
-            const int sel = (oy - py * PH) * PW + (ox - px * PW);
+            // arg-max position relative to the window's first element: 0, 1, OW or OW + 1 (no integer division per sample)
+            const int diff = m - wbase[wi];
+            const int dy = diff >= g.OW ? 1 : 0, dx = diff - dy * g.OW;
+            const int oy = wy[wi] + dy, ox = wx[wi] + dx;
+            const int sel = dy * PW + dx;
 #pragma unroll
             for (int q = 0; q < PH * PW; ++q) db[wi][q] += (q == sel) ? gval : R(0);
             if (gval != R(0)) {   // the reference skips zero factors as well (Tensor.cpp:484-486)
@@ -690,7 +680,6 @@ void conv_pool_forward_fpt(cudaStream_t st, const ConvPoolPlan& pl, int grid, co
 #define DLB_CPF2(FPT, PP)                                          \
     do {                                                           \
         if (pl.fwd_threads <= 320) DLB_CPF3(FPT, PP, 320);         \
-        else if (pl.fwd_threads <= 576) DLB_CPF3(FPT, PP, 576);    \
         else DLB_CPF3(FPT, PP, 640);                               \
     } while (0)
 #define DLB_CPF(FPT)                                 \
