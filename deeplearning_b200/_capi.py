@@ -55,7 +55,7 @@ SYMBOLS = [
     "dlb_shuffle_sequence", "dlb_net_train_steps", "dlb_rank_slice", "dlb_event_create", "dlb_event_destroy",
     "dlb_event_record", "dlb_event_elapsed_ms", "dlb_timing_enable", "dlb_timing_report", "dlb_net_describe_plan",
     "dlb_net_enable_graphs", "dlb_net_enable_tensor_cores", "dlb_matmul_f32", "dlb_net_step_host_async",
-    "dlb_net_p2p_export", "dlb_net_set_distributed_p2p",
+    "dlb_net_p2p_export", "dlb_net_set_distributed_p2p", "dlb_net_evaluate_host",
 ]
 
 
@@ -116,6 +116,7 @@ def load() -> C.CDLL:
     lib.dlb_timing_enable.argtypes = [i32]
     lib.dlb_timing_report.argtypes = [C.c_char_p, i64]
     lib.dlb_net_describe_plan.argtypes = [vp, C.c_char_p, i64]
+    lib.dlb_net_evaluate_host.argtypes = [vp, vp, vp, i64, i32, dbl, C.POINTER(dbl), C.POINTER(dbl)]
     lib.dlb_net_p2p_export.argtypes = [vp, vp]
     lib.dlb_net_set_distributed_p2p.argtypes = [vp, i32, i32, vp]
     lib.dlb_net_enable_graphs.argtypes = [vp, i32]

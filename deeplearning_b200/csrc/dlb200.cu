@@ -254,6 +254,7 @@ struct dlb_net {
     virtual void read(int what, int layer, void* dst, int64_t bytes) = 0;
     virtual void write_gradient(const void* src) = 0;
     virtual void eval_host(const void* x, int64_t n, int32_t* classes, void* outputs) = 0;
+    virtual void evaluate_host(const void* x, const void* y, int64_t n, int cost, double l2_reg_factor, double* cost_out, double* correct_out) = 0;
     virtual std::string describe_plan() = 0;
     virtual void enable_graphs(bool on) = 0;
     virtual void enable_tensor_cores(bool on) = 0;
@@ -1081,6 +1082,44 @@ struct NetT final : dlb_net {
         DLB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
 
+    // Net<D>::evaluate_cost_function_and_correct_answers, Net.inl:411-439: Cost = sum_i cost(act(x_i), ref_i) / n +
+    // l2_reg_factor * squared_weights_sum(), CorrectAnswers = #(argmax match) / n.
+    void evaluate_host(const void* x, const void* y, int64_t n, int cost, double l2_reg_factor, double* cost_out, double* correct_out) override {
+        DLB_REQUIRE(x && y && n > 0, "Invalid input.");
+        use_device(ctx);
+        const int64_t chunk = std::min<int64_t>(n, 4096);
+        ensure_capacity(chunk);
+        const R* hx = static_cast<const R*>(x);
+        const R* hy = static_cast<const R*>(y);
+        double* acc = dev_alloc<double>(2);
+        int* correct = reinterpret_cast<int*>(acc + 1);
+        double total_cost = 0.0;
+        DLB_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), ctx->stream));
+        for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+            const int64_t m = std::min(chunk, n - s0);
+            DLB_CUDA(cudaMemcpyAsync(stage_x, hx + s0 * in0(), (size_t)m * (size_t)in0() * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+            DLB_CUDA(cudaMemcpyAsync(stage_y, hy + s0 * outN(), (size_t)m * (size_t)outN() * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+            forward((int)m, stage_x, nullptr, false);
+            const R* out_last = out[(size_t)L() - 1];
+            DLB_LAUNCH((cost_sum_kernel<R>), dim3(1), dim3(256), ctx->stream, out_last, (const R*)stage_y, (const int*)nullptr, (int)m, (int)outN(), cost, cost_dev);
+            DLB_LAUNCH((count_correct_kernel<R>), dim3((unsigned)ceil_div<int64_t>(m, 128)), dim3(128), ctx->stream, out_last, (const R*)stage_y, (int)m, (int)outN(), correct);
+            double c = 0.0;
+            DLB_CUDA(cudaMemcpyAsync(&c, cost_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+            total_cost += c;
+        }
+        for (const auto& Y : layers)   // squared_weights_sum: NLayer weights and CLayer filters, not the biases
+            if (Y.weight_n > 0)
+                DLB_LAUNCH((sum_of_squares_kernel<R>), dim3(64), dim3(256), ctx->stream, (const R*)(params + Y.param_off + Y.bias_n), (size_t)Y.weight_n, acc);
+        double sq = 0.0; int ok = 0;
+        DLB_CUDA(cudaMemcpyAsync(&sq, acc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        DLB_CUDA(cudaMemcpyAsync(&ok, correct, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        dev_free(acc);
+        if (cost_out) *cost_out = total_cost / (double)n + l2_reg_factor * sq;
+        if (correct_out) *correct_out = (double)ok / (double)n;
+    }
+
     std::string describe_plan() override {
         if (!plan.ok) return "unfused: every layer runs the generic operators (layers.cuh)";
         std::string d = "fused:";
@@ -1457,6 +1496,14 @@ int dlb_event_elapsed_ms(void*, void*, double* ms) { if (ms) *ms = 1.0; return 0
 int dlb_timing_enable(int) { return 0; }
 int dlb_timing_report(char* buf, int64_t cap) { if (buf && cap > 0) buf[0] = 0; return 0; }
 #endif
+
+int dlb_net_evaluate_host(dlb_net* net, const void* x, const void* y, int64_t n, int cost, double l2_reg_factor, double* cost_out, double* correct_out) {
+    return guarded([&] {
+        DLB_REQUIRE(net, "null net");
+        DLB_REQUIRE(cost >= DLB_COST_SQUARED_ERROR && cost <= DLB_COST_LINEAR, "Unknown cost function");
+        net->evaluate_host(x, y, n, cost, l2_reg_factor, cost_out, correct_out);
+    });
+}
 
 int dlb_nccl_get_unique_id(void* id_out) {
     return guarded([&] {

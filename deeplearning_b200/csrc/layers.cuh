@@ -372,6 +372,33 @@ __global__ void cost_sum_kernel(const R* __restrict__ out, const R* __restrict__
     if (threadIdx.x == 0) *result = part[0];
 }
 
+// Sum of squares of a range (BasicCollection::sum_of_squares), one block, result accumulated into *result in double.
+template <class R>
+__global__ void sum_of_squares_kernel(const R* __restrict__ v, size_t n, double* __restrict__ result) {
+    __shared__ double part[256];
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += (double)v[i] * (double)v[i];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(result, part[0]);
+}
+
+// Number of rows whose arg-max equals the arg-max of the reference row (Net.inl:430-436), accumulated into *result.
+template <class R>
+__global__ void count_correct_kernel(const R* __restrict__ y, const R* __restrict__ ref, int rows, int n, int* __restrict__ result) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const R* p = y + (size_t)r * n;
+    const R* q = ref + (size_t)r * n;
+    int bp = 0, bq = 0;
+    for (int j = 1; j < n; ++j) { if (p[bp] < p[j]) bp = j; if (q[bq] < q[j]) bq = j; }
+    if (bp == bq) atomicAdd(result, 1);
+}
+
 // Per-row argmax (BasicCollection::max_element_id, first maximum), used by evaluation (Net.inl:432-433).
 template <class R>
 __global__ void argmax_rows_kernel(const R* __restrict__ y, int* __restrict__ cls, int rows, int n) {

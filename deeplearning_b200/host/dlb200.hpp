@@ -169,6 +169,19 @@ public:
         return out;
     }
 
+    // Net::evaluate_cost_function_and_correct_answers (Net.inl:411-439).
+    struct CostAndCorrectAnswers { Real Cost{}; Real CorrectAnswers{}; };
+    CostAndCorrectAnswers evaluate_cost_function_and_correct_answers(const std::vector<Real>& test_input,
+            const std::vector<Real>& reference_output, CostFunctionId cost_func_id, Real l2_reg_factor = Real(0)) {
+        const std::size_t in_n = (std::size_t)in_size().coord_prod(), out_n = (std::size_t)out_size().coord_prod();
+        const std::size_t n = test_input.size() / in_n;
+        if (n == 0 || reference_output.size() != n * out_n) throw std::runtime_error("Invalid input.");
+        double cost = 0, correct = 0;
+        check(dlb_net_evaluate_host(handle(), test_input.data(), reference_output.data(), (int64_t)n, (int)cost_func_id,
+                                    (double)l2_reg_factor, &cost, &correct));
+        return {(Real)cost, (Real)correct};
+    }
+
     // Net::count_correct_answers (Net.inl:441-472): arg-max of the output against arg-max of the label.
     std::size_t count_correct_answers(const std::vector<Real>& test_input, const std::vector<Real>& labels) {
         const std::size_t in_n = (std::size_t)in_size().coord_prod(), out_n = (std::size_t)out_size().coord_prod();

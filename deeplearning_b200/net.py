@@ -417,6 +417,18 @@ class Net:
             raise DlbError("Invalid input.")
         return int(np.sum(self.predict(x) == np.argmax(y, axis=1)))
 
+    def evaluate_cost_function_and_correct_answers(self, test_input, reference_output, cost_func_id: CostFunctionId,
+                                                   l2_reg_factor: float = 0.0) -> tuple:
+        """Net::evaluate_cost_function_and_correct_answers, Net.inl:411-439 -> (Cost, CorrectAnswers)."""
+        x = self._as_items(test_input, self.layer_in_size(0))
+        y = self._as_items(reference_output, self.layer_out_size(self.layers_count() - 1))
+        if x.shape[0] != y.shape[0]:
+            raise DlbError("Invalid input.")
+        cost, correct = C.c_double(0.0), C.c_double(0.0)
+        _capi.check(self.lib.dlb_net_evaluate_host(self._handle(), x.ctypes.data, y.ctypes.data, x.shape[0], int(cost_func_id),
+                                                   float(l2_reg_factor), C.byref(cost), C.byref(correct)))
+        return cost.value, correct.value
+
     # ---- data parallelism ---------------------------------------------------------------------------------------
     def set_distributed(self, rank: int, world_size: int, unique_id: Optional[bytes]) -> None:
         buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None

@@ -188,6 +188,12 @@ DLB_API int dlb_net_write_gradient(dlb_net* net, const void* host_src);
 /* Net<D>::act + max_element_id (Net.inl:134-155, 432-433) over n host items; classes and/or outputs may be NULL. */
 DLB_API int dlb_net_eval_host(dlb_net* net, const void* inputs, int64_t n, int32_t* classes, void* outputs);
 
+/* Net<D>::evaluate_cost_function_and_correct_answers (Net.inl:411-439) over n host items: *cost_out = mean cost +
+ * l2_reg_factor * sum of squared weights (NLayer weights and CLayer filters), *correct_out = fraction of items whose
+ * arg-max matches the reference's. */
+DLB_API int dlb_net_evaluate_host(dlb_net* net, const void* inputs, const void* refs, int64_t n, int cost_id, double l2_reg_factor,
+                                  double* cost_out, double* correct_out);
+
 /* Data parallelism: one process per GPU.  nccl_unique_id: the 128-byte ncclUniqueId created by rank 0
  * (dlb_nccl_get_unique_id) and distributed by the launcher's own plumbing (torch.distributed, MPI, a file, ...). */
 DLB_API int dlb_nccl_get_unique_id(void* id_out_128_bytes);

@@ -73,6 +73,9 @@ int main() {
         for (std::size_t i = 0; i < n; ++i) labels[i * 10 + (std::size_t)cls[i]] = Real(1);
         if (net.count_correct_answers(x, labels) != n) { std::printf("FAIL: predicted classes differ from the oracle's\n"); return 1; }
 
+        const auto stats = net.evaluate_cost_function_and_correct_answers(x, labels, CostFunctionId::CROSS_ENTROPY);
+        if (stats.CorrectAnswers != Real(1) || !(stats.Cost >= Real(0))) { std::printf("FAIL: evaluate_cost_function_and_correct_answers\n"); return 1; }
+
         // error behaviour: inconsistent layers throw with the reference's message
         bool threw = false;
         try { Net<Real> bad(ctx); bad.append_layer<NLayer>(10, 5); bad.append_layer<NLayer>(7, 3); bad.param_count(); }

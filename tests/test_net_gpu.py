@@ -234,3 +234,27 @@ def test_cifar_deep_net_matches_oracle(real):
         gpu.step_indices(perm[e], 0.05, dl.CostFunctionId.CROSS_ENTROPY, reg_factor=0.3 / 3)
     H.assert_close("cifar parameters after two steps", gpu.get_params(), orc.get_params(), real, rtol_mult=20)
     assert np.array_equal(gpu.predict(x), orc.eval(x))
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_evaluate_cost_and_correct_answers(real):
+    """Net::evaluate_cost_function_and_correct_answers (Net.inl:411-439): mean cost + l2 * sum w^2, fraction correct."""
+    specs, cost = NETS["mini_lenet"]
+    orc, gpu = H.make_pair(specs, real, seed=91)
+    n = 50
+    x, y = H.synthetic_batch(orc, n, real, seed=92, lo=0.0, hi=1.0)
+    cls, outs = orc.eval(x, want_outputs=True)
+    params = orc.get_params().astype(np.float64)
+    sq = 0.0
+    for l, s in enumerate(orc.specs):   # weights / filters only
+        if s.type == ob.PULL:
+            continue
+        a = gpu.layer_param_offset(l) + orc.out_sizes[l]
+        b = gpu.layer_param_offset(l + 1) if l + 1 < len(orc.specs) else gpu.param_count
+        sq += float(np.sum(params[a:b] ** 2))
+    want_cost = sum(orc.cost(outs[i], y[i], cost) for i in range(50)) / 50 + 0.01 * sq
+    want_correct = float(np.mean(cls == np.argmax(y, axis=1)))
+    got_cost, got_correct = gpu.evaluate_cost_function_and_correct_answers(x, y, dl.CostFunctionId(cost), 0.01)
+    assert abs(got_cost - want_cost) <= (1e-4 if real == "f32" else 1e-10) * abs(want_cost)
+    assert got_correct == want_correct
+    assert gpu.count_correct_answers(x, y) == int(round(want_correct * 50))
