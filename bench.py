@@ -112,6 +112,8 @@ def algorithmic_bytes(net, key: str, batch: int, sz: int) -> float | None:
         return 3.0 * P * sz
     if tag == "cost_grad":
         return 3.0 * batch * net.layer_out_size(L - 1) * sz
+    if tag == "reduce_update":
+        return 3.0 * P * sz     # gradient in, parameter in, parameter out (partial sums are overhead of the split)
     if l < 0 or l >= L:
         return None
     in_n, out_n = net.layer_in_size(l), net.layer_out_size(l)
@@ -119,8 +121,6 @@ def algorithmic_bytes(net, key: str, batch: int, sz: int) -> float | None:
     spec = net._specs[l]
     bias_n = out_n if spec.type != 3 else 0
     weight_n = n_par - bias_n
-    if tag == "reduce_update":
-        return 3.0 * P * sz     # gradient in, parameter in, parameter out (partial sums are overhead of the split)
     if tag == "conv_pool_fwd":   # fused CLayer + PLayer forward: input, pooled output, index map, parameters
         o1 = net.layer_out_size(l + 1)
         return batch * (in_n * sz + o1 * sz + o1 * 4) + n_par * sz
@@ -165,6 +165,18 @@ def step_bytes_per_sample(net, batch: int, sz: int) -> float:
         act += fwd + bwd
     act += 3 * net.layer_out_size(L - 1)              # cost: output, reference, derivative
     return act * sz + 6.0 * net.param_count * sz / batch
+
+
+def measured_traffic(key: str, batch: int, real: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/summarize_ncu.py --traffic), or None when that kernel was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            table = json.load(f)
+        tag = key.split(":", 2)[1]
+        return table.get(f"{real}_B{batch}", {}).get(tag)
+    except Exception:
+        return None
 
 
 def hbm_peak():
@@ -368,7 +380,8 @@ def main():
         peak, peak_src = hbm_peak()
         top = kernels[0] if kernels else {"kernel": None, "gbs": None, "share": None, "us_per_launch": None}
         line["roofline"] = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
-                            "frac": (top["gbs"] / peak) if top["gbs"] else None, "traffic": None, "peak_source": peak_src,
+                            "frac": (top["gbs"] / peak) if top["gbs"] else None, "traffic": measured_traffic(top["kernel"], batch, args.real) if top["kernel"] else None,
+                            "algorithmic_bytes": top.get("algorithmic_bytes"), "peak_source": peak_src,
                             "share_of_step": top["share"], "us_per_launch": top["us_per_launch"]}
         line["kernels"] = kernels[:12]
         bps = step_bytes_per_sample(net, batch, sz)

@@ -54,8 +54,42 @@ def launches(src, dst):
     print(open(dst).read())
 
 
+TAGS = (("conv_pool_forward_kernel", "conv_pool_fwd"), ("conv_pool_backward_kernel", "conv_pool_bwd"), ("full_head_kernel", "head"),
+        ("p2p_reduce_update_kernel", "reduce_update"), ("reduce_update_kernel", "reduce_update"), ("batch_outer_partial_kernel", "head_dW"),
+        ("tc_gemm_kernel<dlb::EpiFullForward", "full_fwd"), ("tc_gemm_kernel<dlb::EpiWeightAndBias", "full_dW"),
+        ("tc_gemm_kernel<dlb::EpiStoreTimesDeriv", "full_dX"))
+
+
+def traffic(src, key, dst):
+    """profiles/traffic.json[key][bench tag] = dram read + write bytes per launch (mean over the captured launches) from a
+    raw-page CSV of an ncu --set full capture.  key is e.g. f32_B256."""
+    import json, os
+    rows = list(csv.reader(open(src).read().splitlines()))
+    header, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(header)}
+    def num(r, k):
+        v = float(r[idx[k]].replace(",", "")); u = units[idx[k]]
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    acc = collections.defaultdict(list)
+    for r in data:
+        name = r[idx["Kernel Name"]]
+        for pat, tag in TAGS:
+            if pat in name:
+                acc[tag].append(num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"))
+                break
+    table = json.load(open(dst)) if os.path.exists(dst) else {}
+    table[key] = {t: sum(v) / len(v) for t, v in sorted(acc.items())}
+    table.setdefault("_note", "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none "
+                              "--cache-control none (warm L2: small batches are served from the 126 MB L2, so traffic can be below the algorithmic bytes)")
+    json.dump(table, open(dst, "w"), indent=1, sort_keys=True)
+    print(json.dumps(table[key], indent=1))
+
+
 def full(src, dst):
-    out = subprocess.check_output(["ncu", "-i", src, "--page", "raw", "--csv"], text=True)
+    if src.endswith(".csv"):
+        out = open(src).read()
+    else:
+        out = subprocess.check_output(["ncu", "-i", src, "--page", "raw", "--csv"], text=True)
     rows = list(csv.reader(out.splitlines()))
     header, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(header)}
@@ -75,4 +109,4 @@ def full(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
