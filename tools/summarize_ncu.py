@@ -56,8 +56,8 @@ def launches(src, dst):
 
 TAGS = (("conv_pool_forward_kernel", "conv_pool_fwd"), ("conv_pool_backward_kernel", "conv_pool_bwd"), ("full_head_kernel", "head"),
         ("p2p_reduce_update_kernel", "reduce_update"), ("reduce_update_kernel", "reduce_update"), ("batch_outer_partial_kernel", "head_dW"),
-        ("tc_gemm_kernel<dlb::EpiFullForward", "full_fwd"), ("tc_gemm_kernel<dlb::EpiWeightAndBias", "full_dW"),
-        ("tc_gemm_kernel<dlb::EpiStoreTimesDeriv", "full_dX"))
+        ("tc_gemm_kernel<EpiFullForward", "full_fwd"), ("tc_gemm_kernel<EpiWeightAndBias", "full_dW"),
+        ("tc_gemm_kernel<EpiStoreTimesDeriv", "full_dX"))
 
 
 def traffic(src, key, dst):
