@@ -201,6 +201,200 @@ __global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Real = float variant of the forward kernel on the packed fp32 pipe (FFMA2, `fma.rn.f32x2`, sm_100+): one instruction
+// performs two fused multiply-adds on a 64-bit register pair, with the filter tap broadcast to both halves - half the
+// issue slots of the scalar FFMA loop for the same IEEE fma results.  A thread owns 2 horizontally adjacent pooled
+// positions (4 convolution columns q = 0..3) x 2 rows x 4 filters; accumulators are kept as pairs (q, q+2) and the input
+// patch as pairs (column j, column j+2), so every pair an FFMA2 needs is an aligned register pair for every tap.
+// Filters sit in shared memory tap-major [K][Fp] (Fp = filters padded to a multiple of 4): the 4 taps of a thread's
+// filters are one 16-byte broadcast load.  One sample per CTA iteration; filter groups beyond `fgp` are looped.
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef DLB_CUDA_EMU
+struct f32x2 { float lo, hi; };
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { return f32x2{lo, hi}; }
+__device__ __forceinline__ float lo_of(f32x2 v) { return v.lo; }
+__device__ __forceinline__ float hi_of(f32x2 v) { return v.hi; }
+__device__ __forceinline__ f32x2 ffma2_bcast(f32x2 a, float w, f32x2 c) { return f32x2{fmaf(a.lo, w, c.lo), fmaf(a.hi, w, c.hi)}; }
+#else
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo_of(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float hi_of(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ f32x2 ffma2_bcast(f32x2 a, float w, f32x2 c) {
+    f32x2 d;
+    asm("{ .reg .b64 ww; mov.b64 ww, {%2, %2}; fma.rn.f32x2 %0, %1, ww, %3; }" : "=l"(d) : "l"(a), "f"(w), "l"(c));
+    return d;
+}
+#endif
+
+constexpr int kX2Threads = 384;   // launch bound of the packed kernel: 168 registers per thread
+constexpr int kX2VecRows = 1, kX2VecBias = 2, kX2VecOut = 4;
+
+template <int ACT, bool IS_MAX>
+__device__ __forceinline__ void conv_pool_epilogue_x2(const f32x2 (&acc)[4][2][2], const float* __restrict__ bias, float* __restrict__ pooled,
+                                                      int* __restrict__ map, const ConvPoolGeom& g, int fs, int py, int pxg, size_t b, int flags) {
+    const int col0 = pxg * 4;
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi) {
+        const int f = fs * 4 + fi;
+        if (f >= g.F) continue;
+        float v[2][4];
+        const int id0 = (f * g.OH + py * 2) * g.OW + col0;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            float bz[4];
+            if (flags & kX2VecBias) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(bias + id0 + dy * g.OW));
+                bz[0] = t.x; bz[1] = t.y; bz[2] = t.z; bz[3] = t.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bz[q] = col0 + q < g.OW ? __ldg(bias + id0 + dy * g.OW + q) : 0.f;
+            }
+            v[dy][0] = activation_ct<float, ACT>(lo_of(acc[fi][dy][0]) + bz[0]);
+            v[dy][1] = activation_ct<float, ACT>(lo_of(acc[fi][dy][1]) + bz[1]);
+            v[dy][2] = activation_ct<float, ACT>(hi_of(acc[fi][dy][0]) + bz[2]);
+            v[dy][3] = activation_ct<float, ACT>(hi_of(acc[fi][dy][1]) + bz[3]);
+        }
+        float best[2]; int best_id[2];
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+            best[pp] = IS_MAX ? -real_limits<float>::max() : real_limits<float>::max();
+            best_id[pp] = -1;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const float c = v[dy][pp * 2 + dx];
+                    if (IS_MAX ? (best[pp] < c) : (best[pp] > c)) { best[pp] = c; best_id[pp] = id0 + dy * g.OW + pp * 2 + dx; }   // strict: the first wins ties
+                }
+        }
+        const size_t o = (b * g.F + f) * g.NPOS + py * g.POW + pxg * 2;
+        if (flags & kX2VecOut) {
+            *reinterpret_cast<float2*>(pooled + o) = make_float2(best[0], best[1]);
+            *reinterpret_cast<int2*>(map + o) = make_int2(best_id[0], best_id[1]);
+        } else {
+            pooled[o] = best[0]; map[o] = best_id[0];
+            if (pxg * 2 + 1 < g.POW) { pooled[o + 1] = best[1]; map[o + 1] = best_id[1]; }
+        }
+    }
+}
+
+template <int KH, int KW>
+__global__ void __launch_bounds__(kX2Threads, 1) conv_pool_forward_x2_kernel(const float* __restrict__ x, const int* __restrict__ gather_base,
+                                                                               const int* __restrict__ cursor, const float* __restrict__ bias,
+                                                                               const float* __restrict__ filt, float* __restrict__ pooled,
+                                                                               int* __restrict__ map, int B, ConvPoolGeom g, int act, int is_max,
+                                                                               int nfg, int fgp, int flags) {
+    DLB_DYNAMIC_SMEM(float, smem);
+    const int Fp = nfg * 4;
+    float* filt_s = smem;                 // [K][Fp], zero padded filters
+    float* x_s = smem + g.K * Fp;         // zero-padded image [C][Hp][Wp]
+    const int img = g.C * g.Hp * g.Wp;
+    const int* gather = resolve_gather(gather_base, cursor);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < g.K * Fp; i += nt) {
+        const int k = i / Fp, f = i - k * Fp;
+        filt_s[i] = f < g.F ? filt[f * g.K + k] : 0.f;
+    }
+    for (int i = tid; i < img + 8; i += nt) x_s[i] = 0.f;   // the borders stay zero (padding)
+    __syncthreads();
+
+    const int PGW = (g.POW + 1) / 2, NPG = g.POH * PGW;
+    const int fsl = tid / NPG, pg = tid - fsl * NPG;
+    const int py = pg / PGW, pxg = pg - py * PGW;
+    const bool active = fsl < fgp;
+    const int HW = g.H * g.W, n_in = g.C * HW;
+    constexpr int PR = KH + 1, PC = KW + 3, NP = KW + 1;
+
+    constexpr int XPT = 3;
+    const bool prefetch = n_in <= XPT * nt;
+    float xr[XPT];
+    auto fetch = [&](int b) {
+        const float* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
+#pragma unroll
+        for (int j = 0; j < XPT; ++j) { const int i = tid + j * nt; xr[j] = i < n_in ? __ldg(xs + i) : 0.f; }
+    };
+    auto stage_one = [&](int e, float v) {
+        const int c = e / HW, r = e - c * HW;
+        const int yy = r / g.W, xx = r - yy * g.W;
+        x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = v;
+    };
+    if (prefetch && (int)blockIdx.x < B) fetch(blockIdx.x);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        if (prefetch) {
+#pragma unroll
+            for (int j = 0; j < XPT; ++j) { const int i = tid + j * nt; if (i < n_in) stage_one(i, xr[j]); }
+            if (b + (int)gridDim.x < B) fetch(b + gridDim.x);
+        } else {
+            const float* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
+            for (int i = tid; i < n_in; i += nt) stage_one(i, xs[i]);
+        }
+        __syncthreads();
+        if (active) {
+            for (int fs = fsl; fs < nfg; fs += fgp) {
+                f32x2 acc[4][2][2];
+#pragma unroll
+                for (int fi = 0; fi < 4; ++fi)
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy) { acc[fi][dy][0] = pack2(0.f, 0.f); acc[fi][dy][1] = pack2(0.f, 0.f); }
+                for (int c = 0; c < g.C; ++c) {
+                    f32x2 pr[PR][NP];   // pr[r][j] = (patch[r][j], patch[r][j + 2])
+#pragma unroll
+                    for (int r = 0; r < PR; ++r) {
+                        float p[PC];
+                        const float* row = x_s + (c * g.Hp + py * 2 + r) * g.Wp + pxg * 4;
+                        if (flags & kX2VecRows) {
+                            const float4 t0 = *reinterpret_cast<const float4*>(row);
+                            p[0] = t0.x; p[1] = t0.y; p[2] = t0.z; p[3] = t0.w;
+                            if (PC == 8) {
+                                const float4 t1 = *reinterpret_cast<const float4*>(row + 4);
+                                p[4] = t1.x; p[5] = t1.y; p[6] = t1.z; p[PC - 1] = t1.w;
+                            } else {
+                                const float2 t1 = *reinterpret_cast<const float2*>(row + 4);
+                                p[4] = t1.x; p[PC - 1] = t1.y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < PC; ++q) p[q] = pxg * 4 + q < g.Wp ? row[q] : 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < NP; ++j) pr[r][j] = pack2(p[j], p[j + 2]);
+                    }
+                    const float* wbase = filt_s + c * (KH * KW) * Fp + fs * 4;
+#pragma unroll
+                    for (int ky = 0; ky < KH; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < KW; ++kx) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(wbase + (ky * KW + kx) * Fp);
+                            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int fi = 0; fi < 4; ++fi)
+#pragma unroll
+                                for (int dy = 0; dy < 2; ++dy) {
+                                    acc[fi][dy][0] = ffma2_bcast(pr[dy + ky][kx], wv[fi], acc[fi][dy][0]);
+                                    acc[fi][dy][1] = ffma2_bcast(pr[dy + ky][kx + 1], wv[fi], acc[fi][dy][1]);
+                                }
+                        }
+                }
+#define DLB_EPI(ACT)                                                                                                  \
+                do {                                                                                                      \
+                    if (is_max) conv_pool_epilogue_x2<ACT, true>(acc, bias, pooled, map, g, fs, py, pxg, (size_t)b, flags);   \
+                    else conv_pool_epilogue_x2<ACT, false>(acc, bias, pooled, map, g, fs, py, pxg, (size_t)b, flags);         \
+                } while (0)
+                switch (act) {
+                case DLB_ACT_RELU: DLB_EPI(DLB_ACT_RELU); break;
+                case DLB_ACT_SIGMOID: DLB_EPI(DLB_ACT_SIGMOID); break;
+                case DLB_ACT_TANH: DLB_EPI(DLB_ACT_TANH); break;
+                default: DLB_EPI(DLB_ACT_LINEAR); break;
+                }
+#undef DLB_EPI
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Backward of the fused first stage.  One warp per filter; the lanes split the filter's pooled windows.  Per lane:
 // the K = C*KH*KW filter-gradient accumulators and the PH*PW bias-gradient accumulators of each of its windows, all in
 // registers across the CTA's samples.  partial layout per CTA = the layer's flat parameter layout [bias | filters].
@@ -691,10 +885,38 @@ void conv_pool_forward_fpt(cudaStream_t st, const ConvPoolPlan& pl, int grid, co
 #undef DLB_CPF3
 }
 
+// Real = float: the packed-FMA kernel (one sample per CTA iteration; it sizes its own grid).
+template <int KH, int KW>
+inline bool conv_pool_forward_x2(cudaStream_t st, const ConvPoolPlan& pl, const float* x, const int* gather_base, const int* cursor,
+                                 const float* bias, const float* filt, float* pooled, int* map, int B) {
+    const ConvPoolGeom& g = pl.g;
+    const int PGW = ceil_div(g.POW, 2), NPG = g.POH * PGW;
+    if (NPG > kX2Threads) return false;
+    const int nfg = ceil_div(g.F, 4);
+    const int fgp = std::min(nfg, kX2Threads / NPG);
+    const int threads = ceil_div(fgp * NPG, 32) * 32;
+    const size_t smem = ((size_t)g.K * nfg * 4 + (size_t)g.C * g.Hp * g.Wp + 8) * sizeof(float);
+    if (smem > 200 * 1024) return false;
+    int flags = 0;
+    if (g.Wp % 4 == 0 && (PGW - 1) * 4 + KW + 3 <= g.Wp) flags |= kX2VecRows;
+    if (g.OW % 4 == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) flags |= kX2VecBias;
+    if (g.POW % 2 == 0 && g.NPOS % 2 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 7) == 0 && (reinterpret_cast<uintptr_t>(map) & 7) == 0)
+        flags |= kX2VecOut;
+    const dim3 gd((unsigned)std::min(B, kNumSMs)), bd((unsigned)threads);
+    DLB_LAUNCH_SMEM((conv_pool_forward_x2_kernel<KH, KW>), gd, bd, smem, st, x, gather_base, cursor, bias, filt, pooled, map, B, g, pl.act,
+                    pl.is_max, nfg, fgp, flags);
+    return true;
+}
+
 template <class R>
 void conv_pool_forward(cudaStream_t st, const ConvPoolPlan& pl, int grid, const R* x, const int* gather_base, const int* cursor,
                        const R* bias, const R* filt, R* pooled, int* map, int B) {
     TagScope tag_("conv_pool_fwd");
+    if constexpr (std::is_same<R, float>::value) {
+        if (pl.KH == 5 ? conv_pool_forward_x2<5, 5>(st, pl, x, gather_base, cursor, bias, filt, pooled, map, B)
+                       : conv_pool_forward_x2<3, 3>(st, pl, x, gather_base, cursor, bias, filt, pooled, map, B))
+            return;
+    }
     if (pl.KH == 5) conv_pool_forward_fpt<R, 5, 5>(st, pl, grid, x, gather_base, cursor, bias, filt, pooled, map, B);
     else conv_pool_forward_fpt<R, 3, 3>(st, pl, grid, x, gather_base, cursor, bias, filt, pooled, map, B);
 }
