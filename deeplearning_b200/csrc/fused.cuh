@@ -227,13 +227,29 @@ __device__ __forceinline__ f32x2 ffma2_bcast(f32x2 a, float w, f32x2 c) {
 }
 #endif
 
-constexpr int kX2Threads = 384;   // launch bound of the packed kernel: 168 registers per thread
-constexpr int kX2VecRows = 1, kX2VecBias = 2, kX2VecOut = 4;
+constexpr int kX2Threads = 384;   // launch bound of the packed kernel, two CTAs per SM: 85 registers per thread
+constexpr int kX2VecBias = 2, kX2VecOut = 4;
 
 template <int ACT, bool IS_MAX>
 __device__ __forceinline__ void conv_pool_epilogue_x2(const f32x2 (&acc)[4][2][2], const float* __restrict__ bias, float* __restrict__ pooled,
                                                       int* __restrict__ map, const ConvPoolGeom& g, int fs, int py, int pxg, size_t b, int flags) {
     const int col0 = pxg * 4;
+    float bzs[4][2][4];   // all untied biases first (one batch of loads in flight), then the arithmetic
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi) {
+        const int f = min(fs * 4 + fi, g.F - 1);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const float* src = bias + (f * g.OH + py * 2 + dy) * g.OW + col0;
+            if (flags & kX2VecBias) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+                bzs[fi][dy][0] = t.x; bzs[fi][dy][1] = t.y; bzs[fi][dy][2] = t.z; bzs[fi][dy][3] = t.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bzs[fi][dy][q] = col0 + q < g.OW ? __ldg(src + q) : 0.f;
+            }
+        }
+    }
 #pragma unroll
     for (int fi = 0; fi < 4; ++fi) {
         const int f = fs * 4 + fi;
@@ -242,14 +258,7 @@ __device__ __forceinline__ void conv_pool_epilogue_x2(const f32x2 (&acc)[4][2][2
         const int id0 = (f * g.OH + py * 2) * g.OW + col0;
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
-            float bz[4];
-            if (flags & kX2VecBias) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(bias + id0 + dy * g.OW));
-                bz[0] = t.x; bz[1] = t.y; bz[2] = t.z; bz[3] = t.w;
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) bz[q] = col0 + q < g.OW ? __ldg(bias + id0 + dy * g.OW + q) : 0.f;
-            }
+            const float* bz = bzs[fi][dy];
             v[dy][0] = activation_ct<float, ACT>(lo_of(acc[fi][dy][0]) + bz[0]);
             v[dy][1] = activation_ct<float, ACT>(lo_of(acc[fi][dy][1]) + bz[1]);
             v[dy][2] = activation_ct<float, ACT>(hi_of(acc[fi][dy][0]) + bz[2]);
@@ -279,57 +288,91 @@ __device__ __forceinline__ void conv_pool_epilogue_x2(const f32x2 (&acc)[4][2][2
     }
 }
 
+// Asynchronous global -> shared copies for the image staging (the emulator build copies synchronously).
+#ifdef DLB_CUDA_EMU
+__device__ __forceinline__ void stage_copy16(float* dst, const float* src) { for (int q = 0; q < 4; ++q) dst[q] = src[q]; }
+__device__ __forceinline__ void stage_copy4(float* dst, const float* src) { *dst = *src; }
+__device__ __forceinline__ void stage_commit() {}
+template <int N> __device__ __forceinline__ void stage_wait() {}
+#else
+__device__ __forceinline__ void stage_copy16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void stage_copy4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
+struct alignas(16) f32x2_quad { f32x2 a, b; };   // two pairs = one 16-byte shared-memory load
+
+// Shared-memory image of the packed kernel: every element slot holds the PAIR (x[col], x[col + 2]) of the zero-padded row
+// (8 bytes, row stride RS slots), so the pairs an FFMA2 consumes arrive as aligned 64-bit registers straight from 16-byte
+// loads - ptxas otherwise keeps the patch as single registers and re-packs a pair with two MOVs in front of every FFMA2
+// (616 moves per 400 FFMA2 measured).  The image is double buffered and filled by cp.async one sample ahead (the gather
+// index two ahead): a sample costs ONE block barrier and the compute phase never waits on global memory.
 template <int KH, int KW>
 __global__ void __launch_bounds__(kX2Threads, 1) conv_pool_forward_x2_kernel(const float* __restrict__ x, const int* __restrict__ gather_base,
                                                                                const int* __restrict__ cursor, const float* __restrict__ bias,
                                                                                const float* __restrict__ filt, float* __restrict__ pooled,
                                                                                int* __restrict__ map, int B, ConvPoolGeom g, int act, int is_max,
-                                                                               int nfg, int fgp, int flags) {
+                                                                               int nfg, int fgp, int RS, int flags) {
     DLB_DYNAMIC_SMEM(float, smem);
     const int Fp = nfg * 4;
+    const int img_stride = g.C * g.Hp * RS * 2;   // floats per image buffer (a multiple of 4: RS is even)
     float* filt_s = smem;                 // [K][Fp], zero padded filters
-    float* x_s = smem + g.K * Fp;         // zero-padded image [C][Hp][Wp]
-    const int img = g.C * g.Hp * g.Wp;
+    float* x_buf = smem + g.K * Fp;       // two pair images [C][Hp][RS][2]
     const int* gather = resolve_gather(gather_base, cursor);
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < g.K * Fp; i += nt) {
         const int k = i / Fp, f = i - k * Fp;
         filt_s[i] = f < g.F ? filt[f * g.K + k] : 0.f;
     }
-    for (int i = tid; i < img + 8; i += nt) x_s[i] = 0.f;   // the borders stay zero (padding)
+    for (int i = tid; i < 2 * img_stride; i += nt) x_buf[i] = 0.f;   // borders (padding) and unused slots stay zero
     __syncthreads();
 
     const int PGW = (g.POW + 1) / 2, NPG = g.POH * PGW;
     const int fsl = tid / NPG, pg = tid - fsl * NPG;
     const int py = pg / PGW, pxg = pg - py * PGW;
     const bool active = fsl < fgp;
-    const int HW = g.H * g.W, n_in = g.C * HW;
-    constexpr int PR = KH + 1, PC = KW + 3, NP = KW + 1;
+    const int n_in = g.C * g.H * g.W;
+    constexpr int NP = KW + 1;            // pairs per patch row (even)
 
-    constexpr int XPT = 3;
-    const bool prefetch = n_in <= XPT * nt;
-    float xr[XPT];
-    auto fetch = [&](int b) {
-        const float* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
-#pragma unroll
-        for (int j = 0; j < XPT; ++j) { const int i = tid + j * nt; xr[j] = i < n_in ? __ldg(xs + i) : 0.f; }
-    };
-    auto stage_one = [&](int e, float v) {
-        const int c = e / HW, r = e - c * HW;
-        const int yy = r / g.W, xx = r - yy * g.W;
-        x_s[(c * g.Hp + yy + g.ph) * g.Wp + xx + g.pw] = v;
-    };
-    if (prefetch && (int)blockIdx.x < B) fetch(blockIdx.x);
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        if (prefetch) {
-#pragma unroll
-            for (int j = 0; j < XPT; ++j) { const int i = tid + j * nt; if (i < n_in) stage_one(i, xr[j]); }
-            if (b + (int)gridDim.x < B) fetch(b + gridDim.x);
-        } else {
-            const float* xs = x + (size_t)(gather ? gather[b] : b) * n_in;
-            for (int i = tid; i < n_in; i += nt) stage_one(i, xs[i]);
+    // staging: a warp copies whole image rows, lane = column: element (row, col) is the low half of slot col and the high
+    // half of slot col - 2
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    auto stage = [&](long long row, float* dst) {
+        const float* xs = x + (size_t)row * n_in;
+        for (int r = warp; r < g.C * g.H; r += nw) {
+            const int c = g.C == 1 ? 0 : r / g.H;
+            const int yy = r - c * g.H;
+            float* drow = dst + (size_t)((c * g.Hp + yy + g.ph) * RS) * 2;
+            for (int xx = lane; xx < g.W; xx += 32) {
+                const int cc = xx + g.pw;
+                const float* src = xs + r * g.W + xx;
+                stage_copy4(drow + cc * 2, src);
+                if (cc >= 2) stage_copy4(drow + (cc - 2) * 2 + 1, src);
+            }
         }
-        __syncthreads();
+    };
+    auto row_of = [&](int b) -> long long { return b < B ? (gather ? (long long)__ldg(gather + b) : (long long)b) : -1; };
+
+    const int G = gridDim.x;
+    long long row_next = row_of((int)blockIdx.x + G);        // sample it + 1
+    {
+        const long long row0 = row_of(blockIdx.x);
+        if (row0 >= 0) stage(row0, x_buf);
+        stage_commit();
+    }
+    int it = 0;
+    for (int b = blockIdx.x; b < B; b += G, ++it) {
+        stage_wait<0>();        // this thread's copies of sample `it` have landed
+        __syncthreads();        // ... everyone's have, and everyone is done computing on the other buffer
+        const float* x_s = x_buf + (it & 1) * img_stride;
+        if (row_next >= 0) stage(row_next, x_buf + ((it + 1) & 1) * img_stride);
+        stage_commit();
+        row_next = row_of(b + 2 * G);
         if (active) {
             for (int fs = fsl; fs < nfg; fs += fgp) {
                 f32x2 acc[4][2][2];
@@ -338,31 +381,19 @@ __global__ void __launch_bounds__(kX2Threads, 1) conv_pool_forward_x2_kernel(con
 #pragma unroll
                     for (int dy = 0; dy < 2; ++dy) { acc[fi][dy][0] = pack2(0.f, 0.f); acc[fi][dy][1] = pack2(0.f, 0.f); }
                 for (int c = 0; c < g.C; ++c) {
-                    f32x2 pr[PR][NP];   // pr[r][j] = (patch[r][j], patch[r][j + 2])
+                    // rolling window over the patch rows: row r serves tap row ky = r (upper conv row) and ky = r - 1 (lower one),
+                    // so only two rows of pairs are live at a time
+                    auto load_row = [&](int r, f32x2 (&pr)[NP]) {
+                        const f32x2_quad* q = reinterpret_cast<const f32x2_quad*>(x_s + (size_t)((c * g.Hp + py * 2 + r) * RS + pxg * 4) * 2);
 #pragma unroll
-                    for (int r = 0; r < PR; ++r) {
-                        float p[PC];
-                        const float* row = x_s + (c * g.Hp + py * 2 + r) * g.Wp + pxg * 4;
-                        if (flags & kX2VecRows) {
-                            const float4 t0 = *reinterpret_cast<const float4*>(row);
-                            p[0] = t0.x; p[1] = t0.y; p[2] = t0.z; p[3] = t0.w;
-                            if (PC == 8) {
-                                const float4 t1 = *reinterpret_cast<const float4*>(row + 4);
-                                p[4] = t1.x; p[5] = t1.y; p[6] = t1.z; p[PC - 1] = t1.w;
-                            } else {
-                                const float2 t1 = *reinterpret_cast<const float2*>(row + 4);
-                                p[4] = t1.x; p[PC - 1] = t1.y;
-                            }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < PC; ++q) p[q] = pxg * 4 + q < g.Wp ? row[q] : 0.f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < NP; ++j) pr[r][j] = pack2(p[j], p[j + 2]);
-                    }
+                        for (int j = 0; j < NP / 2; ++j) { const f32x2_quad t = q[j]; pr[2 * j] = t.a; pr[2 * j + 1] = t.b; }
+                    };
                     const float* wbase = filt_s + c * (KH * KW) * Fp + fs * 4;
+                    f32x2 rows[2][NP];
+                    load_row(0, rows[0]);
 #pragma unroll
-                    for (int ky = 0; ky < KH; ++ky)
+                    for (int ky = 0; ky < KH; ++ky) {
+                        load_row(ky + 1, rows[(ky + 1) & 1]);
 #pragma unroll
                         for (int kx = 0; kx < KW; ++kx) {
                             const float4 w4 = *reinterpret_cast<const float4*>(wbase + (ky * KW + kx) * Fp);
@@ -371,10 +402,11 @@ __global__ void __launch_bounds__(kX2Threads, 1) conv_pool_forward_x2_kernel(con
                             for (int fi = 0; fi < 4; ++fi)
 #pragma unroll
                                 for (int dy = 0; dy < 2; ++dy) {
-                                    acc[fi][dy][0] = ffma2_bcast(pr[dy + ky][kx], wv[fi], acc[fi][dy][0]);
-                                    acc[fi][dy][1] = ffma2_bcast(pr[dy + ky][kx + 1], wv[fi], acc[fi][dy][1]);
+                                    acc[fi][dy][0] = ffma2_bcast(rows[(ky + dy) & 1][kx], wv[fi], acc[fi][dy][0]);
+                                    acc[fi][dy][1] = ffma2_bcast(rows[(ky + dy) & 1][kx + 1], wv[fi], acc[fi][dy][1]);
                                 }
                         }
+                    }
                 }
 #define DLB_EPI(ACT)                                                                                                  \
                 do {                                                                                                      \
@@ -390,8 +422,8 @@ __global__ void __launch_bounds__(kX2Threads, 1) conv_pool_forward_x2_kernel(con
 #undef DLB_EPI
             }
         }
-        __syncthreads();
     }
+    stage_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -895,16 +927,16 @@ inline bool conv_pool_forward_x2(cudaStream_t st, const ConvPoolPlan& pl, const 
     const int nfg = ceil_div(g.F, 4);
     const int fgp = std::min(nfg, kX2Threads / NPG);
     const int threads = ceil_div(fgp * NPG, 32) * 32;
-    const size_t smem = ((size_t)g.K * nfg * 4 + (size_t)g.C * g.Hp * g.Wp + 8) * sizeof(float);
+    const int RS = (std::max(g.Wp, PGW * 4 + KW + 1) + 1) & ~1;   // pair slots per image row: every 16-byte patch load stays inside its row
+    const size_t smem = ((size_t)g.K * nfg * 4 + 2 * (size_t)g.C * g.Hp * RS * 2) * sizeof(float);
     if (smem > 200 * 1024) return false;
     int flags = 0;
-    if (g.Wp % 4 == 0 && (PGW - 1) * 4 + KW + 3 <= g.Wp) flags |= kX2VecRows;
     if (g.OW % 4 == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) flags |= kX2VecBias;
     if (g.POW % 2 == 0 && g.NPOS % 2 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 7) == 0 && (reinterpret_cast<uintptr_t>(map) & 7) == 0)
         flags |= kX2VecOut;
     const dim3 gd((unsigned)std::min(B, kNumSMs)), bd((unsigned)threads);
     DLB_LAUNCH_SMEM((conv_pool_forward_x2_kernel<KH, KW>), gd, bd, smem, st, x, gather_base, cursor, bias, filt, pooled, map, B, g, pl.act,
-                    pl.is_max, nfg, fgp, flags);
+                    pl.is_max, nfg, fgp, RS, flags);
     return true;
 }
 
