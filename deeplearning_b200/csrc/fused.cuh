@@ -313,7 +313,7 @@ struct alignas(16) f32x2_quad { f32x2 a, b; };   // two pairs = one 16-byte shar
 // (616 moves per 400 FFMA2 measured).  The image is double buffered and filled by cp.async one sample ahead (the gather
 // index two ahead): a sample costs ONE block barrier and the compute phase never waits on global memory.
 template <int KH, int KW>
-__global__ void __launch_bounds__(kX2Threads, 1) conv_pool_forward_x2_kernel(const float* __restrict__ x, const int* __restrict__ gather_base,
+__global__ void __launch_bounds__(kX2Threads, 2) conv_pool_forward_x2_kernel(const float* __restrict__ x, const int* __restrict__ gather_base,
                                                                                const int* __restrict__ cursor, const float* __restrict__ bias,
                                                                                const float* __restrict__ filt, float* __restrict__ pooled,
                                                                                int* __restrict__ map, int B, ConvPoolGeom g, int act, int is_max,
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kX2Threads, 1) conv_pool_forward_x2_kernel(con
     // staging: a warp copies whole image rows, lane = column: element (row, col) is the low half of slot col and the high
     // half of slot col - 2
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-    auto stage = [&](long long row, float* dst) {
+    auto stage = [&](int row, float* dst) {
         const float* xs = x + (size_t)row * n_in;
         for (int r = warp; r < g.C * g.H; r += nw) {
             const int c = g.C == 1 ? 0 : r / g.H;
@@ -356,12 +356,12 @@ __global__ void __launch_bounds__(kX2Threads, 1) conv_pool_forward_x2_kernel(con
             }
         }
     };
-    auto row_of = [&](int b) -> long long { return b < B ? (gather ? (long long)__ldg(gather + b) : (long long)b) : -1; };
+    auto row_of = [&](int b) -> int { return b < B ? (gather ? __ldg(gather + b) : b) : -1; };   // int on purpose: a widening here would wait for the load
 
     const int G = gridDim.x;
-    long long row_next = row_of((int)blockIdx.x + G);        // sample it + 1
+    int row_next = row_of((int)blockIdx.x + G);        // sample it + 1
     {
-        const long long row0 = row_of(blockIdx.x);
+        const int row0 = row_of(blockIdx.x);
         if (row0 >= 0) stage(row0, x_buf);
         stage_commit();
     }
@@ -934,7 +934,7 @@ inline bool conv_pool_forward_x2(cudaStream_t st, const ConvPoolPlan& pl, const 
     if (g.OW % 4 == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) flags |= kX2VecBias;
     if (g.POW % 2 == 0 && g.NPOS % 2 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 7) == 0 && (reinterpret_cast<uintptr_t>(map) & 7) == 0)
         flags |= kX2VecOut;
-    const dim3 gd((unsigned)std::min(B, kNumSMs)), bd((unsigned)threads);
+    const dim3 gd((unsigned)std::min(B, 2 * kNumSMs)), bd((unsigned)threads);   // two resident CTAs per SM
     DLB_LAUNCH_SMEM((conv_pool_forward_x2_kernel<KH, KW>), gd, bd, smem, st, x, gather_base, cursor, bias, filt, pooled, map, B, g, pl.act,
                     pl.is_max, nfg, fgp, RS, flags);
     return true;
