@@ -551,6 +551,164 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Staged variant of the backward kernel (same work split, same partial layout, same arithmetic order).  Everything a
+// sample needs - the image AND the index map / pooled values / pooled gradients of all F * NPOS windows - is copied into a
+// double buffer in shared memory by cp.async one sample ahead, so the compute phase never waits on global memory and a
+// sample costs one block barrier; the window geometry of a lane is fixed for the whole kernel (registers), and the
+// arg-max position is decoded from the index map by one subtraction and one comparison against the window's first flat
+// index - no integer division in the sample loop.  (ncu of the register-prefetch kernel: 75 % of the issued instructions
+// were address arithmetic, 15 % of the stall samples waits on the prefetch, 8 % barriers.)  2 x 2 windows only.
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef DLB_CUDA_EMU
+template <class T> __device__ __forceinline__ void stage_copy_elem(T* dst, const T* src) { *dst = *src; }
+#else
+template <class T> __device__ __forceinline__ void stage_copy_elem(T* dst, const T* src) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "cp.async element size");
+    if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+#endif
+__device__ __forceinline__ void stage_copy_16B(void* dst, const void* src) {
+#ifdef DLB_CUDA_EMU
+    for (int q = 0; q < 16; ++q) static_cast<char*>(dst)[q] = static_cast<const char*>(src)[q];
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
+}
+
+template <class R, int C, int KH, int KW, int WPL, int FMAX>
+__global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_staged_kernel(const R* __restrict__ x, const int* __restrict__ gather_base,
+                                                                                   const int* __restrict__ cursor, const R* __restrict__ dpool,
+                                                                                   const int* __restrict__ map, const R* __restrict__ pooled,
+                                                                                   R* __restrict__ partial, int B, ConvPoolGeom g, int act, int n_par,
+                                                                                   int buf_bytes, int vec_windows) {
+    DLB_DYNAMIC_SMEM(unsigned char, staged_smem);
+    const int* gather = resolve_gather(gather_base, cursor);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int f = tid / 32, lane = tid % 32;
+    constexpr int K = C * KH * KW;
+    const int NW = g.F * g.NPOS;                       // windows per sample
+    const int img_elems = C * g.Hp * g.bRS;
+    // buffer layout: image [C][Hp][bRS] (even columns, then odd columns at +bHO) | pooled [NW] | dpool [NW] | map [NW]
+    const int off_wp = (img_elems * (int)sizeof(R) + 15) & ~15;
+    const int off_wd = off_wp + ((NW * (int)sizeof(R) + 15) & ~15);
+    const int off_wm = off_wd + ((NW * (int)sizeof(R) + 15) & ~15);
+    for (int i = tid; i < 2 * buf_bytes / 4; i += nt) reinterpret_cast<int*>(staged_smem)[i] = 0;   // image borders stay zero
+    __syncthreads();
+
+    const int warp = tid >> 5, nw = nt >> 5;
+    const int n_in = C * g.H * g.W;
+    auto stage = [&](int b, int row, unsigned char* buf) {
+        R* img = reinterpret_cast<R*>(buf);
+        const R* xs = x + (size_t)row * n_in;
+        for (int r = warp; r < C * g.H; r += nw) {      // a warp copies whole image rows, lane = column
+            const int c = C == 1 ? 0 : r / g.H;
+            const int yy = r - c * g.H;
+            R* drow = img + (c * g.Hp + yy + g.ph) * g.bRS;
+            for (int xx = lane; xx < g.W; xx += 32) {
+                const int col = xx + g.pw;
+                stage_copy_elem(drow + (col & 1) * g.bHO + (col >> 1), xs + r * g.W + xx);
+            }
+        }
+        const size_t o = (size_t)b * NW;
+        if (vec_windows) {
+            const int nr = NW * (int)sizeof(R) / 16, ni = NW * 4 / 16;
+            for (int i = tid; i < nr; i += nt) {
+                stage_copy_16B(buf + off_wp + 16 * i, reinterpret_cast<const unsigned char*>(pooled + o) + 16 * i);
+                stage_copy_16B(buf + off_wd + 16 * i, reinterpret_cast<const unsigned char*>(dpool + o) + 16 * i);
+            }
+            for (int i = tid; i < ni; i += nt) stage_copy_16B(buf + off_wm + 16 * i, reinterpret_cast<const unsigned char*>(map + o) + 16 * i);
+        } else {
+            for (int i = tid; i < NW; i += nt) {
+                stage_copy_elem(reinterpret_cast<R*>(buf + off_wp) + i, pooled + o + i);
+                stage_copy_elem(reinterpret_cast<R*>(buf + off_wd) + i, dpool + o + i);
+                stage_copy_elem(reinterpret_cast<int*>(buf + off_wm) + i, map + o + i);
+            }
+        }
+    };
+    auto row_of = [&](int b) -> int { return b < B ? (gather ? __ldg(gather + b) : b) : -1; };
+
+    R dk[K];
+    R db[WPL][4];
+    int base_id[WPL], addr0[WPL];     // first flat index of the lane's window, shared-memory offset of its first element
+#pragma unroll
+    for (int k = 0; k < K; ++k) dk[k] = R(0);
+#pragma unroll
+    for (int wi = 0; wi < WPL; ++wi) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) db[wi][q] = R(0);
+        const int win = min(lane + 32 * wi, g.NPOS - 1);
+        const int py = win / g.POW, px = win - py * g.POW;
+        base_id[wi] = (f * g.OH + 2 * py) * g.OW + 2 * px;
+        addr0[wi] = 2 * py * g.bRS + px;
+    }
+
+    const int G = gridDim.x;
+    int row_next = row_of((int)blockIdx.x + G);
+    {
+        const int row0 = row_of(blockIdx.x);
+        if (row0 >= 0) stage(blockIdx.x, row0, staged_smem);
+        stage_commit();
+    }
+    int it = 0;
+    for (int b = blockIdx.x; b < B; b += G, ++it) {
+        stage_wait<0>();
+        __syncthreads();
+        const unsigned char* buf = staged_smem + (it & 1) * buf_bytes;
+        if (row_next >= 0) stage(b + G, row_next, staged_smem + ((it + 1) & 1) * buf_bytes);
+        stage_commit();
+        row_next = row_of(b + 2 * G);
+        const R* x_s = reinterpret_cast<const R*>(buf);
+        const R* wp_s = reinterpret_cast<const R*>(buf + off_wp) + f * g.NPOS;
+        const R* wd_s = reinterpret_cast<const R*>(buf + off_wd) + f * g.NPOS;
+        const int* wm_s = reinterpret_cast<const int*>(buf + off_wm) + f * g.NPOS;
+#pragma unroll
+        for (int wi = 0; wi < WPL; ++wi) {
+            const int win = lane + 32 * wi;
+            if (win >= g.NPOS) continue;
+            const int m = wm_s[win];
+            if (m < 0) continue;
+            const R gval = deriv_from_value<R>(act, wp_s[win]) * wd_s[win];
+            const int diff = m - base_id[wi];
+            const int dy = diff >= g.OW ? 1 : 0;
+            const int dx = diff - dy * g.OW;
+            const int sel = dy * 2 + dx;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) db[wi][q] += (q == sel) ? gval : R(0);
+            if (gval != R(0)) {   // the reference skips zero factors as well (Tensor.cpp:484-486)
+                // column 2 px + dx: even taps come from the half with the column's parity, odd taps from the other half
+                const R* pa = x_s + addr0[wi] + dy * g.bRS + dx * g.bHO;
+                const R* pb = x_s + addr0[wi] + dy * g.bRS + (dx ? 1 : g.bHO);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int ky = 0; ky < KH; ++ky) {
+                        const int ro = (c * g.Hp + ky) * g.bRS;
+#pragma unroll
+                        for (int kx = 0; kx < KW; ++kx)
+                            dk[(c * KH + ky) * KW + kx] += ((kx & 1) ? pb[ro + (kx >> 1)] : pa[ro + (kx >> 1)]) * gval;
+                    }
+            }
+        }
+    }
+    stage_wait<0>();
+
+    R* pb = partial + (size_t)blockIdx.x * n_par;
+#pragma unroll
+    for (int wi = 0; wi < WPL; ++wi) {
+        const int win = lane + 32 * wi;
+        if (win >= g.NPOS) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pb[base_id[wi] + (q >> 1) * g.OW + (q & 1)] = db[wi][q];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const R v = warp_sum<R>(dk[k]);
+        if (lane == 0) pb[g.F * g.OH * g.OW + f * K + k] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // The head: last NLayer (n <= NMAX outputs) forward, activation (incl. whole-vector softmax), cost derivative,
 // activation gradient g = dC/dz, and the input gradient dx = W^T g (optionally times the previous layer's activation
 // derivative recomputed from x, which IS that layer's output).  One warp per sample; W lives in shared memory.
@@ -978,10 +1136,46 @@ void conv_pool_backward_wpl(cudaStream_t st, const ConvPoolPlan& pl, int grid, c
 #undef DLB_CPB2
 }
 
+// Staged backward kernel: launches when its double buffer fits in shared memory; returns false otherwise.
+template <class R, int C, int KH, int KW>
+bool conv_pool_backward_staged(cudaStream_t st, const ConvPoolPlan& pl, int grid, const R* x, const int* gather_base, const int* cursor,
+                               const R* dpool, const int* map, const R* pooled, R* partial, int B) {
+    const ConvPoolGeom& g = pl.g;
+    const int NW = g.F * g.NPOS;
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t buf = up16((size_t)C * g.Hp * g.bRS * sizeof(R)) + 2 * up16((size_t)NW * sizeof(R)) + up16((size_t)NW * 4);
+    if (2 * buf > 200 * 1024) return false;
+    const bool vec = (NW * sizeof(R)) % 16 == 0 && (NW * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(dpool) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(pooled) & 15) == 0 && (reinterpret_cast<uintptr_t>(map) & 15) == 0;
+    const dim3 gd((unsigned)grid), bd((unsigned)pl.bwd_threads);
+#define DLB_CPBS2(WPL, FMAX)                                                                                                          \
+    DLB_LAUNCH_SMEM((conv_pool_backward_staged_kernel<R, C, KH, KW, WPL, FMAX>), gd, bd, 2 * buf, st, x, gather_base, cursor, dpool, map, \
+                    pooled, partial, B, g, pl.act, pl.n_par, (int)buf, vec ? 1 : 0)
+#define DLB_CPBS(WPL)                                          \
+    do {                                                       \
+        if (g.F <= 8) DLB_CPBS2(WPL, 8);                       \
+        else if (g.F <= 20) DLB_CPBS2(WPL, 20);                \
+        else DLB_CPBS2(WPL, 32);                               \
+    } while (0)
+    switch (pl.wpl) {
+    case 1: DLB_CPBS(1); break;
+    case 2: DLB_CPBS(2); break;
+    case 5: DLB_CPBS(5); break;
+    default: DLB_CPBS(8); break;
+    }
+#undef DLB_CPBS
+#undef DLB_CPBS2
+    return true;
+}
+
 template <class R>
 void conv_pool_backward(cudaStream_t st, const ConvPoolPlan& pl, int grid, const R* x, const int* gather_base, const int* cursor,
                         const R* dpool, const int* map, const R* pooled, R* partial, int B) {
     TagScope tag_("conv_pool_bwd");
+    if (pl.KH == 5 ? conv_pool_backward_staged<R, 1, 5, 5>(st, pl, grid, x, gather_base, cursor, dpool, map, pooled, partial, B)
+        : pl.g.C == 1 ? conv_pool_backward_staged<R, 1, 3, 3>(st, pl, grid, x, gather_base, cursor, dpool, map, pooled, partial, B)
+                      : conv_pool_backward_staged<R, 3, 3, 3>(st, pl, grid, x, gather_base, cursor, dpool, map, pooled, partial, B))
+        return;
     if (pl.KH == 5) conv_pool_backward_wpl<R, 1, 5, 5>(st, pl, grid, x, gather_base, cursor, dpool, map, pooled, partial, B);
     else if (pl.g.C == 1) conv_pool_backward_wpl<R, 1, 3, 3>(st, pl, grid, x, gather_base, cursor, dpool, map, pooled, partial, B);
     else conv_pool_backward_wpl<R, 3, 3, 3>(st, pl, grid, x, gather_base, cursor, dpool, map, pooled, partial, B);
