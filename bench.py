@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--real", default="f32", choices=["f32", "f64"])
     ap.add_argument("--batch", type=int, default=0, help="override the (global) mini-batch size")
+    ap.add_argument("--tc", type=int, default=1, choices=[0, 1, 2], help="fp32 contractions: 0 packed-FMA, 1 library default (tcgen05 from 128 samples per GPU), 2 tcgen05 always")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="multi-GPU gradient exchange")
     args = ap.parse_args()
 
@@ -283,6 +284,8 @@ def main():
     ctx = dl.Context(device=local_rank)
     net = dl.lenet(real=args.real, context=ctx)
     net.init_params(seed=0)
+    if args.real == "f32" and args.tc != 1:
+        net.enable_tensor_cores(args.tc)
     if world > 1 and args.collective == "nccl":
         uid = [dl.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)

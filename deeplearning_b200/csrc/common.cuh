@@ -72,6 +72,28 @@ struct TagScope {
 #endif
 #define DLB_LAUNCH(kernel, grid, block, stream, ...) DLB_LAUNCH_SMEM(kernel, grid, block, 0, stream, __VA_ARGS__)
 
+// Packed fp32 pairs for the FFMA2 pipe (`fma.rn.f32x2`, sm_100+): one instruction performs two IEEE fused multiply-adds
+// on a 64-bit register pair; the scalar operand is broadcast to both halves (SASS: FFMA2 Rd, Ra.F32x2.HI_LO, Rb.F32, Rc).
+// The emulator build carries the pair as a struct.
+#ifdef DLB_CUDA_EMU
+struct f32x2 { float lo, hi; };
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { return f32x2{lo, hi}; }
+__device__ __forceinline__ float lo_of(f32x2 v) { return v.lo; }
+__device__ __forceinline__ float hi_of(f32x2 v) { return v.hi; }
+__device__ __forceinline__ f32x2 ffma2_bcast(f32x2 a, float w, f32x2 c) { return f32x2{fmaf(a.lo, w, c.lo), fmaf(a.hi, w, c.hi)}; }
+#else
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo_of(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float hi_of(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ f32x2 ffma2_bcast(f32x2 a, float w, f32x2 c) {
+    f32x2 d;
+    asm("{ .reg .b64 ww; mov.b64 ww, {%2, %2}; fma.rn.f32x2 %0, %1, ww, %3; }" : "=l"(d) : "l"(a), "f"(w), "l"(c));
+    return d;
+}
+#endif
+struct alignas(16) f32x2_quad { f32x2 a, b; };   // two pairs = one 16-byte shared-memory load
+
 template <class T> __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
 constexpr int kNumSMs = 148;  // B200

@@ -257,7 +257,7 @@ struct dlb_net {
     virtual void evaluate_host(const void* x, const void* y, int64_t n, int cost, double l2_reg_factor, double* cost_out, double* correct_out) = 0;
     virtual std::string describe_plan() = 0;
     virtual void enable_graphs(bool on) = 0;
-    virtual void enable_tensor_cores(bool on) = 0;
+    virtual void enable_tensor_cores(int mode) = 0;
     virtual void p2p_export(void* handle64) = 0;
     virtual void p2p_connect(int rank, int world, const void* handles) = 0;
 };
@@ -367,7 +367,11 @@ struct NetT final : dlb_net {
     bool overlap_enabled = true;
     const void* ws_stamp = nullptr;   // the context scratch the captured graphs point into
     bool graphs_enabled = true;
-    bool use_tensor_cores = true;     // fp32 NLayer contractions on tcgen05 (3xTF32); off = FMA path (gemm.cuh)
+    // fp32 NLayer contractions: 0 = packed-FMA path (gemm.cuh), 1 = tcgen05 3xTF32 (tc_gemm.cuh) for mini-batches that fill
+    // at least one 128-row tensor-core tile (tc_min_batch samples per GPU) and the packed-FMA path below, 2 = tcgen05 always
+    int tc_mode = 1;
+    int tc_min_batch = 128;
+    bool tc_for(int B) const { return tc_mode == 2 || (tc_mode == 1 && B >= tc_min_batch); }
     void drop_graphs() {
 #ifndef DLB_CUDA_EMU
         for (auto& g : step_graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
@@ -646,7 +650,7 @@ struct NetT final : dlb_net {
             const R* bias = params + Y.param_off;
 #ifndef DLB_CUDA_EMU
             if constexpr (std::is_same_v<R, float>) {
-                if (use_tensor_cores) {   // y = act(X W^T + b): both operands reduction-contiguous
+                if (tc_for(B)) {   // y = act(X W^T + b): both operands reduction-contiguous
                     const TcOperand A{l == 0 ? x : out[(size_t)l - 1], (long long)Y.in_n, 0, l == 0 ? gather_base : nullptr, l == 0 ? cursor : nullptr, -1};
                     const TcOperand Bo{bias + Y.bias_n, (long long)Y.in_n, 0, nullptr, nullptr, -1};
                     tc_gemm(st, B, (int)Y.out_n, (int)Y.in_n, A, Bo, EpiFullForward<float>{out[(size_t)l], nullptr, bias, (int)Y.out_n, Y.s.activation}, lc.ws);
@@ -717,7 +721,7 @@ struct NetT final : dlb_net {
                 ws_stream = side_dw; ws_for_dw = ws_side; forked_dw = true;
             }
             if constexpr (std::is_same_v<R, float>) {
-                if (use_tensor_cores) {
+                if (tc_for(B)) {
                     {   // dW[n][k] = sum_b g[b][n] x[b][k], db[n] = sum_b g[b][n] (column of ones): both operands outer-contiguous
                         TagScope tag_("full_dW");
                         const TcOperand A{gl, (long long)Y.out_n, 1, nullptr, nullptr, -1};
@@ -1130,7 +1134,7 @@ struct NetT final : dlb_net {
         return d;
     }
     void enable_graphs(bool on) override { graphs_enabled = on; if (!on) drop_graphs(); }
-    void enable_tensor_cores(bool on) override { use_tensor_cores = on; drop_graphs(); }
+    void enable_tensor_cores(int mode) override { tc_mode = mode; drop_graphs(); }
 
     // Allocates the shared region [publish 0 | publish 1 | flags] and returns its CUDA IPC handle (64 bytes).
     void p2p_export(void* handle64) override {
@@ -1410,7 +1414,13 @@ int dlb_net_eval_host(dlb_net* net, const void* x, int64_t n, int32_t* classes, 
 int dlb_net_describe_plan(dlb_net* net, char* buf, int64_t cap) {
     return guarded([&] { DLB_REQUIRE(net && buf && cap > 0, "null argument"); std::snprintf(buf, (size_t)cap, "%s", net->describe_plan().c_str()); });
 }
-int dlb_net_enable_tensor_cores(dlb_net* net, int on) { return guarded([&] { DLB_REQUIRE(net, "null net"); net->enable_tensor_cores(on != 0); }); }
+int dlb_net_enable_tensor_cores(dlb_net* net, int mode) {
+    return guarded([&] {
+        DLB_REQUIRE(net, "null net");
+        DLB_REQUIRE(mode >= 0 && mode <= 2, "tensor-core mode must be 0 (off), 1 (auto) or 2 (always)");
+        net->enable_tensor_cores(mode);
+    });
+}
 
 // C[M][N] = sum_k A(m, k) * B(n, k) in fp32.  a_transposed / b_transposed: the operand is stored [K][M] / [K][N]
 // (leading dimension lda / ldb) instead of [M][K] / [N][K].  use_tensor_cores: tcgen05 3xTF32 (tc_gemm.cuh) or FMA.

@@ -209,24 +209,6 @@ __global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __r
 // Filters sit in shared memory tap-major [K][Fp] (Fp = filters padded to a multiple of 4): the 4 taps of a thread's
 // filters are one 16-byte broadcast load.  One sample per CTA iteration; filter groups beyond `fgp` are looped.
 // ---------------------------------------------------------------------------------------------------------------
-#ifdef DLB_CUDA_EMU
-struct f32x2 { float lo, hi; };
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) { return f32x2{lo, hi}; }
-__device__ __forceinline__ float lo_of(f32x2 v) { return v.lo; }
-__device__ __forceinline__ float hi_of(f32x2 v) { return v.hi; }
-__device__ __forceinline__ f32x2 ffma2_bcast(f32x2 a, float w, f32x2 c) { return f32x2{fmaf(a.lo, w, c.lo), fmaf(a.hi, w, c.hi)}; }
-#else
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ float lo_of(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
-__device__ __forceinline__ float hi_of(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
-__device__ __forceinline__ f32x2 ffma2_bcast(f32x2 a, float w, f32x2 c) {
-    f32x2 d;
-    asm("{ .reg .b64 ww; mov.b64 ww, {%2, %2}; fma.rn.f32x2 %0, %1, ww, %3; }" : "=l"(d) : "l"(a), "f"(w), "l"(c));
-    return d;
-}
-#endif
-
 constexpr int kX2Threads = 384;   // launch bound of the packed kernel, two CTAs per SM: 85 registers per thread
 constexpr int kX2VecBias = 2, kX2VecOut = 4;
 
@@ -304,8 +286,6 @@ __device__ __forceinline__ void stage_copy4(float* dst, const float* src) {
 __device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
-
-struct alignas(16) f32x2_quad { f32x2 a, b; };   // two pairs = one 16-byte shared-memory load
 
 // Shared-memory image of the packed kernel: every element slot holds the PAIR (x[col], x[col + 2]) of the zero-padded row
 // (8 bytes, row stride RS slots), so the pairs an FFMA2 consumes arrive as aligned 64-bit registers straight from 16-byte

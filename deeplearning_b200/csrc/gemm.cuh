@@ -85,6 +85,116 @@ gemm_kernel(int M, int N, int K, int k_per_split, AL a, BL b, EP ep, R* __restri
     }
 }
 
+// 64 x 64 output tile, 256 threads, 4 x 4 outputs per thread, BK reduction steps per stage.  The operand functors of the
+// next stage are evaluated into registers while the current stage is multiplied out of shared memory (two stages, one
+// barrier per stage).  Real = float runs the micro-kernel on the packed fp32 pipe: the 4 consecutive columns of a thread
+// are two register pairs fetched by one 16-byte load, the row operand is the broadcast scalar of FFMA2.
+template <class R> struct Gemm64 { static constexpr int BK = sizeof(R) == 4 ? 32 : 16; };
+
+template <class R, class AL, class BL, class EP>
+__global__ void __launch_bounds__(256)
+gemm64_kernel(int M, int N, int K, int k_per_split, AL a, BL b, EP ep, R* __restrict__ partials) {
+    constexpr int BM = 64, BN = 64, BK = Gemm64<R>::BK, NT = 256, PAD = 4;
+    constexpr int EPT = BM * BK / NT;               // operand elements per thread and stage (8 / 4)
+    __shared__ __align__(16) R As[2][BK][BM + PAD];
+    __shared__ __align__(16) R Bs[2][BK][BN + PAD];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int kb = blockIdx.z * k_per_split;
+    const int ke = min(K, kb + k_per_split);
+
+    R ra[EPT], rb[EPT];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int e = tid + q * NT;
+            int oo, rr;
+            if (AL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BM; rr = e / BM; }
+            ra[q] = (i0 + oo < M && k0 + rr < ke) ? a(i0 + oo, k0 + rr) : R(0);
+            if (BL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BN; rr = e / BN; }
+            rb[q] = (j0 + oo < N && k0 + rr < ke) ? b(j0 + oo, k0 + rr) : R(0);
+        }
+    };
+    auto store = [&](int s) {
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int e = tid + q * NT;
+            int oo, rr;
+            if (AL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BM; rr = e / BM; }
+            As[s][rr][oo] = ra[q];
+            if (BL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BN; rr = e / BN; }
+            Bs[s][rr][oo] = rb[q];
+        }
+    };
+
+    constexpr bool kPacked = sizeof(R) == 4;
+    f32x2 acc2[4][2];
+    R acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        acc2[i][0] = pack2(0.f, 0.f); acc2[i][1] = pack2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = R(0);
+    }
+
+    fetch(kb);
+    store(0);
+    __syncthreads();
+    int s = 0;
+    for (int k0 = kb; k0 < ke; k0 += BK, s ^= 1) {
+        const bool more = k0 + BK < ke;
+        if (more) fetch(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            if constexpr (kPacked) {
+                const float4 av = *reinterpret_cast<const float4*>(&As[s][kk][ty * 4]);
+                const f32x2_quad bq = *reinterpret_cast<const f32x2_quad*>(&Bs[s][kk][tx * 4]);
+                const float ar[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc2[i][0] = ffma2_bcast(bq.a, ar[i], acc2[i][0]);
+                    acc2[i][1] = ffma2_bcast(bq.b, ar[i], acc2[i][1]);
+                }
+            } else {
+                R ar[4], br[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ar[i] = As[s][kk][ty * 4 + i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) br[j] = Bs[s][kk][tx * 4 + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] += ar[i] * br[j];
+            }
+        }
+        if (more) store(s ^ 1);
+        __syncthreads();
+    }
+    if constexpr (kPacked) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            acc[i][0] = (R)lo_of(acc2[i][0]); acc[i][1] = (R)hi_of(acc2[i][0]);
+            acc[i][2] = (R)lo_of(acc2[i][1]); acc[i][3] = (R)hi_of(acc2[i][1]);
+        }
+    }
+
+    const bool split = gridDim.z > 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = i0 + ty * 4 + i;
+        if (gi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gj = j0 + tx * 4 + j;
+            if (gj >= N) continue;
+            if (split) partials[((size_t)blockIdx.z * M + gi) * N + gj] = acc[i][j];
+            else ep(gi, gj, acc[i][j]);
+        }
+    }
+}
+
 // Adds the split partials in split order and runs the epilogue once per output element.
 template <class R, class EP>
 __global__ void gemm_finalize_kernel(const R* __restrict__ partials, int splits, int M, int N, EP ep) {
@@ -109,15 +219,14 @@ struct GemmWorkspace {
     size_t bytes = 0;
 };
 
-// Host launcher: picks the tile (64x64 / 32x32) and the number of reduction splits so that even the skinny
-// contractions of small mini-batches put at least ~2 CTAs on each of the 148 SMs.
+// Host launcher: 64 x 64 tiles (32 x 32 for outputs smaller than one such tile) and as many reduction splits as it takes
+// for even the skinny contractions of small mini-batches to put about two CTAs on each of the 148 SMs.
 template <class R, class AL, class BL, class EP>
 void gemm(cudaStream_t st, int M, int N, int K, AL a, BL b, EP ep, const GemmWorkspace& ws) {
     if (M <= 0 || N <= 0) return;
-    constexpr int BK = 16;
-    const long tiles64 = (long)ceil_div(M, 64) * ceil_div(N, 64);
-    const bool big = tiles64 >= 2 * kNumSMs;
-    const int BM = big ? 64 : 32, BN = BM;
+    const bool small = M <= 32 || N <= 32;
+    const int BM = small ? 32 : 64, BN = BM;
+    const int BK = small ? 16 : Gemm64<R>::BK;
     const long tiles = (long)ceil_div(M, BM) * ceil_div(N, BN);
     int splits = 1;
     if (tiles < 2 * kNumSMs && K > 4 * BK) {
@@ -133,10 +242,10 @@ void gemm(cudaStream_t st, int M, int N, int K, AL a, BL b, EP ep, const GemmWor
     splits = ceil_div(K > 0 ? K : 1, k_per_split);
     const dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
     R* partials = static_cast<R*>(ws.ptr);
-    if (big) {
-        DLB_LAUNCH((gemm_kernel<R, 64, 64, BK, 4, 4, AL, BL, EP>), grid, dim3(256), st, M, N, K, k_per_split, a, b, ep, partials);
+    if (small) {
+        DLB_LAUNCH((gemm_kernel<R, 32, 32, 16, 2, 2, AL, BL, EP>), grid, dim3(256), st, M, N, K, k_per_split, a, b, ep, partials);
     } else {
-        DLB_LAUNCH((gemm_kernel<R, 32, 32, BK, 2, 2, AL, BL, EP>), grid, dim3(256), st, M, N, K, k_per_split, a, b, ep, partials);
+        DLB_LAUNCH((gemm64_kernel<R, AL, BL, EP>), grid, dim3(256), st, M, N, K, k_per_split, a, b, ep, partials);
     }
     if (splits > 1) {
         const size_t total = (size_t)M * N;

@@ -263,8 +263,10 @@ class Net:
         _capi.check(self.lib.dlb_net_describe_plan(self._handle(), buf, len(buf)))
         return buf.value.decode()
 
-    def enable_tensor_cores(self, on: bool) -> None:
-        _capi.check(self.lib.dlb_net_enable_tensor_cores(self._handle(), 1 if on else 0))
+    def enable_tensor_cores(self, mode) -> None:
+        """fp32 NLayer contractions: 0 / False = packed-FMA kernels, 1 / True = tcgen05 3xTF32 for mini-batches of at
+        least 128 samples per GPU (the default), 2 = tcgen05 at every batch size."""
+        _capi.check(self.lib.dlb_net_enable_tensor_cores(self._handle(), int(mode)))
 
     def enable_graphs(self, on: bool) -> None:
         _capi.check(self.lib.dlb_net_enable_graphs(self._handle(), 1 if on else 0))

@@ -143,9 +143,11 @@ DLB_API int dlb_net_describe_plan(dlb_net* net, char* buf, int64_t cap);
 /* CUDA-graph replay of the step on the resident-data path (on by default); off = every step launches its kernels. */
 DLB_API int dlb_net_enable_graphs(dlb_net* net, int on);
 
-/* fp32 NLayer contractions of the fused path on the tcgen05 tensor cores with 3xTF32 operand splitting (on by default
- * for Real = float); off = the FMA path.  Real = double always uses the FMA path (tcgen05 has no fp64 kind). */
-DLB_API int dlb_net_enable_tensor_cores(dlb_net* net, int on);
+/* fp32 NLayer contractions of the fused path: mode 1 (default) = tcgen05 tensor cores with 3xTF32 operand splitting for
+ * mini-batches that fill at least one 128-row tensor-core tile (128 samples per GPU) and the packed-FMA (FFMA2) kernels
+ * below that; 0 = packed-FMA always; 2 = tcgen05 always.  Real = double always uses the
+ * FMA path (tcgen05 has no fp64 kind). */
+DLB_API int dlb_net_enable_tensor_cores(dlb_net* net, int mode);
 
 /* Dense fp32 contraction C[M][N] = sum_k A(m,k) * B(n,k) (replaces CudaMatrix::mul_add / transpose_mul /
  * vector_col_times_vector_row style products, CudaMatrix.cu:227-498, for whole batches).  a_transposed / b_transposed:

@@ -40,14 +40,18 @@ def synthetic_params(n: int, specs, real: str, seed: int = 0) -> np.ndarray:
     return flat
 
 
-def make_pair(specs, real: str, seed: int = 0):
-    """(oracle net, gpu net) with identical parameters."""
+def make_pair(specs, real: str, seed: int = 0, tc_mode: int = 2):
+    """(oracle net, gpu net) with identical parameters.  tc_mode: 0 = packed-FMA contractions, 1 = the library default
+    (tcgen05 from 128 samples per batch), 2 = tcgen05 at every batch size (the default here, so that the small parity
+    cases exercise the tensor-core kernels)."""
     orc = ob.OracleNet(specs, real)
     params = synthetic_params(orc.param_count, specs, real, seed)
     orc.set_params(params)
     gpu = dl.Net([to_dl_spec(s) for s in specs], real=real)
     assert gpu.param_count == orc.param_count
     gpu.set_params(params)
+    if real == "f32":
+        gpu.enable_tensor_cores(tc_mode)
     return orc, gpu
 
 

@@ -94,12 +94,13 @@ def test_learn_matches_oracle(name, batch, n_items, lam, real):
     assert np.array_equal(gpu.predict(x), orc.eval(x)), "predicted classes differ"
 
 
-@pytest.mark.parametrize("real", ["f32", "f64"])
-def test_lenet_step_full_size(real):
+@pytest.mark.parametrize("real,tc_mode", [("f32", 2), ("f32", 1), ("f32", 0), ("f64", 1)])
+def test_lenet_step_full_size(real, tc_mode):
     """BASELINE configs[1] at its real size: one mini-batch of 256 through LeNet; gradient = sum over the batch of the
-    oracle's per-sample gradients; one update."""
+    oracle's per-sample gradients; one update.  f32 with the contractions on tcgen05 (modes 1, 2) and on the packed-FMA
+    kernels (mode 0)."""
     specs = ob.lenet_specs()
-    orc, gpu = H.make_pair(specs, real, seed=21)
+    orc, gpu = H.make_pair(specs, real, seed=21, tc_mode=tc_mode)
     n = 256 if real == "f32" else 64
     x, y = H.synthetic_batch(orc, n, real, seed=22, lo=0.0, hi=1.0)
     want = H.oracle_batch_trace(orc, x, y, ob.CROSS_ENTROPY)

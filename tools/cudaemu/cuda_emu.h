@@ -26,6 +26,9 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#ifndef __align__
+#define __align__(n) __attribute__((aligned(n)))
+#endif
 
 struct dim3 {
     unsigned x, y, z;
