@@ -209,26 +209,63 @@ __global__ void __launch_bounds__(TMAX, 1) conv_pool_forward_kernel(const R* __r
 // Filters sit in shared memory tap-major [K][Fp] (Fp = filters padded to a multiple of 4): the 4 taps of a thread's
 // filters are one 16-byte broadcast load.  One sample per CTA iteration; filter groups beyond `fgp` are looped.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kX2Threads = 384;   // launch bound of the packed kernel, two CTAs per SM: 85 registers per thread
+// Pair arithmetic of the kernel below: float = one FFMA2 on a 64-bit register pair, double = two DFMA on a {lo, hi} struct
+// (same data layout and control flow, so Real = double gets the staging / rolling-window structure as well).
+template <class R> struct PairOf;
+template <> struct PairOf<float> {
+    using type = f32x2;
+    static __device__ __forceinline__ type zero() { return pack2(0.f, 0.f); }
+    static __device__ __forceinline__ type fma(type a, float w, type c) { return ffma2_bcast(a, w, c); }
+    static __device__ __forceinline__ float lo(type v) { return lo_of(v); }
+    static __device__ __forceinline__ float hi(type v) { return hi_of(v); }
+};
+struct alignas(16) f64x2 { double lo, hi; };
+template <> struct PairOf<double> {
+    using type = f64x2;
+    static __device__ __forceinline__ type zero() { return f64x2{0.0, 0.0}; }
+    static __device__ __forceinline__ type fma(type a, double w, type c) { return f64x2{::fma(a.lo, w, c.lo), ::fma(a.hi, w, c.hi)}; }
+    static __device__ __forceinline__ double lo(type v) { return v.lo; }
+    static __device__ __forceinline__ double hi(type v) { return v.hi; }
+};
+template <class R> struct alignas(16) PairQuad { typename PairOf<R>::type a, b; };   // two pair slots
+template <class R> struct alignas(16) Vec4 { R v[4]; };                              // the 4 taps of a thread's filters
+
+#ifdef DLB_CUDA_EMU
+template <class T> __device__ __forceinline__ void stage_copy_elem(T* dst, const T* src) { *dst = *src; }
+#else
+template <class T> __device__ __forceinline__ void stage_copy_elem(T* dst, const T* src) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "cp.async element size");
+    if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+#endif
+
+constexpr int kX2Threads = 384;   // launch bound of the packed kernel; float: two CTAs per SM (80 registers per thread)
 constexpr int kX2VecBias = 2, kX2VecOut = 4;
 
-template <int ACT, bool IS_MAX>
-__device__ __forceinline__ void conv_pool_epilogue_x2(const f32x2 (&acc)[4][2][2], const float* __restrict__ bias, float* __restrict__ pooled,
+template <class R, int ACT, bool IS_MAX>
+__device__ __forceinline__ void conv_pool_epilogue_x2(const typename PairOf<R>::type (&acc)[4][2][2], const R* __restrict__ bias, R* __restrict__ pooled,
                                                       int* __restrict__ map, const ConvPoolGeom& g, int fs, int py, int pxg, size_t b, int flags) {
+    using P = PairOf<R>;
     const int col0 = pxg * 4;
-    float bzs[4][2][4];   // all untied biases first (one batch of loads in flight), then the arithmetic
+    R bzs[4][2][4];   // all untied biases first (one batch of loads in flight), then the arithmetic
 #pragma unroll
     for (int fi = 0; fi < 4; ++fi) {
         const int f = min(fs * 4 + fi, g.F - 1);
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
-            const float* src = bias + (f * g.OH + py * 2 + dy) * g.OW + col0;
-            if (flags & kX2VecBias) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(src));
-                bzs[fi][dy][0] = t.x; bzs[fi][dy][1] = t.y; bzs[fi][dy][2] = t.z; bzs[fi][dy][3] = t.w;
-            } else {
+            const R* src = bias + (f * g.OH + py * 2 + dy) * g.OW + col0;
+            bool vec = false;
+            if constexpr (sizeof(R) == 4) {
+                if (flags & kX2VecBias) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+                    bzs[fi][dy][0] = t.x; bzs[fi][dy][1] = t.y; bzs[fi][dy][2] = t.z; bzs[fi][dy][3] = t.w;
+                    vec = true;
+                }
+            }
+            if (!vec) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) bzs[fi][dy][q] = col0 + q < g.OW ? __ldg(src + q) : 0.f;
+                for (int q = 0; q < 4; ++q) bzs[fi][dy][q] = col0 + q < g.OW ? __ldg(src + q) : R(0);
             }
         }
     }
@@ -236,34 +273,39 @@ __device__ __forceinline__ void conv_pool_epilogue_x2(const f32x2 (&acc)[4][2][2
     for (int fi = 0; fi < 4; ++fi) {
         const int f = fs * 4 + fi;
         if (f >= g.F) continue;
-        float v[2][4];
+        R v[2][4];
         const int id0 = (f * g.OH + py * 2) * g.OW + col0;
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
-            const float* bz = bzs[fi][dy];
-            v[dy][0] = activation_ct<float, ACT>(lo_of(acc[fi][dy][0]) + bz[0]);
-            v[dy][1] = activation_ct<float, ACT>(lo_of(acc[fi][dy][1]) + bz[1]);
-            v[dy][2] = activation_ct<float, ACT>(hi_of(acc[fi][dy][0]) + bz[2]);
-            v[dy][3] = activation_ct<float, ACT>(hi_of(acc[fi][dy][1]) + bz[3]);
+            const R* bz = bzs[fi][dy];
+            v[dy][0] = activation_ct<R, ACT>(P::lo(acc[fi][dy][0]) + bz[0]);
+            v[dy][1] = activation_ct<R, ACT>(P::lo(acc[fi][dy][1]) + bz[1]);
+            v[dy][2] = activation_ct<R, ACT>(P::hi(acc[fi][dy][0]) + bz[2]);
+            v[dy][3] = activation_ct<R, ACT>(P::hi(acc[fi][dy][1]) + bz[3]);
         }
-        float best[2]; int best_id[2];
+        R best[2]; int best_id[2];
 #pragma unroll
         for (int pp = 0; pp < 2; ++pp) {
-            best[pp] = IS_MAX ? -real_limits<float>::max() : real_limits<float>::max();
+            best[pp] = IS_MAX ? -real_limits<R>::max() : real_limits<R>::max();
             best_id[pp] = -1;
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
-                    const float c = v[dy][pp * 2 + dx];
+                    const R c = v[dy][pp * 2 + dx];
                     if (IS_MAX ? (best[pp] < c) : (best[pp] > c)) { best[pp] = c; best_id[pp] = id0 + dy * g.OW + pp * 2 + dx; }   // strict: the first wins ties
                 }
         }
         const size_t o = (b * g.F + f) * g.NPOS + py * g.POW + pxg * 2;
-        if (flags & kX2VecOut) {
-            *reinterpret_cast<float2*>(pooled + o) = make_float2(best[0], best[1]);
-            *reinterpret_cast<int2*>(map + o) = make_int2(best_id[0], best_id[1]);
-        } else {
+        bool stored = false;
+        if constexpr (sizeof(R) == 4) {
+            if (flags & kX2VecOut) {
+                *reinterpret_cast<float2*>(pooled + o) = make_float2(best[0], best[1]);
+                *reinterpret_cast<int2*>(map + o) = make_int2(best_id[0], best_id[1]);
+                stored = true;
+            }
+        }
+        if (!stored) {
             pooled[o] = best[0]; map[o] = best_id[0];
             if (pxg * 2 + 1 < g.POW) { pooled[o + 1] = best[1]; map[o + 1] = best_id[1]; }
         }
@@ -292,24 +334,26 @@ template <int N> __device__ __forceinline__ void stage_wait() { asm volatile("cp
 // loads - ptxas otherwise keeps the patch as single registers and re-packs a pair with two MOVs in front of every FFMA2
 // (616 moves per 400 FFMA2 measured).  The image is double buffered and filled by cp.async one sample ahead (the gather
 // index two ahead): a sample costs ONE block barrier and the compute phase never waits on global memory.
-template <int KH, int KW>
-__global__ void __launch_bounds__(kX2Threads, 2) conv_pool_forward_x2_kernel(const float* __restrict__ x, const int* __restrict__ gather_base,
-                                                                               const int* __restrict__ cursor, const float* __restrict__ bias,
-                                                                               const float* __restrict__ filt, float* __restrict__ pooled,
+template <class R, int KH, int KW>
+__global__ void __launch_bounds__(kX2Threads, sizeof(R) == 4 ? 2 : 1) conv_pool_forward_x2_kernel(const R* __restrict__ x, const int* __restrict__ gather_base,
+                                                                               const int* __restrict__ cursor, const R* __restrict__ bias,
+                                                                               const R* __restrict__ filt, R* __restrict__ pooled,
                                                                                int* __restrict__ map, int B, ConvPoolGeom g, int act, int is_max,
                                                                                int nfg, int fgp, int RS, int flags) {
-    DLB_DYNAMIC_SMEM(float, smem);
+    using P = PairOf<R>;
+    using pair_t = typename P::type;
+    DLB_DYNAMIC_SMEM(R, smem);
     const int Fp = nfg * 4;
     const int img_stride = g.C * g.Hp * RS * 2;   // floats per image buffer (a multiple of 4: RS is even)
-    float* filt_s = smem;                 // [K][Fp], zero padded filters
-    float* x_buf = smem + g.K * Fp;       // two pair images [C][Hp][RS][2]
+    R* filt_s = smem;                 // [K][Fp], zero padded filters
+    R* x_buf = smem + g.K * Fp;       // two pair images [C][Hp][RS][2]
     const int* gather = resolve_gather(gather_base, cursor);
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < g.K * Fp; i += nt) {
         const int k = i / Fp, f = i - k * Fp;
-        filt_s[i] = f < g.F ? filt[f * g.K + k] : 0.f;
+        filt_s[i] = f < g.F ? filt[f * g.K + k] : R(0);
     }
-    for (int i = tid; i < 2 * img_stride; i += nt) x_buf[i] = 0.f;   // borders (padding) and unused slots stay zero
+    for (int i = tid; i < 2 * img_stride; i += nt) x_buf[i] = R(0);   // borders (padding) and unused slots stay zero
     __syncthreads();
 
     const int PGW = (g.POW + 1) / 2, NPG = g.POH * PGW;
@@ -322,17 +366,17 @@ __global__ void __launch_bounds__(kX2Threads, 2) conv_pool_forward_x2_kernel(con
     // staging: a warp copies whole image rows, lane = column: element (row, col) is the low half of slot col and the high
     // half of slot col - 2
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-    auto stage = [&](int row, float* dst) {
-        const float* xs = x + (size_t)row * n_in;
+    auto stage = [&](int row, R* dst) {
+        const R* xs = x + (size_t)row * n_in;
         for (int r = warp; r < g.C * g.H; r += nw) {
             const int c = g.C == 1 ? 0 : r / g.H;
             const int yy = r - c * g.H;
-            float* drow = dst + (size_t)((c * g.Hp + yy + g.ph) * RS) * 2;
+            R* drow = dst + (size_t)((c * g.Hp + yy + g.ph) * RS) * 2;
             for (int xx = lane; xx < g.W; xx += 32) {
                 const int cc = xx + g.pw;
-                const float* src = xs + r * g.W + xx;
-                stage_copy4(drow + cc * 2, src);
-                if (cc >= 2) stage_copy4(drow + (cc - 2) * 2 + 1, src);
+                const R* src = xs + r * g.W + xx;
+                stage_copy_elem(drow + cc * 2, src);
+                if (cc >= 2) stage_copy_elem(drow + (cc - 2) * 2 + 1, src);
             }
         }
     };
@@ -349,49 +393,48 @@ __global__ void __launch_bounds__(kX2Threads, 2) conv_pool_forward_x2_kernel(con
     for (int b = blockIdx.x; b < B; b += G, ++it) {
         stage_wait<0>();        // this thread's copies of sample `it` have landed
         __syncthreads();        // ... everyone's have, and everyone is done computing on the other buffer
-        const float* x_s = x_buf + (it & 1) * img_stride;
+        const R* x_s = x_buf + (it & 1) * img_stride;
         if (row_next >= 0) stage(row_next, x_buf + ((it + 1) & 1) * img_stride);
         stage_commit();
         row_next = row_of(b + 2 * G);
         if (active) {
             for (int fs = fsl; fs < nfg; fs += fgp) {
-                f32x2 acc[4][2][2];
+                pair_t acc[4][2][2];
 #pragma unroll
                 for (int fi = 0; fi < 4; ++fi)
 #pragma unroll
-                    for (int dy = 0; dy < 2; ++dy) { acc[fi][dy][0] = pack2(0.f, 0.f); acc[fi][dy][1] = pack2(0.f, 0.f); }
+                    for (int dy = 0; dy < 2; ++dy) { acc[fi][dy][0] = P::zero(); acc[fi][dy][1] = P::zero(); }
                 for (int c = 0; c < g.C; ++c) {
                     // rolling window over the patch rows: row r serves tap row ky = r (upper conv row) and ky = r - 1 (lower one),
                     // so only two rows of pairs are live at a time
-                    auto load_row = [&](int r, f32x2 (&pr)[NP]) {
-                        const f32x2_quad* q = reinterpret_cast<const f32x2_quad*>(x_s + (size_t)((c * g.Hp + py * 2 + r) * RS + pxg * 4) * 2);
+                    auto load_row = [&](int r, pair_t (&pr)[NP]) {
+                        const PairQuad<R>* q = reinterpret_cast<const PairQuad<R>*>(x_s + (size_t)((c * g.Hp + py * 2 + r) * RS + pxg * 4) * 2);
 #pragma unroll
-                        for (int j = 0; j < NP / 2; ++j) { const f32x2_quad t = q[j]; pr[2 * j] = t.a; pr[2 * j + 1] = t.b; }
+                        for (int j = 0; j < NP / 2; ++j) { const PairQuad<R> t = q[j]; pr[2 * j] = t.a; pr[2 * j + 1] = t.b; }
                     };
-                    const float* wbase = filt_s + c * (KH * KW) * Fp + fs * 4;
-                    f32x2 rows[2][NP];
+                    const R* wbase = filt_s + c * (KH * KW) * Fp + fs * 4;
+                    pair_t rows[2][NP];
                     load_row(0, rows[0]);
 #pragma unroll
                     for (int ky = 0; ky < KH; ++ky) {
                         load_row(ky + 1, rows[(ky + 1) & 1]);
 #pragma unroll
                         for (int kx = 0; kx < KW; ++kx) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(wbase + (ky * KW + kx) * Fp);
-                            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                            const Vec4<R> w4 = *reinterpret_cast<const Vec4<R>*>(wbase + (ky * KW + kx) * Fp);
 #pragma unroll
                             for (int fi = 0; fi < 4; ++fi)
 #pragma unroll
                                 for (int dy = 0; dy < 2; ++dy) {
-                                    acc[fi][dy][0] = ffma2_bcast(rows[(ky + dy) & 1][kx], wv[fi], acc[fi][dy][0]);
-                                    acc[fi][dy][1] = ffma2_bcast(rows[(ky + dy) & 1][kx + 1], wv[fi], acc[fi][dy][1]);
+                                    acc[fi][dy][0] = P::fma(rows[(ky + dy) & 1][kx], w4.v[fi], acc[fi][dy][0]);
+                                    acc[fi][dy][1] = P::fma(rows[(ky + dy) & 1][kx + 1], w4.v[fi], acc[fi][dy][1]);
                                 }
                         }
                     }
                 }
-#define DLB_EPI(ACT)                                                                                                  \
+#define DLB_EPI(ACT)                                                                                                     \
                 do {                                                                                                      \
-                    if (is_max) conv_pool_epilogue_x2<ACT, true>(acc, bias, pooled, map, g, fs, py, pxg, (size_t)b, flags);   \
-                    else conv_pool_epilogue_x2<ACT, false>(acc, bias, pooled, map, g, fs, py, pxg, (size_t)b, flags);         \
+                    if (is_max) conv_pool_epilogue_x2<R, ACT, true>(acc, bias, pooled, map, g, fs, py, pxg, (size_t)b, flags);   \
+                    else conv_pool_epilogue_x2<R, ACT, false>(acc, bias, pooled, map, g, fs, py, pxg, (size_t)b, flags);         \
                 } while (0)
                 switch (act) {
                 case DLB_ACT_RELU: DLB_EPI(DLB_ACT_RELU); break;
@@ -539,15 +582,6 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_kernel(const 
 // index - no integer division in the sample loop.  (ncu of the register-prefetch kernel: 75 % of the issued instructions
 // were address arithmetic, 15 % of the stall samples waits on the prefetch, 8 % barriers.)  2 x 2 windows only.
 // ---------------------------------------------------------------------------------------------------------------
-#ifdef DLB_CUDA_EMU
-template <class T> __device__ __forceinline__ void stage_copy_elem(T* dst, const T* src) { *dst = *src; }
-#else
-template <class T> __device__ __forceinline__ void stage_copy_elem(T* dst, const T* src) {
-    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "cp.async element size");
-    if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-#endif
 __device__ __forceinline__ void stage_copy_16B(void* dst, const void* src) {
 #ifdef DLB_CUDA_EMU
     for (int q = 0; q < 16; ++q) static_cast<char*>(dst)[q] = static_cast<const char*>(src)[q];
@@ -1055,10 +1089,10 @@ void conv_pool_forward_fpt(cudaStream_t st, const ConvPoolPlan& pl, int grid, co
 #undef DLB_CPF3
 }
 
-// Real = float: the packed-FMA kernel (one sample per CTA iteration; it sizes its own grid).
-template <int KH, int KW>
-inline bool conv_pool_forward_x2(cudaStream_t st, const ConvPoolPlan& pl, const float* x, const int* gather_base, const int* cursor,
-                                 const float* bias, const float* filt, float* pooled, int* map, int B) {
+// The pair kernel (one sample per CTA iteration; it sizes its own grid): FFMA2 for float, DFMA pairs for double.
+template <class R, int KH, int KW>
+inline bool conv_pool_forward_x2(cudaStream_t st, const ConvPoolPlan& pl, const R* x, const int* gather_base, const int* cursor,
+                                 const R* bias, const R* filt, R* pooled, int* map, int B) {
     const ConvPoolGeom& g = pl.g;
     const int PGW = ceil_div(g.POW, 2), NPG = g.POH * PGW;
     if (NPG > kX2Threads) return false;
@@ -1066,14 +1100,14 @@ inline bool conv_pool_forward_x2(cudaStream_t st, const ConvPoolPlan& pl, const 
     const int fgp = std::min(nfg, kX2Threads / NPG);
     const int threads = ceil_div(fgp * NPG, 32) * 32;
     const int RS = (std::max(g.Wp, PGW * 4 + KW + 1) + 1) & ~1;   // pair slots per image row: every 16-byte patch load stays inside its row
-    const size_t smem = ((size_t)g.K * nfg * 4 + 2 * (size_t)g.C * g.Hp * RS * 2) * sizeof(float);
+    const size_t smem = ((size_t)g.K * nfg * 4 + 2 * (size_t)g.C * g.Hp * RS * 2) * sizeof(R);
     if (smem > 200 * 1024) return false;
     int flags = 0;
     if (g.OW % 4 == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) flags |= kX2VecBias;
     if (g.POW % 2 == 0 && g.NPOS % 2 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 7) == 0 && (reinterpret_cast<uintptr_t>(map) & 7) == 0)
         flags |= kX2VecOut;
-    const dim3 gd((unsigned)std::min(B, 2 * kNumSMs)), bd((unsigned)threads);   // two resident CTAs per SM
-    DLB_LAUNCH_SMEM((conv_pool_forward_x2_kernel<KH, KW>), gd, bd, smem, st, x, gather_base, cursor, bias, filt, pooled, map, B, g, pl.act,
+    const dim3 gd((unsigned)std::min(B, (sizeof(R) == 4 ? 2 : 1) * kNumSMs)), bd((unsigned)threads);   // float: two resident CTAs per SM
+    DLB_LAUNCH_SMEM((conv_pool_forward_x2_kernel<R, KH, KW>), gd, bd, smem, st, x, gather_base, cursor, bias, filt, pooled, map, B, g, pl.act,
                     pl.is_max, nfg, fgp, RS, flags);
     return true;
 }
@@ -1082,11 +1116,9 @@ template <class R>
 void conv_pool_forward(cudaStream_t st, const ConvPoolPlan& pl, int grid, const R* x, const int* gather_base, const int* cursor,
                        const R* bias, const R* filt, R* pooled, int* map, int B) {
     TagScope tag_("conv_pool_fwd");
-    if constexpr (std::is_same<R, float>::value) {
-        if (pl.KH == 5 ? conv_pool_forward_x2<5, 5>(st, pl, x, gather_base, cursor, bias, filt, pooled, map, B)
-                       : conv_pool_forward_x2<3, 3>(st, pl, x, gather_base, cursor, bias, filt, pooled, map, B))
-            return;
-    }
+    if (pl.KH == 5 ? conv_pool_forward_x2<R, 5, 5>(st, pl, x, gather_base, cursor, bias, filt, pooled, map, B)
+                   : conv_pool_forward_x2<R, 3, 3>(st, pl, x, gather_base, cursor, bias, filt, pooled, map, B))
+        return;
     if (pl.KH == 5) conv_pool_forward_fpt<R, 5, 5>(st, pl, grid, x, gather_base, cursor, bias, filt, pooled, map, B);
     else conv_pool_forward_fpt<R, 3, 3>(st, pl, grid, x, gather_base, cursor, bias, filt, pooled, map, B);
 }
