@@ -443,7 +443,7 @@ struct NetT final : dlb_net {
         if (L() - 1 == 0) return;   // a single NLayer: the head would have to read the gathered data set
         const auto& H = layers.back();
         if (H.out_n > 32 || (size_t)H.out_n * (size_t)H.in_n * sizeof(R) > 96 * 1024) return;
-        plan.head_nmax = H.out_n <= 16 ? 16 : 32;
+        plan.head_nmax = H.out_n <= 10 ? 10 : H.out_n <= 16 ? 16 : 32;
         plan.ok = true;
     }
 
@@ -679,7 +679,11 @@ struct NetT final : dlb_net {
             const int grid = std::min((int)ceil_div(B, 8), 4 * kNumSMs);
             {
                 TagScope tag_("head");
-                if (plan.head_nmax == 16)
+                if (plan.head_nmax == 10)
+                    DLB_LAUNCH_SMEM((full_head_kernel<R, 10>), dim3((unsigned)grid), dim3(256), smem, st, (const R*)out[(size_t)h - 1], bias,
+                                    bias + Y.bias_n, refs, gather_base, cursor, out[(size_t)h], in_grad[(size_t)Ln], in_grad[(size_t)h], B,
+                                    (int)Y.in_n, (int)Y.out_n, Y.s.activation, cost, prev_act);
+                else if (plan.head_nmax == 16)
                     DLB_LAUNCH_SMEM((full_head_kernel<R, 16>), dim3((unsigned)grid), dim3(256), smem, st, (const R*)out[(size_t)h - 1], bias,
                                     bias + Y.bias_n, refs, gather_base, cursor, out[(size_t)h], in_grad[(size_t)Ln], in_grad[(size_t)h], B,
                                     (int)Y.in_n, (int)Y.out_n, Y.s.activation, cost, prev_act);

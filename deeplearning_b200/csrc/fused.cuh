@@ -751,51 +751,46 @@ __global__ void full_head_kernel(const R* __restrict__ x, const R* __restrict__ 
         for (int nn = 0; nn < NMAX; ++nn)
             if (nn < n) z[nn] = warp_sum<R>(z[nn]) + bias[nn];
 
-        // activation: y in z[], auxiliary (derivative or softmax exponent) in aux[]
-        R aux[NMAX];
-        R soft_sum = R(0);
+        // From here on lane nn owns output nn (lanes >= n mirror output 0 and are discarded): the activation, the cost
+        // derivative and the activation gradient are evaluated once per output instead of n times per lane; the sums over
+        // the outputs run in ascending order over shuffled values, i.e. in the order of the reference's loops.
+        const int mine = lane < n ? lane : 0;
+        R zl = z[0];
+#pragma unroll
+        for (int nn = 1; nn < NMAX; ++nn)
+            if (nn < n && mine == nn) zl = z[nn];
+        const size_t row = gather ? (size_t)gather[b] : (size_t)b;
+        const R refl = ref[row * n + mine];
+        R yl, auxl, ggl;
         if (act == DLB_ACT_SOFTMAX) {
             R m = z[0];
 #pragma unroll
             for (int nn = 1; nn < NMAX; ++nn)
                 if (nn < n && m < z[nn]) m = z[nn];
+            auxl = dl_exp<R>(zl - m);
+            R soft_sum = R(0);
 #pragma unroll
             for (int nn = 0; nn < NMAX; ++nn)
-                if (nn < n) { aux[nn] = dl_exp<R>(z[nn] - m); soft_sum += aux[nn]; }
-            const R factor = R(1) / soft_sum;
-#pragma unroll
-            for (int nn = 0; nn < NMAX; ++nn)
-                if (nn < n) z[nn] = aux[nn] * factor;
-        } else {
-#pragma unroll
-            for (int nn = 0; nn < NMAX; ++nn)
-                if (nn < n) { R d; z[nn] = apply_activation<R>(act, z[nn], d); aux[nn] = d; }
-        }
-        const size_t row = gather ? (size_t)gather[b] : (size_t)b;
-        R gg[NMAX];
-#pragma unroll
-        for (int nn = 0; nn < NMAX; ++nn) gg[nn] = nn < n ? cost_derivative<R>(cost_id, z[nn], ref[row * n + nn]) : R(0);
-        if (act == DLB_ACT_SOFTMAX) {   // ActivationFunctionHelper.cpp:50-58
-            const R ood = R(1) / soft_sum;
+                if (nn < n) soft_sum += __shfl_sync(0xffffffffu, auxl, nn);
+            yl = auxl * (R(1) / soft_sum);
+            const R ood = R(1) / soft_sum;                        // ActivationFunctionHelper.cpp:50-58
+            ggl = auxl * cost_derivative<R>(cost_id, yl, refl) * ood;
             R t = R(0);
 #pragma unroll
             for (int nn = 0; nn < NMAX; ++nn)
-                if (nn < n) { gg[nn] = aux[nn] * gg[nn] * ood; t += gg[nn]; }
-            const R temp_sum = t * ood;
-#pragma unroll
-            for (int nn = 0; nn < NMAX; ++nn)
-                if (nn < n) gg[nn] = gg[nn] - aux[nn] * temp_sum;
+                if (nn < n) t += __shfl_sync(0xffffffffu, ggl, nn);
+            ggl = ggl - auxl * (t * ood);
         } else {
-#pragma unroll
-            for (int nn = 0; nn < NMAX; ++nn)
-                if (nn < n) gg[nn] = aux[nn] * gg[nn];
+            yl = apply_activation<R>(act, zl, auxl);
+            ggl = auxl * cost_derivative<R>(cost_id, yl, refl);
         }
+        if (lane < n) {
+            g_out[(size_t)b * n + lane] = ggl;
+            if (out) out[(size_t)b * n + lane] = yl;
+        }
+        R gg[NMAX];
 #pragma unroll
-        for (int nn = 0; nn < NMAX; ++nn)
-            if (nn < n && lane == (nn % 32)) {
-                g_out[(size_t)b * n + nn] = gg[nn];
-                if (out) out[(size_t)b * n + nn] = z[nn];
-            }
+        for (int nn = 0; nn < NMAX; ++nn) gg[nn] = nn < n ? __shfl_sync(0xffffffffu, ggl, nn) : R(0);
         if (dx) {
             for (int k = lane; k < in_n; k += 32) {
                 R s = R(0);
