@@ -733,19 +733,46 @@ __global__ void full_head_kernel(const R* __restrict__ x, const R* __restrict__ 
                                  R* __restrict__ g_out, R* __restrict__ dx, int B, int in_n, int n, int act, int cost_id, int prev_act) {
     DLB_DYNAMIC_SMEM(R, W_s);
     const int* gather = resolve_gather(gather_base, cursor);
+    const int lane = threadIdx.x % 32, wpb = blockDim.x / 32;
+    // the first sample's operands are requested before the weights are staged: their latencies overlap
+    constexpr int XP = 4;
+    const int b_first = blockIdx.x * wpb + threadIdx.x / 32;
+    const bool pre = in_n <= 32 * XP;
+    R xpre[XP];
+#pragma unroll
+    for (int j = 0; j < XP; ++j) {
+        const int k = lane + 32 * j;
+        xpre[j] = (pre && b_first < B && k < in_n) ? x[(size_t)b_first * in_n + k] : R(0);
+    }
+    size_t row_pre = (b_first < B && gather) ? (size_t)gather[b_first] : (size_t)b_first;
     for (int i = threadIdx.x; i < n * in_n; i += blockDim.x) W_s[i] = W[i];
     __syncthreads();
-    const int lane = threadIdx.x % 32, wpb = blockDim.x / 32;
-    for (int b = blockIdx.x * wpb + threadIdx.x / 32; b < B; b += gridDim.x * wpb) {
+    for (int b = b_first; b < B; b += gridDim.x * wpb) {
         const R* xb = x + (size_t)b * in_n;
+        const size_t row = b == b_first ? row_pre : (gather ? (size_t)gather[b] : (size_t)b);
+        const int mine = lane < n ? lane : 0;
+        const R refl = ref[row * n + mine];
         R z[NMAX];
 #pragma unroll
         for (int nn = 0; nn < NMAX; ++nn) z[nn] = R(0);
-        for (int k = lane; k < in_n; k += 32) {
-            const R xv = xb[k];
+        if (pre) {
 #pragma unroll
-            for (int nn = 0; nn < NMAX; ++nn)
-                if (nn < n) z[nn] += W_s[nn * in_n + k] * xv;
+            for (int j = 0; j < XP; ++j) {
+                const int k = lane + 32 * j;
+                if (k < in_n) {
+                    const R xv = b == b_first ? xpre[j] : xb[k];
+#pragma unroll
+                    for (int nn = 0; nn < NMAX; ++nn)
+                        if (nn < n) z[nn] += W_s[nn * in_n + k] * xv;
+                }
+            }
+        } else {
+            for (int k = lane; k < in_n; k += 32) {
+                const R xv = xb[k];
+#pragma unroll
+                for (int nn = 0; nn < NMAX; ++nn)
+                    if (nn < n) z[nn] += W_s[nn * in_n + k] * xv;
+            }
         }
 #pragma unroll
         for (int nn = 0; nn < NMAX; ++nn)
@@ -754,13 +781,10 @@ __global__ void full_head_kernel(const R* __restrict__ x, const R* __restrict__ 
         // From here on lane nn owns output nn (lanes >= n mirror output 0 and are discarded): the activation, the cost
         // derivative and the activation gradient are evaluated once per output instead of n times per lane; the sums over
         // the outputs run in ascending order over shuffled values, i.e. in the order of the reference's loops.
-        const int mine = lane < n ? lane : 0;
         R zl = z[0];
 #pragma unroll
         for (int nn = 1; nn < NMAX; ++nn)
             if (nn < n && mine == nn) zl = z[nn];
-        const size_t row = gather ? (size_t)gather[b] : (size_t)b;
-        const R refl = ref[row * n + mine];
         R yl, auxl, ggl;
         if (act == DLB_ACT_SOFTMAX) {
             R m = z[0];
