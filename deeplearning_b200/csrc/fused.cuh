@@ -349,6 +349,11 @@ __global__ void __launch_bounds__(kX2Threads, sizeof(R) == 4 ? 2 : 1) conv_pool_
     R* x_buf = smem + g.K * Fp;       // two pair images [C][Hp][RS][2]
     const int* gather = resolve_gather(gather_base, cursor);
     const int tid = threadIdx.x, nt = blockDim.x;
+    // the gather indices of the first two samples are requested before anything else: their latency overlaps the set-up
+    auto row_of = [&](int b) -> int { return b < B ? (gather ? __ldg(gather + b) : b) : -1; };   // int on purpose: a widening here would wait for the load
+    const int G = gridDim.x;
+    const int row0 = row_of(blockIdx.x);
+    int row_next = row_of((int)blockIdx.x + G);        // sample it + 1
     for (int i = tid; i < g.K * Fp; i += nt) {
         const int k = i / Fp, f = i - k * Fp;
         filt_s[i] = f < g.F ? filt[f * g.K + k] : R(0);
@@ -380,15 +385,8 @@ __global__ void __launch_bounds__(kX2Threads, sizeof(R) == 4 ? 2 : 1) conv_pool_
             }
         }
     };
-    auto row_of = [&](int b) -> int { return b < B ? (gather ? __ldg(gather + b) : b) : -1; };   // int on purpose: a widening here would wait for the load
-
-    const int G = gridDim.x;
-    int row_next = row_of((int)blockIdx.x + G);        // sample it + 1
-    {
-        const int row0 = row_of(blockIdx.x);
-        if (row0 >= 0) stage(row0, x_buf);
-        stage_commit();
-    }
+    if (row0 >= 0) stage(row0, x_buf);
+    stage_commit();
     int it = 0;
     for (int b = blockIdx.x; b < B; b += G, ++it) {
         stage_wait<0>();        // this thread's copies of sample `it` have landed
@@ -599,6 +597,11 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_staged_kernel
     DLB_DYNAMIC_SMEM(unsigned char, staged_smem);
     const int* gather = resolve_gather(gather_base, cursor);
     const int tid = threadIdx.x, nt = blockDim.x;
+    // the gather indices of the first two samples are requested before anything else: their latency overlaps the set-up
+    auto row_of = [&](int b) -> int { return b < B ? (gather ? __ldg(gather + b) : b) : -1; };
+    const int G = gridDim.x;
+    const int row0 = row_of(blockIdx.x);
+    int row_next = row_of((int)blockIdx.x + G);
     const int f = tid / 32, lane = tid % 32;
     constexpr int K = C * KH * KW;
     const int NW = g.F * g.NPOS;                       // windows per sample
@@ -640,8 +643,6 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_staged_kernel
             }
         }
     };
-    auto row_of = [&](int b) -> int { return b < B ? (gather ? __ldg(gather + b) : b) : -1; };
-
     R dk[K];
     R db[WPL][4];
     int base_id[WPL], addr0[WPL];     // first flat index of the lane's window, shared-memory offset of its first element
@@ -657,13 +658,8 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_staged_kernel
         addr0[wi] = 2 * py * g.bRS + px;
     }
 
-    const int G = gridDim.x;
-    int row_next = row_of((int)blockIdx.x + G);
-    {
-        const int row0 = row_of(blockIdx.x);
-        if (row0 >= 0) stage(blockIdx.x, row0, staged_smem);
-        stage_commit();
-    }
+    if (row0 >= 0) stage(blockIdx.x, row0, staged_smem);
+    stage_commit();
     int it = 0;
     for (int b = blockIdx.x; b < B; b += G, ++it) {
         stage_wait<0>();
