@@ -565,7 +565,8 @@ struct NetT final : dlb_net {
     // ---- forward / backward over one batch --------------------------------------------------------------------
     // x: [rows][in0] device; gather (nullable): batch slot -> row of x.
     void forward(int B, const R* x, const int* gather, bool traces) {
-        const LaunchCtx lc = ctx->lc();
+        LaunchCtx lc = ctx->lc();
+        lc.tc = std::is_same_v<R, float> && tc_for(B);
         const R* in = x;
         const int* ga = gather;
         for (int l = 0; l < L(); ++l) {
@@ -588,7 +589,8 @@ struct NetT final : dlb_net {
 
     // Deltas enter in in_grad[L] (cost derivative).  scale: gradient_scale_factor on the previous gradient content.
     void backward(int B, const R* x, const int* gather, R scale) {
-        const LaunchCtx lc = ctx->lc();
+        LaunchCtx lc = ctx->lc();
+        lc.tc = std::is_same_v<R, float> && tc_for(B);
         const R* delta = in_grad[(size_t)L()];
         for (int l = L() - 1; l >= 0; --l) {
             const auto& Y = layers[(size_t)l];

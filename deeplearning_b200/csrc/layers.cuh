@@ -4,7 +4,11 @@
 // (Net.inl:257-277); here each runs once per step.
 #pragma once
 
+#include <algorithm>
+#include <type_traits>
+
 #include "gemm.cuh"
+#include "tc_gemm.cuh"
 
 namespace dlb {
 
@@ -440,7 +444,87 @@ __global__ void sgd_update_kernel(R* __restrict__ p, const R* __restrict__ g, si
 struct LaunchCtx {
     cudaStream_t stream;
     GemmWorkspace ws;
+    bool tc = false;     // Real = float only: contractions on the tensor cores (tc_gemm.cuh, 3xTF32) instead of the FMA path
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution on the tensor cores (Real = float).  The receptive-field matrix of the mini-batch
+// (Tensor.cpp:40-72 builds it per sample on the CPU) only exists as the index map of the producers (tc_tiles.cuh);
+// the 128-row MMA dimension is always the long one (pixels, or C*KH*KW for the filter gradient) and the MMA's N is the
+// filter / channel count rounded up to 16, so that 32- and 64-filter layers do not pay for 128 columns.
+//   forward          Y[(b,p)][f]   = sum_k  patch[(b,p)][k] * filters[f][k]            M = B*P,   N = F, K = C*KH*KW
+//   filter gradient  dK[k][f]      = sum_(b,p) patch[(b,p)][k] * G[b][f][p]            M = C*KH*KW, N = F, K = B*P (split)
+//   input gradient   dX[(b,yx)][c] = sum_(f,q) G-patch[(b,yx)][(f,q)] * filtersT[c][(f,q)]   M = B*H*W, N = C, K = F*KH*KW
+// The input gradient gathers the output gradient through the mirrored window (stride 1 only; other strides stay on the
+// FMA path) and reads the filters through a channel-major copy made by filters_channel_major_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef DLB_CUDA_EMU
+struct EpiConvForwardPix {  // i = (b, p), j = f: y[b][f][p] = act(acc + bias[f][p]) with the UNTIED bias (CLayer.inl:130)
+    static constexpr bool kLaneIsRow = true;
+    float* y; float* deriv; const float* bias; int F, P; int act;
+    __device__ __forceinline__ void operator()(int i, int f, float acc) const {
+        const int b = i / P, p = i - b * P;
+        float d; const float v = apply_activation<float>(act, acc + bias[(size_t)f * P + p], d);
+        const size_t o = ((size_t)b * F + f) * P + p;
+        y[o] = v;
+        if (deriv) deriv[o] = d;
+    }
+};
+
+struct EpiConvInputGradPix {  // i = (b, yx), j = channel c: dx[b][c][yx]
+    static constexpr bool kLaneIsRow = true;
+    float* dx; int C, HW;
+    __device__ __forceinline__ void operator()(int i, int c, float acc) const {
+        const int b = i / HW, yx = i - b * HW;
+        dx[((size_t)b * C + c) * HW + yx] = acc;
+    }
+};
+
+struct EpiAccumulateT {  // out[j][i] = scale != 0 ? scale * out[j][i] + acc : acc   (the transposed EpiAccumulate)
+    float* out; size_t ld; float scale;
+    __device__ __forceinline__ void operator()(int i, int j, float acc) const {
+        const size_t o = (size_t)j * ld + i;
+        out[o] = scale != 0.f ? acc + scale * out[o] : acc;
+    }
+};
+
+// filters[f][c][q] -> out[c][f * KK + q]
+__global__ void filters_channel_major_kernel(const float* __restrict__ filt, float* __restrict__ out, int F, int C, int KK) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= F * C * KK) return;
+    const int q = e % KK, fc = e / KK;
+    const int c = fc % C, f = fc / C;
+    out[((size_t)c * F + f) * KK + q] = filt[e];
+}
+
+inline bool tc_conv_ok(const ConvGeom& g, int B) {
+    return g.KH < 32768 && g.KW < 32768 && (long long)B * std::max(g.P, g.HW) < (1LL << 31) && g.P > 0;
+}
+
+inline void tc_conv_forward(const LaunchCtx& lc, int B, const ConvGeom& g, int act, const float* x, const int* gather, const int* cursor,
+                            const float* bias, const float* filters, float* y, float* deriv) {
+    const TcOperand A{x, 0, kPatchOuter, gather, cursor, -1, make_patch(g.C, g.H, g.W, g.OH, g.OW, g.KH, g.KW, g.sh, g.sw, -g.ph, -g.pw, 1)};
+    const TcOperand Bo{filters, (long long)g.K, kRedContig, nullptr, nullptr, -1, {}};
+    tc_gemm(lc.stream, B * g.P, g.F, g.K, A, Bo, EpiConvForwardPix{y, deriv, bias, g.F, g.P, act}, lc.ws);
+}
+
+inline void tc_conv_filter_gradient(const LaunchCtx& lc, int B, const ConvGeom& g, const float* x, const int* gather, const int* cursor,
+                                    const float* grad, float* dfilters, float scale) {
+    const TcOperand A{x, 0, kPatchRed, gather, cursor, -1, make_patch(g.C, g.H, g.W, g.OH, g.OW, g.KH, g.KW, g.sh, g.sw, -g.ph, -g.pw, 1)};
+    const TcOperand Bo{grad, 0, kPixelRed, nullptr, nullptr, -1, make_patch(g.F, g.OH, g.OW, g.OH, g.OW, 1, 1, 1, 1, 0, 0, 1)};
+    tc_gemm(lc.stream, g.K, g.F, B * g.P, A, Bo, EpiAccumulateT{dfilters, (size_t)g.K, scale}, lc.ws);
+}
+
+inline void tc_conv_input_gradient(const LaunchCtx& lc, int B, const ConvGeom& g, const float* grad, const float* filters, float* dx) {
+    // channel-major filter copy at the tail of the scratch; the contraction's split partials use the rest
+    const size_t wt_bytes = ((size_t)g.F * g.K * sizeof(float) + 255) & ~(size_t)255;
+    float* wt = reinterpret_cast<float*>(static_cast<unsigned char*>(lc.ws.ptr) + (lc.ws.bytes - wt_bytes));
+    DLB_LAUNCH((filters_channel_major_kernel), dim3((unsigned)ceil_div(g.F * g.K, 256)), dim3(256), lc.stream, filters, wt, g.F, g.C, g.KK);
+    const TcOperand A{grad, 0, kPatchOuter, nullptr, nullptr, -1, make_patch(g.F, g.OH, g.OW, g.H, g.W, g.KH, g.KW, 1, 1, g.ph, g.pw, -1)};
+    const TcOperand Bo{wt, (long long)g.F * g.KK, kRedContig, nullptr, nullptr, -1, {}};
+    tc_gemm(lc.stream, B * g.HW, g.C, g.F * g.KK, A, Bo, EpiConvInputGradPix{dx, g.C, g.HW}, GemmWorkspace{lc.ws.ptr, lc.ws.bytes - wt_bytes});
+}
+#endif
 
 template <class R>
 void softmax_forward(const LaunchCtx& lc, R* zy, R* aux, int rows, int n) {
@@ -455,8 +539,20 @@ void full_forward(const LaunchCtx& lc, int B, int in_n, int out_n, int act, cons
                   const R* bias, const R* W, R* y, R* deriv) {
     {
         TagScope tag_("full_fwd");
-        gemm<R>(lc.stream, B, out_n, in_n, DenseRowLoader<R>{x, (size_t)in_n, gather}, DenseRowLoader<R>{W, (size_t)in_n, nullptr},
-                EpiFullForward<R>{y, act == DLB_ACT_SOFTMAX ? nullptr : deriv, bias, out_n, act}, lc.ws);
+        bool done = false;
+#ifndef DLB_CUDA_EMU
+        if constexpr (std::is_same_v<R, float>) {
+            if (lc.tc) {
+                tc_gemm(lc.stream, B, out_n, in_n, TcOperand{x, (long long)in_n, kRedContig, gather, nullptr, -1, {}},
+                        TcOperand{W, (long long)in_n, kRedContig, nullptr, nullptr, -1, {}},
+                        EpiFullForward<float>{y, act == DLB_ACT_SOFTMAX ? nullptr : deriv, bias, out_n, act}, lc.ws);
+                done = true;
+            }
+        }
+#endif
+        if (!done)
+            gemm<R>(lc.stream, B, out_n, in_n, DenseRowLoader<R>{x, (size_t)in_n, gather}, DenseRowLoader<R>{W, (size_t)in_n, nullptr},
+                    EpiFullForward<R>{y, act == DLB_ACT_SOFTMAX ? nullptr : deriv, bias, out_n, act}, lc.ws);
     }
     if (act == DLB_ACT_SOFTMAX) softmax_forward<R>(lc, y, deriv, B, out_n);
 }
@@ -466,8 +562,18 @@ void conv_forward(const LaunchCtx& lc, int B, const ConvGeom& g, int act, const 
                   const R* bias, const R* filters, R* y, R* deriv) {
     {
         TagScope tag_("conv_fwd");
-        gemm<R>(lc.stream, g.F, B * g.P, g.K, DenseRowLoader<R>{filters, (size_t)g.K, nullptr}, Im2colLoader<R, false>{x, gather, g},
-                EpiConvForward<R>{y, act == DLB_ACT_SOFTMAX ? nullptr : deriv, bias, g.F, g.P, act}, lc.ws);
+        bool done = false;
+#ifndef DLB_CUDA_EMU
+        if constexpr (std::is_same_v<R, float>) {
+            if (lc.tc && tc_conv_ok(g, B)) {
+                tc_conv_forward(lc, B, g, act, x, gather, nullptr, bias, filters, y, act == DLB_ACT_SOFTMAX ? nullptr : deriv);
+                done = true;
+            }
+        }
+#endif
+        if (!done)
+            gemm<R>(lc.stream, g.F, B * g.P, g.K, DenseRowLoader<R>{filters, (size_t)g.K, nullptr}, Im2colLoader<R, false>{x, gather, g},
+                    EpiConvForward<R>{y, act == DLB_ACT_SOFTMAX ? nullptr : deriv, bias, g.F, g.P, act}, lc.ws);
     }
     if (act == DLB_ACT_SOFTMAX) softmax_forward<R>(lc, y, deriv, B, g.out_n);
 }
@@ -496,6 +602,23 @@ template <class R>
 void full_backward(const LaunchCtx& lc, int B, int in_n, int out_n, int act, const R* x, const int* gather, const R* delta,
                    const R* deriv, const R* W, R* g, R* dbias, R* dW, R* dx, R scale) {
     activation_grad_and_bias<R>(lc, B, out_n, act, delta, deriv, g, dbias, scale);
+#ifndef DLB_CUDA_EMU
+    if constexpr (std::is_same_v<R, float>) {
+        if (lc.tc) {
+            {   // dW[n][k] = sum_b g[b][n] x[b][k]: both operands outer-contiguous
+                TagScope tag_("full_dW");
+                tc_gemm(lc.stream, out_n, in_n, B, TcOperand{g, (long long)out_n, kOuterContig, nullptr, nullptr, -1, {}},
+                        TcOperand{x, (long long)in_n, kOuterContig, gather, nullptr, -1, {}}, EpiAccumulate<float>{dW, (size_t)in_n, scale}, lc.ws);
+            }
+            if (dx) {   // dx[b][k] = sum_n g[b][n] W[n][k]
+                TagScope tag_("full_dX");
+                tc_gemm(lc.stream, B, in_n, out_n, TcOperand{g, (long long)out_n, kRedContig, nullptr, nullptr, -1, {}},
+                        TcOperand{W, (long long)in_n, kOuterContig, nullptr, nullptr, -1, {}}, EpiStore<float>{dx, (size_t)in_n}, lc.ws);
+            }
+            return;
+        }
+    }
+#endif
     {
         TagScope tag_("full_dW");
         gemm<R>(lc.stream, out_n, in_n, B, DenseColLoader<R>{g, (size_t)out_n, nullptr}, DenseColLoader<R>{x, (size_t)in_n, gather},
@@ -513,15 +636,33 @@ template <class R>
 void conv_backward(const LaunchCtx& lc, int B, const ConvGeom& cg, int act, const R* x, const int* gather, const R* delta,
                    const R* deriv, const R* filters, R* g, R* dbias, R* dfilters, R* dx, R scale) {
     activation_grad_and_bias<R>(lc, B, cg.out_n, act, delta, deriv, g, dbias, scale);
+    bool tc = false;
+#ifndef DLB_CUDA_EMU
+    if constexpr (std::is_same_v<R, float>) tc = lc.tc && tc_conv_ok(cg, B);
+#endif
     {
         TagScope tag_("conv_dK");
-        gemm<R>(lc.stream, cg.F, cg.K, B * cg.P, GradPixelLoader<R>{g, cg.F, cg.P}, Im2colLoader<R, true>{x, gather, cg},
-                EpiAccumulate<R>{dfilters, (size_t)cg.K, scale}, lc.ws);
+        bool done = false;
+#ifndef DLB_CUDA_EMU
+        if constexpr (std::is_same_v<R, float>) {
+            if (tc) { tc_conv_filter_gradient(lc, B, cg, x, gather, nullptr, g, dfilters, scale); done = true; }
+        }
+#endif
+        if (!done)
+            gemm<R>(lc.stream, cg.F, cg.K, B * cg.P, GradPixelLoader<R>{g, cg.F, cg.P}, Im2colLoader<R, true>{x, gather, cg},
+                    EpiAccumulate<R>{dfilters, (size_t)cg.K, scale}, lc.ws);
     }
     if (dx) {
         TagScope tag_("conv_dX");
-        gemm<R>(lc.stream, cg.C, B * cg.HW, cg.F * cg.KK, FilterTLoader<R>{filters, cg.C, cg.KK}, GradGatherLoader<R>{g, cg},
-                EpiConvInputGrad<R>{dx, cg.C, cg.HW}, lc.ws);
+        bool done = false;
+#ifndef DLB_CUDA_EMU
+        if constexpr (std::is_same_v<R, float>) {
+            if (tc && cg.sh == 1 && cg.sw == 1) { tc_conv_input_gradient(lc, B, cg, g, filters, dx); done = true; }
+        }
+#endif
+        if (!done)
+            gemm<R>(lc.stream, cg.C, B * cg.HW, cg.F * cg.KK, FilterTLoader<R>{filters, cg.C, cg.KK}, GradGatherLoader<R>{g, cg},
+                    EpiConvInputGrad<R>{dx, cg.C, cg.HW}, lc.ws);
     }
 }
 

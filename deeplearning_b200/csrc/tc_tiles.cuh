@@ -1,0 +1,357 @@
+// tc_tiles.cuh — operand tiles of the tensor-core contraction (tc_gemm.cuh): which global element lands where in the
+// shared-memory tile that tcgen05.mma reads.  Pure index arithmetic around two copy primitives, written as
+// __host__ __device__ code so that tests/cpp/test_tc_tiles.cu can run every producer thread's part on the CPU and compare
+// the finished tiles with the definition value(outer, red) element by element (the only part of the tensor-core path that
+// can be checked without a GPU).
+//
+// An operand is a function value(outer, red): `outer` is the output row (A) or column (B) of the contraction, `red` the
+// reduction index.  Kinds:
+//   kRedContig   base[row(outer) * ld + red]                 NLayer forward X and W (NLayer.inl:131-142)
+//   kOuterContig base[row(red) * ld + outer]                 W^T, G^T, X^T of NLayer::backpropagate (NLayer.inl:144-171)
+//   kPatchOuter  receptive-field matrix, outer = pixel (b, py, px), red = (c, ky, kx)
+//                                                            CLayer::act (Tensor.cpp:371-408: rows of the im2col matrix) and,
+//                                                            with the window mirrored (sgn = -1), the input gradient
+//                                                            (Tensor.cpp:500-546)
+//   kPatchRed    the same matrix with outer = (c, ky, kx), red = pixel: the filter gradient (Tensor.cpp:466-498)
+//   kPixelRed    G[b][f][p] with outer = f, red = (b, p): the other operand of the filter gradient
+// A mini-batch is [B][C][H][W]; `gather` (layer 0) maps the batch slot to the row of the resident data set.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+
+#ifndef __CUDACC__
+#define DLB_HD inline
+#else
+#define DLB_HD __host__ __device__ __forceinline__
+#endif
+
+namespace dlb {
+
+enum TcKind : int { kRedContig = 0, kOuterContig = 1, kPatchOuter = 2, kPatchRed = 3, kPixelRed = 4 };
+
+// Geometry of a receptive-field operand: source tensor [SC][SH][SW] per sample, pixel grid PH x PW, window KH x KW.
+// Window tap (ky, kx) of pixel (py, px) reads source row py * sy + dy + sgn * ky, column px * sx + dx + sgn * kx
+// (forward: dy = -pad, sgn = +1; input gradient of a stride-1 convolution: dy = +pad, sgn = -1, source = output gradient).
+struct TcPatch {
+    int SC, SH, SW, PH, PW, KH, KW, sy, sx, dy, dx, sgn;
+    int SHW, KK, PP;     // SH * SW, KH * KW, PH * PW
+};
+
+struct TcOperand {
+    const float* base;
+    long long ld;              // kRedContig / kOuterContig: leading dimension; kPixelRed: unused
+    int kind;                  // TcKind
+    const int* gather_base;    // optional row / sample gather (device int32), addressed through *cursor when cursor != nullptr
+    const int* cursor;
+    int ones_col;              // kOuterContig: outer index that reads as 1 (bias folded into the contraction); -1: none
+    TcPatch patch;             // kPatchOuter / kPatchRed: the geometry; kPixelRed: SC = F, PP = P
+};
+
+inline TcPatch make_patch(int SC, int SH, int SW, int PH, int PW, int KH, int KW, int sy, int sx, int dy, int dx, int sgn) {
+    TcPatch p{SC, SH, SW, PH, PW, KH, KW, sy, sx, dy, dx, sgn, SH * SW, KH * KW, PH * PW};
+    return p;
+}
+
+namespace tc {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32;
+constexpr int kProducerWarps = 8;
+constexpr int kProducers = kProducerWarps * 32;            // producer threads
+constexpr int kOwned = 1024 / kProducers;                  // 16-byte chunks of a 128 x 32 fp32 tile per producer thread
+constexpr int kTileBytes = kBM * kBK * 4;                  // 16 KiB: one raw, hi or lo tile of either operand
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+#endif
+
+// The two copy primitives: asynchronous global -> shared copies on the device (zero fill through cp.async's src-size
+// operand), plain copies in the host check.
+DLB_HD void tile_copy16(unsigned char* dst, const float* src, int ok_bytes) {
+#ifdef __CUDA_ARCH__
+    cp_async_16(smem_u32(dst), src, (uint32_t)ok_bytes);
+#else
+    std::memset(dst, 0, 16);
+    std::memcpy(dst, src, (size_t)ok_bytes);
+#endif
+}
+DLB_HD void tile_copy4(unsigned char* dst, const float* src, bool ok) {
+#ifdef __CUDA_ARCH__
+    cp_async_4(smem_u32(dst), src, ok ? 4u : 0u);
+#else
+    const float v = ok ? *src : 0.f;
+    std::memcpy(dst, &v, 4);
+#endif
+}
+DLB_HD int load_index(const int* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+DLB_HD int imin(int a, int b) { return a < b ? a : b; }
+
+// Byte offset of 16-byte chunk c of tile row `row` in the K-major SWIZZLE_128B layout (row = 32 fp32 = 128 B; chunk c of
+// row r is stored at chunk c ^ (r & 7)).
+DLB_HD int chunk_off(int row, int c) { return row * 128 + ((c ^ (row & 7)) << 4); }
+
+// What a producer thread keeps per operand while it works on one output tile.
+struct TileOwner {
+    long long grow[kOwned];   // kRedContig: stored row of each owned chunk; kPixelRed: f * P; kPatchOuter: [0] = sample offset
+    int koff[kOwned];         // kPatchRed: c * SHW + sgn * (ky * SW + kx) of each owned tile row
+    int kyx[kOwned];          // kPatchRed: ky | kx << 16 of each owned tile row, -1: row beyond the operand
+    int iy0, ix0, valid;      // kPatchOuter: source row / column of tap (0, 0) of this thread's pixel
+};
+
+DLB_HD const int* resolve_rows(const TcOperand& op) {
+    return op.gather_base ? op.gather_base + (op.cursor ? load_index(op.cursor) : 0) : nullptr;
+}
+
+// Thread t of the producers; the tile covers outer indices [o0, o0 + 128) of [0, o_end).
+DLB_HD void owner_init(const TcOperand& op, int o0, int o_end, int t, TileOwner& w) {
+    if (op.kind == kRedContig || op.kind == kPixelRed) {
+        const int* gather = op.kind == kRedContig ? resolve_rows(op) : nullptr;
+#pragma unroll
+        for (int i = 0; i < kOwned; ++i) {
+            const int o = imin(o0 + ((t + kProducers * i) >> 3), o_end - 1);
+            if (op.kind == kPixelRed) w.grow[i] = (long long)o * op.patch.PP;
+            else w.grow[i] = gather ? (long long)load_index(gather + o) : (long long)o;
+        }
+    } else if (op.kind == kPatchOuter) {
+        const TcPatch& p = op.patch;
+        const int pix = o0 + (t & 127);
+        w.valid = pix < o_end;
+        const int pc = w.valid ? pix : 0;
+        const int b = pc / p.PP, rem = pc - b * p.PP;
+        const int py = rem / p.PW, px = rem - py * p.PW;
+        const int* gather = resolve_rows(op);
+        const long long s = (gather && w.valid) ? (long long)load_index(gather + b) : (long long)b;
+        w.grow[0] = s * p.SC * p.SHW;
+        w.iy0 = py * p.sy + p.dy;
+        w.ix0 = px * p.sx + p.dx;
+    } else if (op.kind == kPatchRed) {
+        const TcPatch& p = op.patch;
+#pragma unroll
+        for (int i = 0; i < kOwned; ++i) {
+            const int k = o0 + ((t + kProducers * i) >> 3);
+            if (k < o_end) {
+                const int c = k / p.KK, q = k - c * p.KK;
+                const int ky = q / p.KW, kx = q - ky * p.KW;
+                w.koff[i] = c * p.SHW + p.sgn * (ky * p.SW + kx);
+                w.kyx[i] = ky | (kx << 16);
+            } else {
+                w.koff[i] = 0; w.kyx[i] = -1;
+            }
+        }
+    }
+}
+
+// Issues this thread's copies of one k-block (reduction indices [r0, r0 + 32) of [.., r_end)) into the raw tile.
+// `rows`: tile rows the MMA reads (128 for A, the MMA's N for B); rows beyond are neither copied nor transformed.
+// Raw layouts: reduction-fast kinds (kRedContig, kPatchRed, kPixelRed) are copied straight into the K-major swizzled
+// layout; outer-fast kinds (kOuterContig, kPatchOuter) as plain [32 reduction rows][128 outer] and transposed by
+// transform_tile.
+DLB_HD void issue_tile(const TcOperand& op, const TileOwner& w, int o0, int o_end, int r0, int r_end, int t, int rows,
+                       unsigned char* raw) {
+    if (op.kind == kRedContig) {
+        const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0) && (((r_end - r0) & 3) == 0 || r0 + kBK <= r_end);
+        const int c = t & 7;
+#pragma unroll
+        for (int i = 0; i < kOwned; ++i) {
+            const int row = (t + kProducers * i) >> 3;
+            if (row >= rows) continue;
+            if (vec) {
+                const int r = r0 + 4 * c;
+                const bool ok = (o0 + row < o_end) && (r < r_end);
+                tile_copy16(raw + chunk_off(row, c), op.base + w.grow[i] * op.ld + imin(r, r_end - 4), ok ? 16 : 0);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r0 + 4 * c + j;
+                    const bool ok = (o0 + row < o_end) && (r < r_end);
+                    tile_copy4(raw + chunk_off(row, c) + 4 * j, op.base + w.grow[i] * op.ld + imin(r, r_end - 1), ok);
+                }
+            }
+        }
+    } else if (op.kind == kOuterContig) {
+        const int* gather = resolve_rows(op);
+        const int o_lim = imin(o_end, (int)op.ld);                 // the column of ones (o == ld) is synthesised in transform_tile
+        const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0);
+        if (vec) {
+            const int oc = (t & 31) * 4;
+            if (oc < rows) {
+#pragma unroll
+                for (int i = 0; i < kOwned; ++i) {
+                    const int k = (t + kProducers * i) >> 5;
+                    const int r = imin(r0 + k, r_end - 1);
+                    const long long grow = gather ? (long long)load_index(gather + r) : (long long)r;
+                    const int o = o0 + oc;
+                    int n_ok = (r0 + k < r_end) ? imin(4, o_lim - o) : 0;
+                    n_ok = n_ok < 0 ? 0 : n_ok;
+                    tile_copy16(raw + (k * 128 + oc) * 4, op.base + grow * op.ld + imin(o, (int)op.ld - 4), 4 * n_ok);
+                }
+            }
+        } else {
+            const int tt = t & 127, k0 = (t >> 7) * (kBK * 128 / kProducers);
+            if (tt < rows) {
+                const int o = o0 + tt;
+                const int oc = imin(imin(o, o_end - 1), (int)op.ld - 1);
+#pragma unroll
+                for (int kk = 0; kk < kBK * 128 / kProducers; ++kk) {
+                    const int k = k0 + kk;
+                    const int r = imin(r0 + k, r_end - 1);
+                    const long long grow = gather ? (long long)load_index(gather + r) : (long long)r;
+                    tile_copy4(raw + (k * 128 + tt) * 4, op.base + grow * op.ld + oc, o < o_lim && r0 + k < r_end);
+                }
+            }
+        }
+    } else if (op.kind == kPatchOuter) {
+        const TcPatch& p = op.patch;
+        const int tt = t & 127, k0 = (t >> 7) * (kBK * 128 / kProducers);
+        if (tt < rows) {
+            const int r = r0 + k0;
+            int c = r / p.KK;
+            const int q = r - c * p.KK;
+            int ky = q / p.KW, kx = q - ky * p.KW;
+#pragma unroll
+            for (int kk = 0; kk < kBK * 128 / kProducers; ++kk) {
+                const int iy = w.iy0 + p.sgn * ky, ix = w.ix0 + p.sgn * kx;
+                const bool ok = w.valid && (r + kk < r_end) && (unsigned)iy < (unsigned)p.SH && (unsigned)ix < (unsigned)p.SW;
+                const long long off = ok ? w.grow[0] + (long long)c * p.SHW + iy * p.SW + ix : 0;
+                tile_copy4(raw + ((k0 + kk) * 128 + tt) * 4, op.base + off, ok);
+                if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++c; } }
+            }
+        }
+    } else if (op.kind == kPatchRed) {
+        // this thread: the 4 pixels r0 + 4 (t & 7) + j of tile rows (t >> 3) + 32 i
+        const TcPatch& p = op.patch;
+        const int* gather = resolve_rows(op);
+        const int c = t & 7;
+        const int pix0 = r0 + 4 * c;
+        int b = pix0 / p.PP;
+        const int rem = pix0 - b * p.PP;
+        int py = rem / p.PW, px = rem - py * p.PW;
+        long long sbase[4]; int iy0[4], ix0[4]; bool okp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            okp[j] = pix0 + j < r_end;
+            const long long s = (gather && okp[j]) ? (long long)load_index(gather + b) : (long long)b;
+            iy0[j] = py * p.sy + p.dy; ix0[j] = px * p.sx + p.dx;
+            sbase[j] = s * p.SC * p.SHW + (long long)iy0[j] * p.SW + ix0[j];
+            if (++px == p.PW) { px = 0; if (++py == p.PH) { py = 0; ++b; } }
+        }
+#pragma unroll
+        for (int i = 0; i < kOwned; ++i) {
+            const int row = (t + kProducers * i) >> 3;
+            if (row >= rows) continue;
+            const int ky = w.kyx[i] & 0xFFFF, kx = w.kyx[i] >> 16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int iy = iy0[j] + p.sgn * ky, ix = ix0[j] + p.sgn * kx;
+                const bool ok = w.kyx[i] >= 0 && okp[j] && (unsigned)iy < (unsigned)p.SH && (unsigned)ix < (unsigned)p.SW;
+                tile_copy4(raw + chunk_off(row, c) + 4 * j, op.base + (ok ? sbase[j] + w.koff[i] : 0), ok);
+            }
+        }
+    } else {   // kPixelRed: G[(b * F + f) * P + p], tile row = f, reduction = (b, p)
+        const TcPatch& p = op.patch;
+        const int c = t & 7;
+        const int r = r0 + 4 * c;
+        int b = r / p.PP, pp = r - b * p.PP;
+        const bool vec = ((p.PP & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0);
+        if (vec) {
+            const long long off = (long long)b * p.SC * p.PP + pp;
+#pragma unroll
+            for (int i = 0; i < kOwned; ++i) {
+                const int row = (t + kProducers * i) >> 3;
+                if (row >= rows) continue;
+                const bool ok = (o0 + row < o_end) && (r < r_end);
+                tile_copy16(raw + chunk_off(row, c), op.base + (ok ? off + w.grow[i] : 0), ok ? 16 : 0);
+            }
+        } else {
+            long long off[4]; bool okr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                okr[j] = r + j < r_end;
+                off[j] = (long long)b * p.SC * p.PP + pp;
+                if (++pp == p.PP) { pp = 0; ++b; }
+            }
+#pragma unroll
+            for (int i = 0; i < kOwned; ++i) {
+                const int row = (t + kProducers * i) >> 3;
+                if (row >= rows) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool ok = (o0 + row < o_end) && okr[j];
+                    tile_copy4(raw + chunk_off(row, c) + 4 * j, op.base + (ok ? off[j] + w.grow[i] : 0), ok);
+                }
+            }
+        }
+    }
+}
+
+struct alignas(16) Quad { float x, y, z, w; };
+
+// raw fp32 chunk -> hi (TF32-representable: low 13 mantissa bits cleared) and lo (exact remainder) chunks at the same
+// offsets of the hi / lo tiles
+DLB_HD float tf32_hi(float v) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+#else
+    uint32_t u; std::memcpy(&u, &v, 4);
+    u &= 0xFFFFE000u;
+    float h; std::memcpy(&h, &u, 4);
+    return h;
+#endif
+}
+DLB_HD void split_store(Quad v, unsigned char* hi_tile, unsigned char* lo_tile, int off) {
+    Quad h, l;
+    h.x = tf32_hi(v.x); l.x = v.x - h.x;
+    h.y = tf32_hi(v.y); l.y = v.y - h.y;
+    h.z = tf32_hi(v.z); l.z = v.z - h.z;
+    h.w = tf32_hi(v.w); l.w = v.w - h.w;
+    *reinterpret_cast<Quad*>(hi_tile + off) = h;
+    *reinterpret_cast<Quad*>(lo_tile + off) = l;
+}
+
+DLB_HD void transform_tile(const TcOperand& op, int o0, int o_end, int r0, int r_end, int t, int rows,
+                           const unsigned char* raw_tile, unsigned char* hi_tile, unsigned char* lo_tile) {
+    if (op.kind == kRedContig || op.kind == kPatchRed || op.kind == kPixelRed) {
+#pragma unroll
+        for (int i = 0; i < kOwned; ++i) {
+            const int q = t + kProducers * i;
+            if ((q >> 3) >= rows) continue;
+            const int off = chunk_off(q >> 3, q & 7);
+            split_store(*reinterpret_cast<const Quad*>(raw_tile + off), hi_tile, lo_tile, off);
+        }
+    } else {
+        // thread t produces half of tile row t & 127 (outer index o0 + (t & 127)): a column of the raw [k][o] block
+        // (conflict-free: lanes read consecutive words), or the implicit column of ones
+        const float* raw = reinterpret_cast<const float*>(raw_tile);
+        const int tt = t & 127, c0 = (t >> 7) * (8 * 128 / kProducers);
+        if (tt >= rows) return;
+        const bool ones = op.kind == kOuterContig && (o0 + tt < o_end) && (o0 + tt == op.ones_col);
+#pragma unroll
+        for (int cc = 0; cc < 8 * 128 / kProducers; ++cc) {
+            const int c = c0 + cc;
+            Quad v;
+            if (ones) {
+                v.x = r0 + 4 * c < r_end ? 1.f : 0.f; v.y = r0 + 4 * c + 1 < r_end ? 1.f : 0.f;
+                v.z = r0 + 4 * c + 2 < r_end ? 1.f : 0.f; v.w = r0 + 4 * c + 3 < r_end ? 1.f : 0.f;
+            } else {
+                v.x = raw[(4 * c) * 128 + tt]; v.y = raw[(4 * c + 1) * 128 + tt];
+                v.z = raw[(4 * c + 2) * 128 + tt]; v.w = raw[(4 * c + 3) * 128 + tt];
+            }
+            split_store(v, hi_tile, lo_tile, chunk_off(tt, c));
+        }
+    }
+}
+
+}  // namespace tc
+}  // namespace dlb

@@ -473,3 +473,19 @@ def lenet(real: str = "f32", context: Optional[Context] = None) -> Net:
     sz = net.append_layer(NLayer(sz, 100, ActivationFunctionId.RELU))
     net.append_layer(NLayer(sz, 10, ActivationFunctionId.SOFTMAX))
     return net
+
+
+def cifar_deep(real: str = "f32", context: Optional[Context] = None) -> Net:
+    """BASELINE.json configs[2]: {3,32,32} -> C 5x5x32 pad 2 ReLU -> P max 2x2 -> C 5x5x64 pad 2 ReLU -> P max 2x2
+    -> C 3x3x128 pad 1 ReLU -> P max 2x2 -> N 2048->256 ReLU -> N 256->10 softmax (711 786 parameters)."""
+    net = Net(real=real, context=context)
+    relu = ActivationFunctionId.RELU
+    sz = net.append_layer(CLayer((3, 32, 32), (5, 5), 32, relu, paddings=(0, 2, 2)))
+    sz = net.append_layer(PLayer(sz, (2, 2), PoolTypeId.MAX))
+    sz = net.append_layer(CLayer(sz, (5, 5), 64, relu, paddings=(0, 2, 2)))
+    sz = net.append_layer(PLayer(sz, (2, 2), PoolTypeId.MAX))
+    sz = net.append_layer(CLayer(sz, (3, 3), 128, relu, paddings=(0, 1, 1)))
+    sz = net.append_layer(PLayer(sz, (2, 2), PoolTypeId.MAX))
+    sz = net.append_layer(NLayer(sz, 256, relu))
+    net.append_layer(NLayer(sz, 10, ActivationFunctionId.SOFTMAX))
+    return net

@@ -237,6 +237,38 @@ def test_cifar_deep_net_matches_oracle(real):
     assert np.array_equal(gpu.predict(x), orc.eval(x))
 
 
+def test_tensor_core_convolutions_match_fma_path_at_batch_96():
+    """Implicit-GEMM convolutions on tcgen05 (tc_gemm.cuh + tc_tiles.cuh) against the packed-FMA contraction, which the
+    tests above pin to the oracle: every layer buffer of the CIFAR-deep net at a batch that fills several 128-pixel tiles
+    per layer and splits the filter-gradient reduction; pooling index maps exactly."""
+    specs = ob.cifar_specs()
+    _, fma = H.make_pair(specs, "f32", seed=91, tc_mode=0)
+    orc, tcn = H.make_pair(specs, "f32", seed=91, tc_mode=2)
+    x, y = H.synthetic_batch(orc, 96, "f32", seed=92, lo=0.0, hi=1.0)
+    for net in (fma, tcn):
+        net.forward_backward(x, y, ob.CROSS_ENTROPY, 0.0)
+    for l, s in enumerate(specs):
+        H.assert_close(f"layer {l} output", tcn.read(dl.BUF_OUTPUT, l), fma.read(dl.BUF_OUTPUT, l), "f32")
+        if s.type == ob.PULL:
+            a, b = tcn.read(dl.BUF_INDEX_MAP, l), fma.read(dl.BUF_INDEX_MAP, l)
+            # an arg-max may legitimately move between two inputs that agree to rounding; the values must still agree (above)
+            assert np.mean(a != b) < 1e-4, f"layer {l}: {np.sum(a != b)} pooling indices differ"
+        elif s.type == ob.CONVOLUTION:
+            # ReLU'(z) is a step: a pre-activation within rounding of 0 may land on either side
+            da, db = tcn.read(dl.BUF_DERIVATIVES, l), fma.read(dl.BUF_DERIVATIVES, l)
+            assert np.mean(da != db) < 1e-5, f"layer {l}: {np.sum(da != db)} ReLU derivatives differ"
+        else:
+            H.assert_close(f"layer {l} derivatives", tcn.read(dl.BUF_DERIVATIVES, l), fma.read(dl.BUF_DERIVATIVES, l), "f32", rtol_mult=5)
+        if l > 0:
+            H.assert_close(f"layer {l} input gradient", tcn.read(dl.BUF_INPUT_GRAD, l), fma.read(dl.BUF_INPUT_GRAD, l), "f32", rtol_mult=20)
+    ga, gb = tcn.read(dl.BUF_GRADIENT), fma.read(dl.BUF_GRADIENT)
+    for l in range(len(specs)):
+        lo = tcn.layer_param_offset(l)
+        hi = tcn.layer_param_offset(l + 1) if l + 1 < len(specs) else tcn.param_count
+        if hi > lo:
+            H.assert_close(f"layer {l} parameter gradient", ga[lo:hi], gb[lo:hi], "f32", rtol_mult=20)
+
+
 @pytest.mark.parametrize("real", ["f32", "f64"])
 def test_evaluate_cost_and_correct_answers(real):
     """Net::evaluate_cost_function_and_correct_answers (Net.inl:411-439): mean cost + l2 * sum w^2, fraction correct."""
