@@ -655,7 +655,7 @@ struct NetT final : dlb_net {
                 if (tc_for(B)) {   // y = act(X W^T + b): both operands reduction-contiguous
                     const TcOperand A{l == 0 ? x : out[(size_t)l - 1], (long long)Y.in_n, 0, l == 0 ? gather_base : nullptr, l == 0 ? cursor : nullptr, -1};
                     const TcOperand Bo{bias + Y.bias_n, (long long)Y.in_n, 0, nullptr, nullptr, -1};
-                    tc_gemm(st, B, (int)Y.out_n, (int)Y.in_n, A, Bo, EpiFullForward<float>{out[(size_t)l], nullptr, bias, (int)Y.out_n, Y.s.activation}, lc.ws);
+                    tc_gemm<kRedContig, kRedContig>(st, B, (int)Y.out_n, (int)Y.in_n, A, Bo, EpiFullForward<float>{out[(size_t)l], nullptr, bias, (int)Y.out_n, Y.s.activation}, lc.ws);
                     continue;
                 }
             }
@@ -733,7 +733,7 @@ struct NetT final : dlb_net {
                         const TcOperand A{gl, (long long)Y.out_n, 1, nullptr, nullptr, -1};
                         const TcOperand Bo{l == 0 ? x : out[(size_t)l - 1], (long long)Y.in_n, 1, l == 0 ? gather_base : nullptr,
                                            l == 0 ? cursor : nullptr, (int)Y.in_n};
-                        tc_gemm(ws_stream, (int)Y.out_n, (int)Y.in_n + 1, B, A, Bo, EpiWeightAndBias<float>{db, db + Y.bias_n, (int)Y.in_n}, ws_for_dw);
+                        tc_gemm<kOuterContig, kOuterContig>(ws_stream, (int)Y.out_n, (int)Y.in_n + 1, B, A, Bo, EpiWeightAndBias<float>{db, db + Y.bias_n, (int)Y.in_n}, ws_for_dw);
                     }
                     if (l > 0) {   // dx[b][k] = sum_n g[b][n] W[n][k]: A reduction-contiguous, B (= W) outer-contiguous
                         TagScope tag_("full_dX");
@@ -741,7 +741,7 @@ struct NetT final : dlb_net {
                         const int prev_act = Pv.s.type == DLB_LAYER_FULL ? Pv.s.activation : 0;
                         const TcOperand A{gl, (long long)Y.out_n, 0, nullptr, nullptr, -1};
                         const TcOperand Bo{params + Y.param_off + Y.bias_n, (long long)Y.in_n, 1, nullptr, nullptr, -1};
-                        tc_gemm(st, B, (int)Y.in_n, (int)Y.out_n, A, Bo,
+                        tc_gemm<kRedContig, kOuterContig>(st, B, (int)Y.in_n, (int)Y.out_n, A, Bo,
                                 EpiStoreTimesDeriv<float>{in_grad[(size_t)l], (size_t)Y.in_n, out[(size_t)l - 1], prev_act}, lc.ws);
                     }
                     done_tc = true;
@@ -1440,8 +1440,13 @@ int dlb_matmul_f32(dlb_context* ctx, int M, int N, int K, const float* A, int64_
 #ifdef DLB_CUDA_EMU
             throw std::runtime_error("tensor cores are not available");
 #else
-            tc_gemm(ctx->stream, M, N, K, TcOperand{A, lda, a_transposed ? 1 : 0, nullptr, nullptr, -1},
-                    TcOperand{B, ldb, b_transposed ? 1 : 0, nullptr, nullptr, -1}, EpiStore<float>{C, (size_t)N}, ctx->ws);
+            const TcOperand oa{A, lda, a_transposed ? kOuterContig : kRedContig, nullptr, nullptr, -1, {}};
+            const TcOperand ob{B, ldb, b_transposed ? kOuterContig : kRedContig, nullptr, nullptr, -1, {}};
+            const EpiStore<float> ep{C, (size_t)N};
+            if (!a_transposed && !b_transposed) tc_gemm<kRedContig, kRedContig>(ctx->stream, M, N, K, oa, ob, ep, ctx->ws);
+            else if (!a_transposed && b_transposed) tc_gemm<kRedContig, kOuterContig>(ctx->stream, M, N, K, oa, ob, ep, ctx->ws);
+            else if (a_transposed && !b_transposed) tc_gemm<kOuterContig, kRedContig>(ctx->stream, M, N, K, oa, ob, ep, ctx->ws);
+            else tc_gemm<kOuterContig, kOuterContig>(ctx->stream, M, N, K, oa, ob, ep, ctx->ws);
 #endif
         } else {
             auto run = [&](auto al, auto bl) { gemm<float>(ctx->stream, M, N, K, al, bl, EpiStore<float>{C, (size_t)N}, ctx->ws); };

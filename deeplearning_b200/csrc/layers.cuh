@@ -497,22 +497,25 @@ __global__ void filters_channel_major_kernel(const float* __restrict__ filt, flo
     out[((size_t)c * F + f) * KK + q] = filt[e];
 }
 
+// Ranges the producers' 32-bit offsets, 15-bit tap masks and reciprocal divisions are exact for (tc_tiles.cuh).
 inline bool tc_conv_ok(const ConvGeom& g, int B) {
-    return g.KH < 32768 && g.KW < 32768 && (long long)B * std::max(g.P, g.HW) < (1LL << 31) && g.P > 0;
+    return g.KH <= 15 && g.KW <= 15 && g.P > 0 && g.H <= 2048 && g.W <= 2048 && g.OH <= 2048 && g.OW <= 2048 &&
+           (long long)g.F * g.KK < 65536 && g.K < 65536 &&
+           (long long)B * std::max(g.in_n, g.out_n) < (1LL << 31);
 }
 
 inline void tc_conv_forward(const LaunchCtx& lc, int B, const ConvGeom& g, int act, const float* x, const int* gather, const int* cursor,
                             const float* bias, const float* filters, float* y, float* deriv) {
     const TcOperand A{x, 0, kPatchOuter, gather, cursor, -1, make_patch(g.C, g.H, g.W, g.OH, g.OW, g.KH, g.KW, g.sh, g.sw, -g.ph, -g.pw, 1)};
     const TcOperand Bo{filters, (long long)g.K, kRedContig, nullptr, nullptr, -1, {}};
-    tc_gemm(lc.stream, B * g.P, g.F, g.K, A, Bo, EpiConvForwardPix{y, deriv, bias, g.F, g.P, act}, lc.ws);
+    tc_gemm<kPatchOuter, kRedContig>(lc.stream, B * g.P, g.F, g.K, A, Bo, EpiConvForwardPix{y, deriv, bias, g.F, g.P, act}, lc.ws);
 }
 
 inline void tc_conv_filter_gradient(const LaunchCtx& lc, int B, const ConvGeom& g, const float* x, const int* gather, const int* cursor,
                                     const float* grad, float* dfilters, float scale) {
     const TcOperand A{x, 0, kPatchRed, gather, cursor, -1, make_patch(g.C, g.H, g.W, g.OH, g.OW, g.KH, g.KW, g.sh, g.sw, -g.ph, -g.pw, 1)};
     const TcOperand Bo{grad, 0, kPixelRed, nullptr, nullptr, -1, make_patch(g.F, g.OH, g.OW, g.OH, g.OW, 1, 1, 1, 1, 0, 0, 1)};
-    tc_gemm(lc.stream, g.K, g.F, B * g.P, A, Bo, EpiAccumulateT{dfilters, (size_t)g.K, scale}, lc.ws);
+    tc_gemm<kPatchRed, kPixelRed>(lc.stream, g.K, g.F, B * g.P, A, Bo, EpiAccumulateT{dfilters, (size_t)g.K, scale}, lc.ws);
 }
 
 inline void tc_conv_input_gradient(const LaunchCtx& lc, int B, const ConvGeom& g, const float* grad, const float* filters, float* dx) {
@@ -522,7 +525,7 @@ inline void tc_conv_input_gradient(const LaunchCtx& lc, int B, const ConvGeom& g
     DLB_LAUNCH((filters_channel_major_kernel), dim3((unsigned)ceil_div(g.F * g.K, 256)), dim3(256), lc.stream, filters, wt, g.F, g.C, g.KK);
     const TcOperand A{grad, 0, kPatchOuter, nullptr, nullptr, -1, make_patch(g.F, g.OH, g.OW, g.H, g.W, g.KH, g.KW, 1, 1, g.ph, g.pw, -1)};
     const TcOperand Bo{wt, (long long)g.F * g.KK, kRedContig, nullptr, nullptr, -1, {}};
-    tc_gemm(lc.stream, B * g.HW, g.C, g.F * g.KK, A, Bo, EpiConvInputGradPix{dx, g.C, g.HW}, GemmWorkspace{lc.ws.ptr, lc.ws.bytes - wt_bytes});
+    tc_gemm<kPatchOuter, kRedContig>(lc.stream, B * g.HW, g.C, g.F * g.KK, A, Bo, EpiConvInputGradPix{dx, g.C, g.HW}, GemmWorkspace{lc.ws.ptr, lc.ws.bytes - wt_bytes});
 }
 #endif
 
@@ -543,7 +546,7 @@ void full_forward(const LaunchCtx& lc, int B, int in_n, int out_n, int act, cons
 #ifndef DLB_CUDA_EMU
         if constexpr (std::is_same_v<R, float>) {
             if (lc.tc) {
-                tc_gemm(lc.stream, B, out_n, in_n, TcOperand{x, (long long)in_n, kRedContig, gather, nullptr, -1, {}},
+                tc_gemm<kRedContig, kRedContig>(lc.stream, B, out_n, in_n, TcOperand{x, (long long)in_n, kRedContig, gather, nullptr, -1, {}},
                         TcOperand{W, (long long)in_n, kRedContig, nullptr, nullptr, -1, {}},
                         EpiFullForward<float>{y, act == DLB_ACT_SOFTMAX ? nullptr : deriv, bias, out_n, act}, lc.ws);
                 done = true;
@@ -607,12 +610,12 @@ void full_backward(const LaunchCtx& lc, int B, int in_n, int out_n, int act, con
         if (lc.tc) {
             {   // dW[n][k] = sum_b g[b][n] x[b][k]: both operands outer-contiguous
                 TagScope tag_("full_dW");
-                tc_gemm(lc.stream, out_n, in_n, B, TcOperand{g, (long long)out_n, kOuterContig, nullptr, nullptr, -1, {}},
+                tc_gemm<kOuterContig, kOuterContig>(lc.stream, out_n, in_n, B, TcOperand{g, (long long)out_n, kOuterContig, nullptr, nullptr, -1, {}},
                         TcOperand{x, (long long)in_n, kOuterContig, gather, nullptr, -1, {}}, EpiAccumulate<float>{dW, (size_t)in_n, scale}, lc.ws);
             }
             if (dx) {   // dx[b][k] = sum_n g[b][n] W[n][k]
                 TagScope tag_("full_dX");
-                tc_gemm(lc.stream, B, in_n, out_n, TcOperand{g, (long long)out_n, kRedContig, nullptr, nullptr, -1, {}},
+                tc_gemm<kRedContig, kOuterContig>(lc.stream, B, in_n, out_n, TcOperand{g, (long long)out_n, kRedContig, nullptr, nullptr, -1, {}},
                         TcOperand{W, (long long)in_n, kOuterContig, nullptr, nullptr, -1, {}}, EpiStore<float>{dx, (size_t)in_n}, lc.ws);
             }
             return;

@@ -119,7 +119,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int tiles_m, int tiles_n
 // mma_n: the N of the MMA instruction (a multiple of 16; < 128 only when the whole output is one column tile narrower
 // than that - the convolutions with 32 / 64 filters or channels - so that neither the tensor pipe nor the producers
 // spend time on columns that do not exist).
-template <class EP>
+template <class EP, int KA, int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, int n_tiles, int n_splits, int mma_n, TcOperand a, TcOperand b, EP ep,
                float* __restrict__ partials) {
@@ -154,12 +154,12 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
         int nt_tile = blockIdx.x;            // tile of the next k-block to issue
         int nt_k = 0;
         TileCoord nc{};
-        TileOwner nwa, nwb;
+        TileOwner<KA> nwa; TileOwner<KB> nwb;
         auto open_next = [&]() {
             if (nt_tile < n_tiles) {
                 nc = decode_tile(nt_tile, tiles_m, tiles_n, K, k_per_split);
-                owner_init(a, nc.i0, M, tid, nwa);
-                owner_init(b, nc.j0, N, tid, nwb);
+                owner_init<KA>(a, nc.i0, M, tid, nwa);
+                owner_init<KB>(b, nc.j0, N, tid, nwb);
             }
         };
         open_next();
@@ -168,8 +168,8 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
             if (nt_tile < n_tiles) {
                 unsigned char* raw = raw_ring + (int)(issued % kRaw) * kRawBytes;
                 const int r0 = nc.kb + nt_k * kBK;
-                issue_tile(a, nwa, nc.i0, M, r0, nc.ke, tid, kBM, raw);
-                issue_tile(b, nwb, nc.j0, N, r0, nc.ke, tid, mma_n, raw + kTileBytes);
+                issue_tile<KA>(a, nwa, nc.i0, M, r0, nc.ke, tid, kBM, raw);
+                issue_tile<KB>(b, nwb, nc.j0, N, r0, nc.ke, tid, mma_n, raw + kTileBytes);
                 ++issued;
                 if (++nt_k == nc.nkb) { nt_k = 0; nt_tile += gridDim.x; open_next(); }
             }
@@ -191,8 +191,8 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
                 const unsigned char* raw = raw_ring + (int)(git % kRaw) * kRawBytes;
                 unsigned char* st = smem + s * kStageBytes;
                 const int r0 = c.kb + it * kBK;
-                transform_tile(a, c.i0, M, r0, c.ke, tid, kBM, raw, st, st + kTileBytes);
-                transform_tile(b, c.j0, N, r0, c.ke, tid, mma_n, raw + kTileBytes, st + 2 * kTileBytes, st + 3 * kTileBytes);
+                transform_tile<KA>(a, c.i0, M, r0, c.ke, tid, kBM, raw, st, st + kTileBytes);
+                transform_tile<KB>(b, c.j0, N, r0, c.ke, tid, mma_n, raw + kTileBytes, st + 2 * kTileBytes, st + 3 * kTileBytes);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (UMMA) reads
                 mbar_arrive(smem_u32(&bar_full[s]));
             }
@@ -317,10 +317,12 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
 
 }  // namespace tc
 
-// Host launcher.  Falls back to nothing: callers decide (by Real type and shape) whether to use this or gemm<R>.
-template <class EP>
+// Host launcher, instantiated per pair of operand kinds (the kernel carries only the producers it needs).  Falls back to
+// nothing: callers decide (by Real type and shape) whether to use this or gemm<R>.
+template <int KA, int KB, class EP>
 void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcOperand& b, EP ep, const GemmWorkspace& ws) {
     if (M <= 0 || N <= 0) return;
+    if (a.kind != KA || b.kind != KB) throw std::logic_error("tc_gemm: operand kind does not match the instantiation");
     const long tiles = (long)ceil_div(M, tc::kBM) * ceil_div(N, tc::kBN);
     const int kblocks = ceil_div(K > 0 ? K : 1, tc::kBK);
     // Persistent CTAs (one per SM): split the reduction only as far as the split tiles still fit in ONE wave, so that no
@@ -341,7 +343,7 @@ void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcO
     const int mma_n = tiles_n == 1 ? std::min(tc::kBN, ceil_div(N, 16) * 16) : tc::kBN;
     const dim3 grid((unsigned)std::min(n_tiles, kNumSMs));
     float* partials = static_cast<float*>(ws.ptr);
-    DLB_LAUNCH_SMEM((tc::tc_gemm_kernel<EP>), grid, dim3(tc::kThreads), (size_t)tc::kSmemBytes, st, M, N, K, k_per_split, tiles_m, tiles_n,
+    DLB_LAUNCH_SMEM((tc::tc_gemm_kernel<EP, KA, KB>), grid, dim3(tc::kThreads), (size_t)tc::kSmemBytes, st, M, N, K, k_per_split, tiles_m, tiles_n,
                     n_tiles, splits, mma_n, a, b, ep, partials);
     if (splits > 1) {
         const size_t total = (size_t)M * N;

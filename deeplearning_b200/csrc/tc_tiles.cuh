@@ -33,30 +33,35 @@ enum TcKind : int { kRedContig = 0, kOuterContig = 1, kPatchOuter = 2, kPatchRed
 // Geometry of a receptive-field operand: source tensor [SC][SH][SW] per sample, pixel grid PH x PW, window KH x KW.
 // Window tap (ky, kx) of pixel (py, px) reads source row py * sy + dy + sgn * ky, column px * sx + dx + sgn * kx
 // (forward: dy = -pad, sgn = +1; input gradient of a stride-1 convolution: dy = +pad, sgn = -1, source = output gradient).
+// mKK / mKW / mPW: ceil(2^32 / d) reciprocals (0 for d = 1), exact for the operand ranges tc_conv_ok admits.
 struct TcPatch {
     int SC, SH, SW, PH, PW, KH, KW, sy, sx, dy, dx, sgn;
     int SHW, KK, PP;     // SH * SW, KH * KW, PH * PW
+    unsigned mKK, mKW, mPW;
 };
 
 struct TcOperand {
     const float* base;
     long long ld;              // kRedContig / kOuterContig: leading dimension; kPixelRed: unused
-    int kind;                  // TcKind
+    int kind;                  // TcKind (the kernel is instantiated per pair of kinds; kept here for the launchers)
     const int* gather_base;    // optional row / sample gather (device int32), addressed through *cursor when cursor != nullptr
     const int* cursor;
     int ones_col;              // kOuterContig: outer index that reads as 1 (bias folded into the contraction); -1: none
     TcPatch patch;             // kPatchOuter / kPatchRed: the geometry; kPixelRed: SC = F, PP = P
 };
 
+inline unsigned tc_reciprocal(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
+
 inline TcPatch make_patch(int SC, int SH, int SW, int PH, int PW, int KH, int KW, int sy, int sx, int dy, int dx, int sgn) {
-    TcPatch p{SC, SH, SW, PH, PW, KH, KW, sy, sx, dy, dx, sgn, SH * SW, KH * KW, PH * PW};
+    TcPatch p{SC, SH, SW, PH, PW, KH, KW, sy, sx, dy, dx, sgn, SH * SW, KH * KW, PH * PW,
+              tc_reciprocal(KH * KW), tc_reciprocal(KW), tc_reciprocal(PW)};
     return p;
 }
 
 namespace tc {
 
 constexpr int kBM = 128, kBN = 128, kBK = 32;
-constexpr int kProducerWarps = 8;
+constexpr int kProducerWarps = 8;                         // the receptive-field lane mappings assume 8 (one 16-byte chunk column per warp)
 constexpr int kProducers = kProducerWarps * 32;            // producer threads
 constexpr int kOwned = 1024 / kProducers;                  // 16-byte chunks of a 128 x 32 fp32 tile per producer thread
 constexpr int kTileBytes = kBM * kBK * 4;                  // 16 KiB: one raw, hi or lo tile of either operand
@@ -102,12 +107,44 @@ DLB_HD int imin(int a, int b) { return a < b ? a : b; }
 // row r is stored at chunk c ^ (r & 7)).
 DLB_HD int chunk_off(int row, int c) { return row * 128 + ((c ^ (row & 7)) << 4); }
 
+// n / d for n * d < 2^32 through the precomputed reciprocal m = ceil(2^32 / d) (m = 0 encodes d = 1)
+DLB_HD int fast_div(int n, unsigned m) { return m ? (int)(((unsigned long long)(unsigned)n * m) >> 32) : n; }
+
+// Bits [lo, hi] of a 16-bit field (empty when lo > hi); lo, hi are clamped to [0, 14].
+DLB_HD unsigned bit_range(int lo, int hi) {
+    lo = lo < 0 ? 0 : lo; hi = hi > 14 ? 14 : hi;
+    return lo > hi ? 0u : (((2u << hi) - 1u) & ~((1u << lo) - 1u));
+}
+// Which window taps of a pixel whose tap (0, 0) reads source (iy0, ix0) fall inside the source: bit ky (rows) and bit
+// 16 + kx (columns).  A tap is valid iff both of its bits are set; windows are at most 15 x 15 here (tc_conv_ok).
+DLB_HD unsigned tap_mask(const TcPatch& p, int iy0, int ix0) {
+    const unsigned my = p.sgn > 0 ? bit_range(-iy0, p.SH - 1 - iy0) : bit_range(iy0 - p.SH + 1, iy0);
+    const unsigned mx = p.sgn > 0 ? bit_range(-ix0, p.SW - 1 - ix0) : bit_range(ix0 - p.SW + 1, ix0);
+    return my | (mx << 16);
+}
+constexpr unsigned kNoTap = 0x80008000u;   // a selector no tap_mask contains
+
+// Window tap k = (c, ky, kx) -> source offset relative to the pixel's tap (0, 0) and the selector matched against tap_mask
+DLB_HD void tap_decode(const TcPatch& p, int k, int& koff, unsigned& sel) {
+    const int c = fast_div(k, p.mKK), q = k - c * p.KK;
+    const int ky = fast_div(q, p.mKW), kx = q - ky * p.KW;
+    koff = c * p.SHW + p.sgn * (ky * p.SW + kx);
+    sel = (1u << ky) | (1u << (16 + kx));
+}
+
 // What a producer thread keeps per operand while it works on one output tile.
-struct TileOwner {
-    long long grow[kOwned];   // kRedContig: stored row of each owned chunk; kPixelRed: f * P; kPatchOuter: [0] = sample offset
-    int koff[kOwned];         // kPatchRed: c * SHW + sgn * (ky * SW + kx) of each owned tile row
-    int kyx[kOwned];          // kPatchRed: ky | kx << 16 of each owned tile row, -1: row beyond the operand
-    int iy0, ix0, valid;      // kPatchOuter: source row / column of tap (0, 0) of this thread's pixel
+constexpr int kPatchElems = 128 * kBK / kProducers;   // receptive-field elements per thread and k-block (16)
+template <int KIND> struct TileOwner {};
+template <> struct TileOwner<kRedContig> { long long grow[kOwned]; };     // stored row of each owned chunk
+template <> struct TileOwner<kPixelRed> { long long grow[kOwned]; };      // f * P of each owned tile row
+template <> struct TileOwner<kOuterContig> {};
+template <> struct TileOwner<kPatchOuter> {   // this thread's 16 pixels (tile rows 8 g + (lane >> 2))
+    int pbase[kPatchElems];        // element offset of tap (0, 0) of the pixel (may point outside: masked)
+    unsigned mask[kPatchElems];    // tap_mask of the pixel, 0 beyond the operand
+};
+template <> struct TileOwner<kPatchRed> {     // this thread's 16 window taps (tile rows warp + 8 i)
+    int koff[kPatchElems];
+    unsigned sel[kPatchElems];     // kNoTap beyond the operand
 };
 
 DLB_HD const int* resolve_rows(const TcOperand& op) {
@@ -115,52 +152,57 @@ DLB_HD const int* resolve_rows(const TcOperand& op) {
 }
 
 // Thread t of the producers; the tile covers outer indices [o0, o0 + 128) of [0, o_end).
-DLB_HD void owner_init(const TcOperand& op, int o0, int o_end, int t, TileOwner& w) {
-    if (op.kind == kRedContig || op.kind == kPixelRed) {
-        const int* gather = op.kind == kRedContig ? resolve_rows(op) : nullptr;
+template <int KIND>
+DLB_HD void owner_init(const TcOperand& op, int o0, int o_end, int t, TileOwner<KIND>& w) {
+    if constexpr (KIND == kRedContig || KIND == kPixelRed) {
+        const int* gather = KIND == kRedContig ? resolve_rows(op) : nullptr;
 #pragma unroll
         for (int i = 0; i < kOwned; ++i) {
             const int o = imin(o0 + ((t + kProducers * i) >> 3), o_end - 1);
-            if (op.kind == kPixelRed) w.grow[i] = (long long)o * op.patch.PP;
+            if constexpr (KIND == kPixelRed) w.grow[i] = (long long)o * op.patch.PP;
             else w.grow[i] = gather ? (long long)load_index(gather + o) : (long long)o;
         }
-    } else if (op.kind == kPatchOuter) {
+    } else if constexpr (KIND == kPatchOuter) {
         const TcPatch& p = op.patch;
-        const int pix = o0 + (t & 127);
-        w.valid = pix < o_end;
-        const int pc = w.valid ? pix : 0;
-        const int b = pc / p.PP, rem = pc - b * p.PP;
-        const int py = rem / p.PW, px = rem - py * p.PW;
         const int* gather = resolve_rows(op);
-        const long long s = (gather && w.valid) ? (long long)load_index(gather + b) : (long long)b;
-        w.grow[0] = s * p.SC * p.SHW;
-        w.iy0 = py * p.sy + p.dy;
-        w.ix0 = px * p.sx + p.dx;
-    } else if (op.kind == kPatchRed) {
+        const int lane = t & 31;
+#pragma unroll
+        for (int g = 0; g < kPatchElems; ++g) {
+            const int pix = o0 + 8 * g + (lane >> 2);
+            if (pix < o_end) {
+                const int b = pix / p.PP, rem = pix - b * p.PP;
+                const int py = fast_div(rem, p.mPW), px = rem - py * p.PW;
+                const int s = gather ? load_index(gather + b) : b;
+                const int iy0 = py * p.sy + p.dy, ix0 = px * p.sx + p.dx;
+                w.pbase[g] = s * p.SC * p.SHW + iy0 * p.SW + ix0;
+                w.mask[g] = tap_mask(p, iy0, ix0);
+            } else {
+                w.pbase[g] = 0; w.mask[g] = 0;
+            }
+        }
+    } else if constexpr (KIND == kPatchRed) {
         const TcPatch& p = op.patch;
 #pragma unroll
-        for (int i = 0; i < kOwned; ++i) {
-            const int k = o0 + ((t + kProducers * i) >> 3);
-            if (k < o_end) {
-                const int c = k / p.KK, q = k - c * p.KK;
-                const int ky = q / p.KW, kx = q - ky * p.KW;
-                w.koff[i] = c * p.SHW + p.sgn * (ky * p.SW + kx);
-                w.kyx[i] = ky | (kx << 16);
-            } else {
-                w.koff[i] = 0; w.kyx[i] = -1;
-            }
+        for (int i = 0; i < kPatchElems; ++i) {
+            const int k = o0 + (t >> 5) + 8 * i;
+            if (k < o_end) tap_decode(p, k, w.koff[i], w.sel[i]);
+            else { w.koff[i] = 0; w.sel[i] = kNoTap; }
         }
     }
 }
 
 // Issues this thread's copies of one k-block (reduction indices [r0, r0 + 32) of [.., r_end)) into the raw tile.
 // `rows`: tile rows the MMA reads (128 for A, the MMA's N for B); rows beyond are neither copied nor transformed.
-// Raw layouts: reduction-fast kinds (kRedContig, kPatchRed, kPixelRed) are copied straight into the K-major swizzled
-// layout; outer-fast kinds (kOuterContig, kPatchOuter) as plain [32 reduction rows][128 outer] and transposed by
-// transform_tile.
-DLB_HD void issue_tile(const TcOperand& op, const TileOwner& w, int o0, int o_end, int r0, int r_end, int t, int rows,
+// Raw layouts: every kind but kOuterContig is copied straight into the K-major swizzled layout; kOuterContig as plain
+// [32 reduction rows][128 outer] and transposed by transform_tile.
+// Receptive-field kinds move single fp32 elements (patch rows are not 16-byte aligned).  Their lane mappings make both
+// sides of the copy efficient: kPatchOuter gives a warp 8 consecutive pixels x 4 consecutive taps of one 16-byte chunk
+// column (global: a few 128-byte lines; shared: the swizzle spreads the 8 rows over all 32 banks), kPatchRed gives a
+// warp 32 consecutive pixels of one tap (global: consecutive addresses; shared: one whole 128-byte tile row).
+template <int KIND>
+DLB_HD void issue_tile(const TcOperand& op, const TileOwner<KIND>& w, int o0, int o_end, int r0, int r_end, int t, int rows,
                        unsigned char* raw) {
-    if (op.kind == kRedContig) {
+    if constexpr (KIND == kRedContig) {
         const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0) && (((r_end - r0) & 3) == 0 || r0 + kBK <= r_end);
         const int c = t & 7;
 #pragma unroll
@@ -180,7 +222,7 @@ DLB_HD void issue_tile(const TcOperand& op, const TileOwner& w, int o0, int o_en
                 }
             }
         }
-    } else if (op.kind == kOuterContig) {
+    } else if constexpr (KIND == kOuterContig) {
         const int* gather = resolve_rows(op);
         const int o_lim = imin(o_end, (int)op.ld);                 // the column of ones (o == ld) is synthesised in transform_tile
         const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0);
@@ -212,52 +254,40 @@ DLB_HD void issue_tile(const TcOperand& op, const TileOwner& w, int o0, int o_en
                 }
             }
         }
-    } else if (op.kind == kPatchOuter) {
-        const TcPatch& p = op.patch;
-        const int tt = t & 127, k0 = (t >> 7) * (kBK * 128 / kProducers);
-        if (tt < rows) {
-            const int r = r0 + k0;
-            int c = r / p.KK;
-            const int q = r - c * p.KK;
-            int ky = q / p.KW, kx = q - ky * p.KW;
+    } else if constexpr (KIND == kPatchOuter) {
+        // this thread: tap k = r0 + 4 * warp + (lane & 3) of its 16 pixels
+        const int lane = t & 31, warp = t >> 5;
+        const int k = r0 + 4 * warp + (lane & 3);
+        int koff = 0; unsigned sel = kNoTap;
+        if (k < r_end) tap_decode(op.patch, k, koff, sel);
+        unsigned char* dst = raw + chunk_off(lane >> 2, warp) + 4 * (lane & 3);
 #pragma unroll
-            for (int kk = 0; kk < kBK * 128 / kProducers; ++kk) {
-                const int iy = w.iy0 + p.sgn * ky, ix = w.ix0 + p.sgn * kx;
-                const bool ok = w.valid && (r + kk < r_end) && (unsigned)iy < (unsigned)p.SH && (unsigned)ix < (unsigned)p.SW;
-                const long long off = ok ? w.grow[0] + (long long)c * p.SHW + iy * p.SW + ix : 0;
-                tile_copy4(raw + ((k0 + kk) * 128 + tt) * 4, op.base + off, ok);
-                if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++c; } }
-            }
+        for (int g = 0; g < kPatchElems; ++g) {
+            if (8 * g >= rows) continue;
+            const bool ok = (w.mask[g] & sel) == sel;
+            tile_copy4(dst + g * 1024, op.base + (ok ? w.pbase[g] + koff : 0), ok);
         }
-    } else if (op.kind == kPatchRed) {
-        // this thread: the 4 pixels r0 + 4 (t & 7) + j of tile rows (t >> 3) + 32 i
+    } else if constexpr (KIND == kPatchRed) {
+        // this thread: pixel r0 + lane under its 16 taps
         const TcPatch& p = op.patch;
-        const int* gather = resolve_rows(op);
-        const int c = t & 7;
-        const int pix0 = r0 + 4 * c;
-        int b = pix0 / p.PP;
-        const int rem = pix0 - b * p.PP;
-        int py = rem / p.PW, px = rem - py * p.PW;
-        long long sbase[4]; int iy0[4], ix0[4]; bool okp[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            okp[j] = pix0 + j < r_end;
-            const long long s = (gather && okp[j]) ? (long long)load_index(gather + b) : (long long)b;
-            iy0[j] = py * p.sy + p.dy; ix0[j] = px * p.sx + p.dx;
-            sbase[j] = s * p.SC * p.SHW + (long long)iy0[j] * p.SW + ix0[j];
-            if (++px == p.PW) { px = 0; if (++py == p.PH) { py = 0; ++b; } }
+        const int lane = t & 31, warp = t >> 5;
+        const int pix = r0 + lane;
+        int sbase = 0; unsigned mask = 0;
+        if (pix < r_end) {
+            const int* gather = resolve_rows(op);
+            const int b = pix / p.PP, rem = pix - b * p.PP;
+            const int py = fast_div(rem, p.mPW), px = rem - py * p.PW;
+            const int s = gather ? load_index(gather + b) : b;
+            const int iy0 = py * p.sy + p.dy, ix0 = px * p.sx + p.dx;
+            sbase = s * p.SC * p.SHW + iy0 * p.SW + ix0;
+            mask = tap_mask(p, iy0, ix0);
         }
+        unsigned char* dst = raw + chunk_off(warp, lane >> 2) + 4 * (lane & 3);
 #pragma unroll
-        for (int i = 0; i < kOwned; ++i) {
-            const int row = (t + kProducers * i) >> 3;
-            if (row >= rows) continue;
-            const int ky = w.kyx[i] & 0xFFFF, kx = w.kyx[i] >> 16;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int iy = iy0[j] + p.sgn * ky, ix = ix0[j] + p.sgn * kx;
-                const bool ok = w.kyx[i] >= 0 && okp[j] && (unsigned)iy < (unsigned)p.SH && (unsigned)ix < (unsigned)p.SW;
-                tile_copy4(raw + chunk_off(row, c) + 4 * j, op.base + (ok ? sbase[j] + w.koff[i] : 0), ok);
-            }
+        for (int i = 0; i < kPatchElems; ++i) {
+            if (warp + 8 * i >= rows) continue;
+            const bool ok = (mask & w.sel[i]) == w.sel[i];
+            tile_copy4(dst + i * 1024, op.base + (ok ? sbase + w.koff[i] : 0), ok);
         }
     } else {   // kPixelRed: G[(b * F + f) * P + p], tile row = f, reduction = (b, p)
         const TcPatch& p = op.patch;
@@ -320,9 +350,10 @@ DLB_HD void split_store(Quad v, unsigned char* hi_tile, unsigned char* lo_tile, 
     *reinterpret_cast<Quad*>(lo_tile + off) = l;
 }
 
+template <int KIND>
 DLB_HD void transform_tile(const TcOperand& op, int o0, int o_end, int r0, int r_end, int t, int rows,
                            const unsigned char* raw_tile, unsigned char* hi_tile, unsigned char* lo_tile) {
-    if (op.kind == kRedContig || op.kind == kPatchRed || op.kind == kPixelRed) {
+    if constexpr (KIND != kOuterContig) {
 #pragma unroll
         for (int i = 0; i < kOwned; ++i) {
             const int q = t + kProducers * i;
@@ -336,7 +367,7 @@ DLB_HD void transform_tile(const TcOperand& op, int o0, int o_end, int r0, int r
         const float* raw = reinterpret_cast<const float*>(raw_tile);
         const int tt = t & 127, c0 = (t >> 7) * (8 * 128 / kProducers);
         if (tt >= rows) return;
-        const bool ones = op.kind == kOuterContig && (o0 + tt < o_end) && (o0 + tt == op.ones_col);
+        const bool ones = (o0 + tt < o_end) && (o0 + tt == op.ones_col);
 #pragma unroll
         for (int cc = 0; cc < 8 * 128 / kProducers; ++cc) {
             const int c = c0 + cc;

@@ -50,6 +50,26 @@ static float expect(const TcOperand& op, const int* gather, int o, int r) {
     }
 }
 
+template <int KIND>
+static void run_kind(const TcOperand& op, int o0, int o_end, int r0, int r_end, int rows, unsigned char* raw, unsigned char* hi, unsigned char* lo) {
+    for (int t = 0; t < kProducers; ++t) {
+        TileOwner<KIND> w{};
+        owner_init<KIND>(op, o0, o_end, t, w);
+        issue_tile<KIND>(op, w, o0, o_end, r0, r_end, t, rows, raw);
+    }
+    for (int t = 0; t < kProducers; ++t) transform_tile<KIND>(op, o0, o_end, r0, r_end, t, rows, raw, hi, lo);
+}
+
+static void run_producers(const TcOperand& op, int o0, int o_end, int r0, int r_end, int rows, unsigned char* raw, unsigned char* hi, unsigned char* lo) {
+    switch (op.kind) {
+    case kRedContig: run_kind<kRedContig>(op, o0, o_end, r0, r_end, rows, raw, hi, lo); break;
+    case kOuterContig: run_kind<kOuterContig>(op, o0, o_end, r0, r_end, rows, raw, hi, lo); break;
+    case kPatchOuter: run_kind<kPatchOuter>(op, o0, o_end, r0, r_end, rows, raw, hi, lo); break;
+    case kPatchRed: run_kind<kPatchRed>(op, o0, o_end, r0, r_end, rows, raw, hi, lo); break;
+    default: run_kind<kPixelRed>(op, o0, o_end, r0, r_end, rows, raw, hi, lo); break;
+    }
+}
+
 static void check_operand(const char* name, const TcOperand& op, const int* gather, int o_end, int r_total, int rows) {
     std::vector<unsigned char> raw(kTileBytes), hi(kTileBytes), lo(kTileBytes);
     // a few reduction slices: whole, and a split that ends inside a k-block
@@ -60,12 +80,7 @@ static void check_operand(const char* name, const TcOperand& op, const int* gath
             if (op.kind == kPixelRed && (op.patch.PP & 3) == 0 && (r_end & 3)) continue;   // the 16-byte path needs r_end % 4 == 0 (true on the device)
             for (int r0 = 0; r0 < r_end; r0 += kBK) {
                 std::fill(raw.begin(), raw.end(), 0xCD); std::fill(hi.begin(), hi.end(), 0xCD); std::fill(lo.begin(), lo.end(), 0xCD);
-                for (int t = 0; t < kProducers; ++t) {
-                    TileOwner w{};
-                    owner_init(op, o0, o_end, t, w);
-                    issue_tile(op, w, o0, o_end, r0, r_end, t, rows, raw.data());
-                }
-                for (int t = 0; t < kProducers; ++t) transform_tile(op, o0, o_end, r0, r_end, t, rows, raw.data(), hi.data(), lo.data());
+                run_producers(op, o0, o_end, r0, r_end, rows, raw.data(), hi.data(), lo.data());
                 for (int row = 0; row < rows; ++row)
                     for (int k = 0; k < kBK; ++k) {
                         const int off = chunk_off(row, k >> 2) + 4 * (k & 3);
