@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdlb200.so")
+LIB_PATH = os.environ.get("DLB200_LIB") or os.path.join(HERE, "libdlb200.so")   # DLB200_LIB: another build of the same library (development)
 
 
 class DlbError(RuntimeError):

@@ -33,10 +33,21 @@ namespace dlb {
 
 namespace tc {
 
-constexpr int kStages = 2;                                 // hi/lo operand stages consumed by the tensor core
-constexpr int kRaw = 2;                                    // raw fp32 stages filled by cp.async (the prefetch depth)
-constexpr int kStageBytes = 4 * kTileBytes;                // A_hi, A_lo, B_hi, B_lo
+// Two shared-memory plans (both 192 KiB), chosen at compile time by the operand kinds:
+//  * an operand that has to be transposed (kOuterContig) is copied into a 2-deep ring of raw [k][outer] blocks and
+//    transformed into a 2-deep ring of stages {A_hi, A_lo, B_hi, B_lo};
+//  * when BOTH operands arrive K-major (the NLayer forward and all three convolution contractions) the copy lands directly
+//    where the MMA reads its "hi" operand and only "lo" is computed: kind::tf32 ignores the low 13 mantissa bits of its
+//    32-bit operands (checked on B200: feeding x instead of x & 0xFFFFE000 gives bit-identical accumulators), so x itself
+//    serves as hi.  One slot = {A, A_lo, B, B_lo}; three slots: one being filled, one being transformed, one under the MMAs.
+//    A quarter less transform work and shared-memory traffic per k-block, and one more k-block in flight.
+constexpr int kStages = 2;                                 // hi/lo operand stages of the transposing plan
+constexpr int kRaw = 2;                                    // raw fp32 blocks of the transposing plan
+constexpr int kSlots = 3;                                  // slots of the K-major plan
+constexpr int kStageBytes = 4 * kTileBytes;                // A_hi, A_lo, B_hi, B_lo  (K-major plan: A, A_lo, B, B_lo)
 constexpr int kRawBytes = 2 * kTileBytes;                  // A_raw, B_raw
+static_assert(kSlots * kStageBytes == kStages * kStageBytes + kRaw * kRawBytes, "both plans use the same shared-memory size");
+template <int KIND> struct KMajor { static constexpr bool value = KIND != kOuterContig; };
 constexpr int kEpiBytes = 4 * 32 * 33 * 4;                 // one padded 32 x 32 fp32 staging block per epilogue warp
 constexpr int kSmemBytes = kStages * kStageBytes + kRaw * kRawBytes + kEpiBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 constexpr int kMmaWarp = kProducerWarps;                   // warp index of the MMA issuer
@@ -124,19 +135,24 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, int n_tiles, int n_splits, int mma_n, TcOperand a, TcOperand b, EP ep,
                float* __restrict__ partials) {
     extern __shared__ unsigned char tc_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (SWIZZLE_128B atoms) by an OFFSET into the shared array, not by an integer round trip of the pointer:
+    // the compiler then still knows these are shared-memory addresses and emits LDS / STS instead of generic LD / ST
+    // (the first version's transform ran on generic accesses: ncu source page, LD.E.128 / ST.E.128 with long-scoreboard stalls).
+    unsigned char* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     unsigned char* raw_ring = smem + kStages * kStageBytes;
     float* epi_stage = reinterpret_cast<float*>(raw_ring + kRaw * kRawBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(epi_stage) + kEpiBytes);
-    // bars: full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2]
-    uint64_t* bar_full = bars; uint64_t* bar_empty = bars + kStages;
-    uint64_t* bar_tfull = bars + 2 * kStages; uint64_t* bar_tempty = bars + 2 * kStages + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    // bars: full[kSlots] | empty[kSlots] | tmem_full[2] | tmem_empty[2]
+    uint64_t* bar_full = bars; uint64_t* bar_empty = bars + kSlots;
+    uint64_t* bar_tfull = bars + 2 * kSlots; uint64_t* bar_tempty = bars + 2 * kSlots + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 4);
+    constexpr bool kDirect = KMajor<KA>::value && KMajor<KB>::value;     // the K-major plan
+    constexpr int kRing = kDirect ? kSlots : kStages;         // operand stages the MMA lane cycles through
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bar_full[s]), kProducers); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < kSlots; ++s) { mbar_init(smem_u32(&bar_full[s]), kProducers); mbar_init(smem_u32(&bar_empty[s]), 1); }
         for (int q = 0; q < 2; ++q) { mbar_init(smem_u32(&bar_tfull[q]), 1); mbar_init(smem_u32(&bar_tempty[q]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -166,35 +182,51 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
         long long issued = 0;
         auto issue_next = [&]() {            // issues one k-block (or nothing at the end of the stream) and commits a group
             if (nt_tile < n_tiles) {
-                unsigned char* raw = raw_ring + (int)(issued % kRaw) * kRawBytes;
+                unsigned char* raw_a; unsigned char* raw_b;
+                if constexpr (kDirect) {
+                    const int s = (int)(issued % kSlots);
+                    mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(((issued / kSlots) & 1) ^ 1));   // the MMAs of this slot's previous use are done
+                    raw_a = smem + s * kStageBytes; raw_b = raw_a + 2 * kTileBytes;
+                } else {
+                    raw_a = raw_ring + (int)(issued % kRaw) * kRawBytes; raw_b = raw_a + kTileBytes;
+                }
                 const int r0 = nc.kb + nt_k * kBK;
-                issue_tile<KA>(a, nwa, nc.i0, M, r0, nc.ke, tid, kBM, raw);
-                issue_tile<KB>(b, nwb, nc.j0, N, r0, nc.ke, tid, mma_n, raw + kTileBytes);
+                issue_tile<KA>(a, nwa, nc.i0, M, r0, nc.ke, tid, kBM, raw_a);
+                issue_tile<KB>(b, nwb, nc.j0, N, r0, nc.ke, tid, mma_n, raw_b);
                 ++issued;
                 if (++nt_k == nc.nkb) { nt_k = 0; nt_tile += gridDim.x; open_next(); }
             }
             cp_async_commit();
         };
-#pragma unroll
-        for (int p = 0; p < kRaw - 1; ++p) issue_next();
+        issue_next();
+        if constexpr (kDirect) issue_next();   // K-major plan: two k-blocks in flight
         long long git = 0;                   // k-blocks consumed so far (stage / phase bookkeeping shared with the MMA lane)
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const TileCoord c = decode_tile(t, tiles_m, tiles_n, K, k_per_split);
             for (int it = 0; it < c.nkb; ++it, ++git) {
-                cp_async_wait<kRaw - 2>();                          // this thread's copies of the current k-block have landed
-                // every producer's copies have landed, and every producer is done reading the raw slot refilled next
-                asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");
-                issue_next();
-                const int s = (int)(git % kStages);
-                const uint32_t phase = (uint32_t)((git / kStages) & 1);
-                mbar_wait(smem_u32(&bar_empty[s]), phase ^ 1);      // hi/lo stage free (first pass: returns at once)
-                const unsigned char* raw = raw_ring + (int)(git % kRaw) * kRawBytes;
+                const int s = (int)(git % kRing);
                 unsigned char* st = smem + s * kStageBytes;
-                const int r0 = c.kb + it * kBK;
-                transform_tile<KA>(a, c.i0, M, r0, c.ke, tid, kBM, raw, st, st + kTileBytes);
-                transform_tile<KB>(b, c.j0, N, r0, c.ke, tid, mma_n, raw + kTileBytes, st + 2 * kTileBytes, st + 3 * kTileBytes);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (UMMA) reads
-                mbar_arrive(smem_u32(&bar_full[s]));
+                if constexpr (kDirect) {
+                    cp_async_wait<1>();                             // this thread's copies of the current k-block have landed (the next one may be in flight)
+                    asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");   // ... and every other producer's
+                    lo_tile<KA>(tid, kBM, st, st + kTileBytes);
+                    lo_tile<KB>(tid, mma_n, st + 2 * kTileBytes, st + 3 * kTileBytes);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // landed copies and lo stores -> async-proxy (UMMA) reads
+                    mbar_arrive(smem_u32(&bar_full[s]));
+                    issue_next();                                   // k-block git + 2 into the slot the MMAs of k-block git - 1 are leaving
+                } else {
+                    cp_async_wait<0>();                             // this thread's copies of the current k-block have landed
+                    // every producer's copies have landed, and every producer is done reading the raw block refilled next
+                    asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");
+                    issue_next();
+                    mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(((git / kStages) & 1) ^ 1));   // hi/lo stage free (first pass: returns at once)
+                    const unsigned char* raw = raw_ring + (int)(git % kRaw) * kRawBytes;
+                    const int r0 = c.kb + it * kBK;
+                    transform_tile<KA>(a, c.i0, M, r0, c.ke, tid, kBM, raw, st, st + kTileBytes);
+                    transform_tile<KB>(b, c.j0, N, r0, c.ke, tid, mma_n, raw + kTileBytes, st + 2 * kTileBytes, st + 3 * kTileBytes);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (UMMA) reads
+                    mbar_arrive(smem_u32(&bar_full[s]));
+                }
             }
         }
         cp_async_wait<0>();
@@ -212,8 +244,8 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kBN);
                 uint32_t accumulate = 0;
                 for (int it = 0; it < c.nkb; ++it, ++git) {
-                    const int s = (int)(git % kStages);
-                    const uint32_t phase = (uint32_t)((git / kStages) & 1);
+                    const int s = (int)(git % kRing);
+                    const uint32_t phase = (uint32_t)((git / kRing) & 1);
                     mbar_wait(smem_u32(&bar_full[s]), phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = smem_u32(smem + s * kStageBytes);
@@ -323,6 +355,7 @@ template <int KA, int KB, class EP>
 void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcOperand& b, EP ep, const GemmWorkspace& ws) {
     if (M <= 0 || N <= 0) return;
     if (a.kind != KA || b.kind != KB) throw std::logic_error("tc_gemm: operand kind does not match the instantiation");
+    if (a.ld >= (1LL << 31) || b.ld >= (1LL << 31)) throw std::invalid_argument("tc_gemm: leading dimension exceeds the 32-bit range");
     const long tiles = (long)ceil_div(M, tc::kBM) * ceil_div(N, tc::kBN);
     const int kblocks = ceil_div(K > 0 ? K : 1, tc::kBK);
     // Persistent CTAs (one per SM): split the reduction only as far as the split tiles still fit in ONE wave, so that no

@@ -94,6 +94,11 @@ DLB_HD void tile_copy4(unsigned char* dst, const float* src, bool ok) {
     std::memcpy(dst, &v, 4);
 #endif
 }
+struct alignas(16) Quad { float x, y, z, w; };
+
+DLB_HD Quad tile_load16(const unsigned char* p) { return *reinterpret_cast<const Quad*>(p); }
+DLB_HD float tile_load4(const unsigned char* p) { return *reinterpret_cast<const float*>(p); }
+DLB_HD void tile_store16(unsigned char* p, Quad v) { *reinterpret_cast<Quad*>(p) = v; }
 DLB_HD int load_index(const int* p) {
 #ifdef __CUDA_ARCH__
     return __ldg(p);
@@ -135,8 +140,8 @@ DLB_HD void tap_decode(const TcPatch& p, int k, int& koff, unsigned& sel) {
 // What a producer thread keeps per operand while it works on one output tile.
 constexpr int kPatchElems = 128 * kBK / kProducers;   // receptive-field elements per thread and k-block (16)
 template <int KIND> struct TileOwner {};
-template <> struct TileOwner<kRedContig> { long long grow[kOwned]; };     // stored row of each owned chunk
-template <> struct TileOwner<kPixelRed> { long long grow[kOwned]; };      // f * P of each owned tile row
+template <> struct TileOwner<kRedContig> { int grow[kOwned]; };           // stored row of each owned chunk
+template <> struct TileOwner<kPixelRed> { int grow[kOwned]; };            // f * P of each owned tile row
 template <> struct TileOwner<kOuterContig> {};
 template <> struct TileOwner<kPatchOuter> {   // this thread's 16 pixels (tile rows 8 g + (lane >> 2))
     int pbase[kPatchElems];        // element offset of tap (0, 0) of the pixel (may point outside: masked)
@@ -159,8 +164,8 @@ DLB_HD void owner_init(const TcOperand& op, int o0, int o_end, int t, TileOwner<
 #pragma unroll
         for (int i = 0; i < kOwned; ++i) {
             const int o = imin(o0 + ((t + kProducers * i) >> 3), o_end - 1);
-            if constexpr (KIND == kPixelRed) w.grow[i] = (long long)o * op.patch.PP;
-            else w.grow[i] = gather ? (long long)load_index(gather + o) : (long long)o;
+            if constexpr (KIND == kPixelRed) w.grow[i] = o * op.patch.PP;
+            else w.grow[i] = gather ? load_index(gather + o) : o;
         }
     } else if constexpr (KIND == kPatchOuter) {
         const TcPatch& p = op.patch;
@@ -203,7 +208,8 @@ template <int KIND>
 DLB_HD void issue_tile(const TcOperand& op, const TileOwner<KIND>& w, int o0, int o_end, int r0, int r_end, int t, int rows,
                        unsigned char* raw) {
     if constexpr (KIND == kRedContig) {
-        const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0) && (((r_end - r0) & 3) == 0 || r0 + kBK <= r_end);
+        const int ld = (int)op.ld;   // leading dimensions are below 2^31 (checked by the launcher): one 32 x 32 -> 64 multiply per address
+        const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0) && (((r_end - r0) & 3) == 0 || r0 + kBK <= r_end);
         const int c = t & 7;
 #pragma unroll
         for (int i = 0; i < kOwned; ++i) {
@@ -212,20 +218,21 @@ DLB_HD void issue_tile(const TcOperand& op, const TileOwner<KIND>& w, int o0, in
             if (vec) {
                 const int r = r0 + 4 * c;
                 const bool ok = (o0 + row < o_end) && (r < r_end);
-                tile_copy16(raw + chunk_off(row, c), op.base + w.grow[i] * op.ld + imin(r, r_end - 4), ok ? 16 : 0);
+                tile_copy16(raw + chunk_off(row, c), op.base + (long long)w.grow[i] * ld + imin(r, r_end - 4), ok ? 16 : 0);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int r = r0 + 4 * c + j;
                     const bool ok = (o0 + row < o_end) && (r < r_end);
-                    tile_copy4(raw + chunk_off(row, c) + 4 * j, op.base + w.grow[i] * op.ld + imin(r, r_end - 1), ok);
+                    tile_copy4(raw + chunk_off(row, c) + 4 * j, op.base + (long long)w.grow[i] * ld + imin(r, r_end - 1), ok);
                 }
             }
         }
     } else if constexpr (KIND == kOuterContig) {
         const int* gather = resolve_rows(op);
-        const int o_lim = imin(o_end, (int)op.ld);                 // the column of ones (o == ld) is synthesised in transform_tile
-        const bool vec = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0);
+        const int ld = (int)op.ld;
+        const int o_lim = imin(o_end, ld);                         // the column of ones (o == ld) is synthesised in transform_tile
+        const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0);
         if (vec) {
             const int oc = (t & 31) * 4;
             if (oc < rows) {
@@ -233,24 +240,24 @@ DLB_HD void issue_tile(const TcOperand& op, const TileOwner<KIND>& w, int o0, in
                 for (int i = 0; i < kOwned; ++i) {
                     const int k = (t + kProducers * i) >> 5;
                     const int r = imin(r0 + k, r_end - 1);
-                    const long long grow = gather ? (long long)load_index(gather + r) : (long long)r;
+                    const int grow = gather ? load_index(gather + r) : r;
                     const int o = o0 + oc;
                     int n_ok = (r0 + k < r_end) ? imin(4, o_lim - o) : 0;
                     n_ok = n_ok < 0 ? 0 : n_ok;
-                    tile_copy16(raw + (k * 128 + oc) * 4, op.base + grow * op.ld + imin(o, (int)op.ld - 4), 4 * n_ok);
+                    tile_copy16(raw + (k * 128 + oc) * 4, op.base + (long long)grow * ld + imin(o, ld - 4), 4 * n_ok);
                 }
             }
         } else {
             const int tt = t & 127, k0 = (t >> 7) * (kBK * 128 / kProducers);
             if (tt < rows) {
                 const int o = o0 + tt;
-                const int oc = imin(imin(o, o_end - 1), (int)op.ld - 1);
+                const int oc = imin(imin(o, o_end - 1), ld - 1);
 #pragma unroll
                 for (int kk = 0; kk < kBK * 128 / kProducers; ++kk) {
                     const int k = k0 + kk;
                     const int r = imin(r0 + k, r_end - 1);
-                    const long long grow = gather ? (long long)load_index(gather + r) : (long long)r;
-                    tile_copy4(raw + (k * 128 + tt) * 4, op.base + grow * op.ld + oc, o < o_lim && r0 + k < r_end);
+                    const int grow = gather ? load_index(gather + r) : r;
+                    tile_copy4(raw + (k * 128 + tt) * 4, op.base + (long long)grow * ld + oc, o < o_lim && r0 + k < r_end);
                 }
             }
         }
@@ -296,7 +303,7 @@ DLB_HD void issue_tile(const TcOperand& op, const TileOwner<KIND>& w, int o0, in
         int b = r / p.PP, pp = r - b * p.PP;
         const bool vec = ((p.PP & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.base) & 15) == 0);
         if (vec) {
-            const long long off = (long long)b * p.SC * p.PP + pp;
+            const int off = b * p.SC * p.PP + pp;                  // B * F * P < 2^31 (tc_conv_ok)
 #pragma unroll
             for (int i = 0; i < kOwned; ++i) {
                 const int row = (t + kProducers * i) >> 3;
@@ -305,11 +312,11 @@ DLB_HD void issue_tile(const TcOperand& op, const TileOwner<KIND>& w, int o0, in
                 tile_copy16(raw + chunk_off(row, c), op.base + (ok ? off + w.grow[i] : 0), ok ? 16 : 0);
             }
         } else {
-            long long off[4]; bool okr[4];
+            int off[4]; bool okr[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 okr[j] = r + j < r_end;
-                off[j] = (long long)b * p.SC * p.PP + pp;
+                off[j] = b * p.SC * p.PP + pp;
                 if (++pp == p.PP) { pp = 0; ++b; }
             }
 #pragma unroll
@@ -325,8 +332,6 @@ DLB_HD void issue_tile(const TcOperand& op, const TileOwner<KIND>& w, int o0, in
         }
     }
 }
-
-struct alignas(16) Quad { float x, y, z, w; };
 
 // raw fp32 chunk -> hi (TF32-representable: low 13 mantissa bits cleared) and lo (exact remainder) chunks at the same
 // offsets of the hi / lo tiles
@@ -346,8 +351,25 @@ DLB_HD void split_store(Quad v, unsigned char* hi_tile, unsigned char* lo_tile, 
     h.y = tf32_hi(v.y); l.y = v.y - h.y;
     h.z = tf32_hi(v.z); l.z = v.z - h.z;
     h.w = tf32_hi(v.w); l.w = v.w - h.w;
-    *reinterpret_cast<Quad*>(hi_tile + off) = h;
-    *reinterpret_cast<Quad*>(lo_tile + off) = l;
+    tile_store16(hi_tile + off, h);
+    tile_store16(lo_tile + off, l);
+}
+
+// K-major plan: the copied tile itself is the MMA's hi operand (the tensor core ignores the low 13 mantissa bits); only
+// the remainder lo = x - (x & 0xFFFFE000) is computed.
+template <int KIND>
+DLB_HD void lo_tile(int t, int rows, const unsigned char* raw_tile, unsigned char* lo_tile_) {
+    static_assert(KIND != kOuterContig, "transposed operands go through transform_tile");
+#pragma unroll
+    for (int i = 0; i < kOwned; ++i) {
+        const int q = t + kProducers * i;
+        if ((q >> 3) >= rows) continue;
+        const int off = chunk_off(q >> 3, q & 7);
+        const Quad v = tile_load16(raw_tile + off);
+        Quad l;
+        l.x = v.x - tf32_hi(v.x); l.y = v.y - tf32_hi(v.y); l.z = v.z - tf32_hi(v.z); l.w = v.w - tf32_hi(v.w);
+        tile_store16(lo_tile_ + off, l);
+    }
 }
 
 template <int KIND>
@@ -359,12 +381,11 @@ DLB_HD void transform_tile(const TcOperand& op, int o0, int o_end, int r0, int r
             const int q = t + kProducers * i;
             if ((q >> 3) >= rows) continue;
             const int off = chunk_off(q >> 3, q & 7);
-            split_store(*reinterpret_cast<const Quad*>(raw_tile + off), hi_tile, lo_tile, off);
+            split_store(tile_load16(raw_tile + off), hi_tile, lo_tile, off);
         }
     } else {
         // thread t produces half of tile row t & 127 (outer index o0 + (t & 127)): a column of the raw [k][o] block
         // (conflict-free: lanes read consecutive words), or the implicit column of ones
-        const float* raw = reinterpret_cast<const float*>(raw_tile);
         const int tt = t & 127, c0 = (t >> 7) * (8 * 128 / kProducers);
         if (tt >= rows) return;
         const bool ones = (o0 + tt < o_end) && (o0 + tt == op.ones_col);
@@ -376,8 +397,8 @@ DLB_HD void transform_tile(const TcOperand& op, int o0, int o_end, int r0, int r
                 v.x = r0 + 4 * c < r_end ? 1.f : 0.f; v.y = r0 + 4 * c + 1 < r_end ? 1.f : 0.f;
                 v.z = r0 + 4 * c + 2 < r_end ? 1.f : 0.f; v.w = r0 + 4 * c + 3 < r_end ? 1.f : 0.f;
             } else {
-                v.x = raw[(4 * c) * 128 + tt]; v.y = raw[(4 * c + 1) * 128 + tt];
-                v.z = raw[(4 * c + 2) * 128 + tt]; v.w = raw[(4 * c + 3) * 128 + tt];
+                v.x = tile_load4(raw_tile + ((4 * c) * 128 + tt) * 4); v.y = tile_load4(raw_tile + ((4 * c + 1) * 128 + tt) * 4);
+                v.z = tile_load4(raw_tile + ((4 * c + 2) * 128 + tt) * 4); v.w = tile_load4(raw_tile + ((4 * c + 3) * 128 + tt) * 4);
             }
             split_store(v, hi_tile, lo_tile, chunk_off(tt, c));
         }

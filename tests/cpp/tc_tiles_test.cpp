@@ -58,6 +58,22 @@ static void run_kind(const TcOperand& op, int o0, int o_end, int r0, int r_end, 
         issue_tile<KIND>(op, w, o0, o_end, r0, r_end, t, rows, raw);
     }
     for (int t = 0; t < kProducers; ++t) transform_tile<KIND>(op, o0, o_end, r0, r_end, t, rows, raw, hi, lo);
+    if constexpr (KIND != kOuterContig) {
+        // K-major plan: the copied tile is the hi operand as it is (the tensor core drops the low 13 mantissa bits), lo_tile
+        // adds the remainder: truncated raw must equal the transform's hi and lo_tile's output its lo, bit for bit
+        std::vector<unsigned char> lo2(kTileBytes, 0xCD);
+        for (int t = 0; t < kProducers; ++t) lo_tile<KIND>(t, rows, raw, lo2.data());
+        for (int row = 0; row < rows; ++row)
+            for (int k = 0; k < kBK; ++k) {
+                const int off = chunk_off(row, k >> 2) + 4 * (k & 3);
+                float r, h, l, l2;
+                std::memcpy(&r, raw + off, 4); std::memcpy(&h, hi + off, 4); std::memcpy(&l, lo + off, 4); std::memcpy(&l2, lo2.data() + off, 4);
+                if (tf32_hi(r) != h || std::memcmp(&l, &l2, 4) != 0) {
+                    if (fails < 10) std::printf("lo_tile: row %d k %d raw %g hi %g lo %g lo2 %g\n", row, k, r, h, l, l2);
+                    ++fails;
+                }
+            }
+    }
 }
 
 static void run_producers(const TcOperand& op, int o0, int o_end, int r0, int r_end, int rows, unsigned char* raw, unsigned char* hi, unsigned char* lo) {
