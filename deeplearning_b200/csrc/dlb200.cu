@@ -567,6 +567,7 @@ struct NetT final : dlb_net {
     void forward(int B, const R* x, const int* gather, bool traces) {
         LaunchCtx lc = ctx->lc();
         lc.tc = std::is_same_v<R, float> && tc_for(B);
+        lc.gather_rows = x == data_x ? n_items : (long long)cap;
         const R* in = x;
         const int* ga = gather;
         for (int l = 0; l < L(); ++l) {
@@ -591,6 +592,7 @@ struct NetT final : dlb_net {
     void backward(int B, const R* x, const int* gather, R scale) {
         LaunchCtx lc = ctx->lc();
         lc.tc = std::is_same_v<R, float> && tc_for(B);
+        lc.gather_rows = x == data_x ? n_items : (long long)cap;
         const R* delta = in_grad[(size_t)L()];
         for (int l = L() - 1; l >= 0; --l) {
             const auto& Y = layers[(size_t)l];

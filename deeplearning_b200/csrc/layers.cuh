@@ -445,6 +445,7 @@ struct LaunchCtx {
     cudaStream_t stream;
     GemmWorkspace ws;
     bool tc = false;     // Real = float only: contractions on the tensor cores (tc_gemm.cuh, 3xTF32) instead of the FMA path
+    long long gather_rows = 0;   // rows of the array a layer-0 gather indexes into (the resident data set); 0: unknown
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -498,7 +499,8 @@ __global__ void filters_channel_major_kernel(const float* __restrict__ filt, flo
 }
 
 // Ranges the producers' 32-bit offsets, 15-bit tap masks and reciprocal divisions are exact for (tc_tiles.cuh).
-inline bool tc_conv_ok(const ConvGeom& g, int B) {
+inline bool tc_conv_ok(const ConvGeom& g, int B, const int* gather = nullptr, long long gather_rows = 0) {
+    if (gather && (gather_rows <= 0 || gather_rows * g.in_n >= (1LL << 31))) return false;   // gathered sample offsets are 32-bit
     return g.KH <= 15 && g.KW <= 15 && g.P > 0 && g.H <= 2048 && g.W <= 2048 && g.OH <= 2048 && g.OW <= 2048 &&
            (long long)g.F * g.KK < 65536 && g.K < 65536 &&
            (long long)B * std::max(g.in_n, g.out_n) < (1LL << 31);
@@ -568,7 +570,7 @@ void conv_forward(const LaunchCtx& lc, int B, const ConvGeom& g, int act, const 
         bool done = false;
 #ifndef DLB_CUDA_EMU
         if constexpr (std::is_same_v<R, float>) {
-            if (lc.tc && tc_conv_ok(g, B)) {
+            if (lc.tc && tc_conv_ok(g, B, gather, lc.gather_rows)) {
                 tc_conv_forward(lc, B, g, act, x, gather, nullptr, bias, filters, y, act == DLB_ACT_SOFTMAX ? nullptr : deriv);
                 done = true;
             }
@@ -641,7 +643,7 @@ void conv_backward(const LaunchCtx& lc, int B, const ConvGeom& cg, int act, cons
     activation_grad_and_bias<R>(lc, B, cg.out_n, act, delta, deriv, g, dbias, scale);
     bool tc = false;
 #ifndef DLB_CUDA_EMU
-    if constexpr (std::is_same_v<R, float>) tc = lc.tc && tc_conv_ok(cg, B);
+    if constexpr (std::is_same_v<R, float>) tc = lc.tc && tc_conv_ok(cg, B, gather, lc.gather_rows);
 #endif
     {
         TagScope tag_("conv_dK");

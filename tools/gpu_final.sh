@@ -8,6 +8,7 @@ echo "== pytest gpu"; timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | ta
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${P}_bench_ref.json 2> gpurun_out/${P}_bench_ref.err; cat gpurun_out/${P}_bench_ref.json | cut -c1-400
 echo "== bench f32"; timeout 600 python bench.py > gpurun_out/${P}_bench_f32.json 2> gpurun_out/${P}_bench_f32.err; python tools/show_bench.py gpurun_out/${P}_bench_f32.json; tail -3 gpurun_out/${P}_bench_f32.err
 echo "== bench f64"; timeout 600 python bench.py --real f64 --steps 512 > gpurun_out/${P}_bench_f64.json 2> gpurun_out/${P}_bench_f64.err; python tools/show_bench.py gpurun_out/${P}_bench_f64.json | head -16
+echo "== CIFAR-deep (BASELINE configs[2]): FMA contractions vs tcgen05 implicit GEMM"; timeout 600 python tools/bench_cifar.py > gpurun_out/${P}_cifar.json 2> gpurun_out/${P}_cifar.err; cut -c1-330 gpurun_out/${P}_cifar.json; tail -2 gpurun_out/${P}_cifar.err
 echo "== ncu launch list of the bench command"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${P}_bench_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${P}_ncu_bench.log 2>&1
 wc -l gpurun_out/${P}_bench_launches.csv
@@ -30,3 +31,7 @@ for B in 256 8192; do
   ncu -i /tmp/${P}_prof_B${B}.ncu-rep --page raw --csv > gpurun_out/${P}_full_raw_B${B}.csv 2>/dev/null
 done
 ls -la gpurun_out | grep ${P}_
+echo "== ncu full: tensor-core contractions of one CIFAR-deep step"
+bash tools/gpu_ncu_cifar.sh ${P}_cifar 1 > /dev/null 2>&1
+rm -f gpurun_out/${P}_cifar_source.csv
+ls -la gpurun_out | grep ${P}_cifar
