@@ -7,5 +7,5 @@ from ._capi import DlbError, LayerSpec  # noqa: F401
 from .net import (  # noqa: F401
     ActivationFunctionId, CLayer, Context, CostFunctionId, LayerTypeId, NLayer, Net, PLayer, PoolTypeId,
     BUF_COST_GRAD, BUF_DERIVATIVES, BUF_GRADIENT, BUF_INDEX_MAP, BUF_INPUT_GRAD, BUF_OUTPUT,
-    Event, cifar_deep, lenet, nccl_unique_id, out_size, pinned_array, rank_slice, shuffle_sequence, timing_enable, timing_report,
+    Event, cifar_deep, dropout_masks, lenet, nccl_unique_id, out_size, pinned_array, rank_slice, shuffle_sequence, timing_enable, timing_report,
 )

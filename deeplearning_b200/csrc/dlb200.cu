@@ -169,6 +169,7 @@ struct LayerRt {
     ConvGeom cg{};
     int out_c = 0, out_h = 0, out_w = 0;
     int64_t in_n = 0, out_n = 0, param_off = 0, bias_n = 0, weight_n = 0;
+    double keep_rate = 1.0;   // ALayer::_keep_rate: one minus the dropout rate of the layer's input (ALayer.h:57-59)
 };
 
 // Validates the specs the way the reference's constructors and script loader would (CLayer.inl:29-40,
@@ -225,6 +226,24 @@ std::vector<LayerRt> build_layers(const dlb_layer_spec* specs, int n, int64_t& n
     return out;
 }
 
+// One keep mask over n inputs: Vector::fill_with_random_selection_map (Vector.cpp:208-233) restated with the same std::
+// calls - uniform values in (-1, 1) as sort keys (BasicCollection.cpp:327-328), the floor(n * keep_rate) smallest are
+// kept (ALayer.inl:31, product taken in Real) - so that with the same generator state the mask is the reference's, bit for
+// bit (same libstdc++).
+template <class R>
+void draw_keep_mask(std::mt19937& gen, size_t n, R keep, R* m, std::vector<R>& vals, std::vector<int>& idx) {
+    const size_t selected = static_cast<size_t>(static_cast<R>(n) * keep);
+    if (selected >= n) { std::fill(m, m + n, R(1)); return; }                     // Vector.cpp:211-215
+    vals.resize(n); idx.resize(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::uniform_real_distribution<R> dist(R(-1), R(1));
+    std::generate(vals.begin(), vals.end(), [&]() { return dist(gen); });
+    const R* v = vals.data();
+    std::ranges::sort(idx, [v](const auto a, const auto b) { return v[a] < v[b]; });
+    for (size_t i = 0; i < selected; ++i) m[idx[i]] = R(1);
+    for (size_t i = selected; i < n; ++i) m[idx[i]] = R(0);
+}
+
 }  // namespace
 
 // =================================================================================================================
@@ -236,6 +255,7 @@ struct dlb_net {
     std::vector<LayerRt> layers;
     int64_t n_params = 0;
     std::mt19937 rng{std::random_device{}()};  // Net<D>::ran_gen, Net.inl:392-396
+    std::mt19937 layer_rng{std::random_device{}()};  // ALayer<D>::ran_gen (ALayer.inl:131-135): draws the keep masks
     int rank = 0, world = 1;
 #ifndef DLB_CUDA_EMU
     NcclApi::comm_t comm = nullptr;
@@ -258,6 +278,9 @@ struct dlb_net {
     virtual std::string describe_plan() = 0;
     virtual void enable_graphs(bool on) = 0;
     virtual void enable_tensor_cores(int mode) = 0;
+    virtual void set_keep_rate(int layer, double keep_rate) = 0;
+    virtual int64_t mask_size() const = 0;
+    virtual void set_dropout_masks(const void* masks_host) = 0;
     virtual void p2p_export(void* handle64) = 0;
     virtual void p2p_connect(int rank, int world, const void* handles) = 0;
 };
@@ -280,6 +303,15 @@ struct NetT final : dlb_net {
     double* cost_dev = nullptr;
     int last_B = 0;
     UpdateSegments segs{};
+
+    // ---- dropout (ALayer.inl:25-55): a layer with keep_rate < 1 sees its input through a 0/1 keep mask that is redrawn for
+    // every mini-batch and shared by the batch's samples; its input gradient passes through the same mask; inference scales
+    // the input by keep_rate instead.  Off (keep_rate = 1 everywhere) the buffers below do not exist.
+    std::vector<R*> masked_in;         // [0]: [cap][in_n] masked (or scaled) copy of the batch when layer 0 drops inputs; deeper layers mask in place
+    std::vector<int64_t> mask_off;     // per layer offset into mask_dev, -1: the layer keeps everything
+    R* mask_dev = nullptr; int64_t mask_n = 0;
+    bool masks_ready = false;
+    std::vector<R> mask_host, mask_vals; std::vector<int> mask_idx;
 
     // ---- train mode (fused fast path, fused.cuh) ----
     struct TrainPlan {
@@ -403,6 +435,7 @@ struct NetT final : dlb_net {
         if (segs.count == 0) { segs.count = 1; segs.end[0] = 0; segs.regularised[0] = 0; }
         d_cursor = dev_alloc<int>(1);
         DLB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(int), ctx->stream));
+        layout_masks();
         build_plan();
 #ifndef DLB_CUDA_EMU
         if (plan.ok) {
@@ -426,6 +459,7 @@ struct NetT final : dlb_net {
     // memory, and at least two layers of parameters after the optional conv stage's position 0.
     void build_plan() {
         plan = TrainPlan{};
+        for (const auto& Y : layers) if (Y.keep_rate < 1.0) return;   // dropout runs through the layer-by-layer operators
         int idx = 0;
         if (layers[0].s.type == DLB_LAYER_CONVOLUTION) {
             if (L() < 3) return;
@@ -468,7 +502,7 @@ struct NetT final : dlb_net {
 #endif
         if (p2p_region) cudaFree(p2p_region);
         dev_free(d_p2p_step);
-        dev_free(cp_partial); dev_free(head_partial); dev_free(d_cursor);
+        dev_free(cp_partial); dev_free(head_partial); dev_free(d_cursor); dev_free(mask_dev);
         if (own_data) { dev_free(data_x); dev_free(data_y); }
 #ifndef DLB_CUDA_EMU
         if (comm) NcclApi::get().CommDestroy(comm);
@@ -480,6 +514,7 @@ struct NetT final : dlb_net {
         for (auto& p : deriv) dev_free(p);
         for (auto& p : in_grad) dev_free(p);
         for (auto& p : imap) dev_free(p);
+        for (auto& p : masked_in) dev_free(p);
         dev_free(g); dev_free(stage_x); dev_free(stage_y); dev_free(gather_dev);
         cap = 0;
     }
@@ -503,6 +538,8 @@ struct NetT final : dlb_net {
             max_out = std::max(max_out, Y.out_n);
         }
         in_grad[(size_t)L()] = dev_alloc<R>(b * (size_t)outN());
+        masked_in.assign((size_t)L(), nullptr);
+        if (layers[0].keep_rate < 1.0) masked_in[0] = dev_alloc<R>(b * (size_t)layers[0].in_n);
         g = dev_alloc<R>(b * (size_t)max_out);
         stage_x = dev_alloc<R>(b * (size_t)in0());
         stage_y = dev_alloc<R>(b * (size_t)outN());
@@ -528,6 +565,55 @@ struct NetT final : dlb_net {
         size_t need = 64u << 20;
         for (const auto& Y : layers) need = std::max(need, (size_t)(Y.weight_n + Y.bias_n) * sizeof(R) * 8);
         ctx->ensure_ws(need);
+    }
+
+    // ---- dropout plumbing ----------------------------------------------------------------------------------------
+    void layout_masks() {
+        mask_off.assign((size_t)L(), -1);
+        mask_n = 0;
+        for (int l = 0; l < L(); ++l)
+            if (layers[(size_t)l].keep_rate < 1.0) { mask_off[(size_t)l] = mask_n; mask_n += layers[(size_t)l].in_n; }
+    }
+
+    void set_keep_rate(int layer, double keep_rate) override {
+        DLB_REQUIRE(layer >= 0 && layer < L(), "Invalid layer index");
+        DLB_REQUIRE(keep_rate > 0.0, "keep_rate must be positive");
+        use_device(ctx);
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        layers[(size_t)layer].keep_rate = keep_rate;
+        drop_graphs();
+        free_workspace();              // the masked-input buffers follow the keep rates
+        build_plan();
+        layout_masks();
+        dev_free(mask_dev);
+        if (mask_n > 0) mask_dev = dev_alloc<R>((size_t)mask_n);
+        masks_ready = false;
+    }
+
+    int64_t mask_size() const override { return mask_n; }
+
+    void upload_masks(const R* host) {
+        DLB_CUDA(cudaMemcpyAsync(mask_dev, host, (size_t)mask_n * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));   // the host array may be pageable and short-lived
+        masks_ready = true;
+    }
+
+    void set_dropout_masks(const void* masks_host) override {
+        DLB_REQUIRE(mask_n > 0, "No layer of this net drops inputs");
+        DLB_REQUIRE(masks_host, "null masks");
+        use_device(ctx);
+        upload_masks(static_cast<const R*>(masks_host));
+    }
+
+    // SetUpDropoutMask of every layer, in layer order, once per mini-batch (Net.inl:228-230, ALayer.inl:26-35) on ALayer's generator.
+    void draw_masks() {
+        if (mask_n == 0) return;
+        mask_host.resize((size_t)mask_n);
+        for (int l = 0; l < L(); ++l)
+            if (mask_off[(size_t)l] >= 0)
+                draw_keep_mask<R>(layer_rng, (size_t)layers[(size_t)l].in_n, static_cast<R>(layers[(size_t)l].keep_rate),
+                                  mask_host.data() + mask_off[(size_t)l], mask_vals, mask_idx);
+        upload_masks(mask_host.data());
     }
 
     // ---- parameter / data movement ---------------------------------------------------------------------------
@@ -577,6 +663,18 @@ struct NetT final : dlb_net {
             R* d = traces ? deriv[(size_t)l] : nullptr;
             const R* bias = params + Y.param_off;
             const R* w = bias + Y.bias_n;
+            if (Y.keep_rate < 1.0) {   // ApplyDropout(input, trainingMode): Net.inl:126 (keep mask) / Net.inl:143 (times keep_rate)
+                DLB_REQUIRE(!traces || masks_ready, "A layer drops inputs but no keep masks have been set up");
+                TagScope tag_("dropout");
+                const size_t total = (size_t)B * (size_t)Y.in_n;
+                // like the reference, in place on the previous layer's output (gradient_cache[l].Input IS that tensor); only the
+                // resident data set (layer 0) is masked into a copy
+                R* dst = l == 0 ? masked_in[0] : out[(size_t)l - 1];
+                DLB_LAUNCH((dropout_apply_kernel<R>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, in, ga,
+                           traces ? (const R*)(mask_dev + mask_off[(size_t)l]) : (const R*)nullptr, static_cast<R>(Y.keep_rate),
+                           dst, total, (int)Y.in_n);
+                in = dst; ga = nullptr;
+            }
             switch (Y.s.type) {
             case DLB_LAYER_CONVOLUTION: conv_forward<R>(lc, B, Y.cg, Y.s.activation, in, ga, bias, w, y, d); break;
             case DLB_LAYER_FULL: full_forward<R>(lc, B, (int)Y.in_n, (int)Y.out_n, Y.s.activation, in, ga, bias, w, y, d); break;
@@ -599,6 +697,7 @@ struct NetT final : dlb_net {
             g_tag_layer = l;
             const R* in = l == 0 ? x : out[(size_t)l - 1];
             const int* ga = l == 0 ? gather : nullptr;
+            if (Y.keep_rate < 1.0 && l == 0) { in = masked_in[0]; ga = nullptr; }   // the layer saw (and differentiates against) the masked input; l > 0: out[l-1] was masked in place
             R* dx = l == 0 ? nullptr : in_grad[(size_t)l];   // evaluate_input_gradient = layer_id != 0 (Net.inl:272)
             R* db = grads + Y.param_off;
             R* dw = db + Y.bias_n;
@@ -610,6 +709,12 @@ struct NetT final : dlb_net {
                 full_backward<R>(lc, B, (int)Y.in_n, (int)Y.out_n, Y.s.activation, in, ga, delta, deriv[(size_t)l], w, g, db, dw, dx, scale); break;
             default:
                 if (dx) pool_backward<R>(lc, B, Y.s, delta, imap[(size_t)l], dx);
+            }
+            if (dx && Y.keep_rate < 1.0) {   // ApplyDropout(e_data.out(), true) on the input gradient, Net.inl:274-275
+                TagScope tag_("dropout");
+                const size_t total = (size_t)B * (size_t)Y.in_n;
+                DLB_LAUNCH((dropout_apply_kernel<R>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, (const R*)dx,
+                           (const int*)nullptr, (const R*)(mask_dev + mask_off[(size_t)l]), R(1), dx, total, (int)Y.in_n);
             }
             delta = dx;
         }
@@ -882,6 +987,7 @@ struct NetT final : dlb_net {
     // gather_base + (*cursor if cursor) addresses this rank's slice; `advance` is added to the cursor at the end of the step.
     void step_device(const R* x, const R* refs, const int* gather_base, const int* cursor, int advance, int64_t mine, int64_t global,
                      double lr, int cost, double reg_factor) {
+        draw_masks();   // one set of keep masks per (global) mini-batch; every rank draws the same ones from the same seed
         if (plan.ok && mine > 0) {
             ensure_capacity(mine);
             auto body = [&] {
@@ -1037,6 +1143,7 @@ struct NetT final : dlb_net {
         DLB_CUDA(cudaStreamWaitEvent(ctx->stream, ev_copied[buf], 0));
 #endif
         const bool want_cost = cost_out != nullptr;
+        draw_masks();
         auto body = [&] {
             if (plan.ok) train_forward_backward((int)n, sx, sy, nullptr, nullptr, cost);
             else forward_backward((int)n, sx, sy, nullptr, cost, R(0));
@@ -1391,7 +1498,12 @@ void* dlb_net_device_grads(dlb_net* net) { return net ? net->device_grads() : nu
 int dlb_net_set_dataset(dlb_net* net, const void* x, const void* y, int64_t n, int on_device) {
     return guarded([&] { DLB_REQUIRE(net, "null net"); net->set_dataset(x, y, n, on_device != 0); });
 }
-int dlb_net_reset_random_generator(dlb_net* net, unsigned seed) { return guarded([&] { DLB_REQUIRE(net, "null net"); net->rng.seed(seed); }); }
+int dlb_net_reset_random_generator(dlb_net* net, unsigned seed) {
+    return guarded([&] { DLB_REQUIRE(net, "null net"); net->rng.seed(seed); net->layer_rng.seed(seed); });   // Net.inl:620-624 seeds both
+}
+int dlb_net_set_keep_rate(dlb_net* net, int layer, double keep_rate) { return guarded([&] { DLB_REQUIRE(net, "null net"); net->set_keep_rate(layer, keep_rate); }); }
+int64_t dlb_net_mask_size(const dlb_net* net) { return net ? net->mask_size() : -1; }
+int dlb_net_set_dropout_masks(dlb_net* net, const void* masks_host) { return guarded([&] { DLB_REQUIRE(net, "null net"); net->set_dropout_masks(masks_host); }); }
 int dlb_net_learn(dlb_net* net, int64_t batch, int64_t epochs, double lr, int cost, double lambda, dlb_epoch_callback cb, void* user) {
     return guarded([&] {
         DLB_REQUIRE(net, "null net");
@@ -1581,6 +1693,26 @@ int dlb_shuffle_sequence(unsigned seed, int64_t n, int64_t epochs, int64_t* out)
             std::ranges::shuffle(idx, gen);
             for (int64_t i = 0; i < n; ++i) out[e * n + i] = (int64_t)idx[(size_t)i];
         }
+    });
+}
+
+int dlb_dropout_masks(unsigned seed, const int64_t* in_sizes, const double* keep_rates, int n_layers, int64_t n_batches, int real_bytes, void* out) {
+    return guarded([&] {
+        DLB_REQUIRE(in_sizes && keep_rates && out && n_layers > 0 && n_batches >= 0, "Invalid input.");
+        DLB_REQUIRE(real_bytes == 4 || real_bytes == 8, "real_bytes must be 4 or 8");
+        std::mt19937 gen(seed);
+        auto run = [&](auto* dst) {
+            using R = std::remove_pointer_t<decltype(dst)>;
+            std::vector<R> vals; std::vector<int> idx;
+            for (int64_t b = 0; b < n_batches; ++b)
+                for (int l = 0; l < n_layers; ++l) {
+                    const R keep = static_cast<R>(keep_rates[l]);
+                    if (!(keep < R(1))) continue;
+                    draw_keep_mask<R>(gen, (size_t)in_sizes[l], keep, dst, vals, idx);
+                    dst += in_sizes[l];
+                }
+        };
+        if (real_bytes == 4) run(static_cast<float*>(out)); else run(static_cast<double*>(out));
     });
 }
 

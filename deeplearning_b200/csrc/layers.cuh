@@ -441,6 +441,17 @@ __global__ void sgd_update_kernel(R* __restrict__ p, const R* __restrict__ g, si
 // ---------------------------------------------------------------------------------------------------------------
 // Typed host-side launchers.
 // ---------------------------------------------------------------------------------------------------------------
+// ApplyDropout (ALayer.inl:46-55) over a batch: out[b][i] = in[row(b)][i] * (mask ? mask[i] : scale); in place when out == in.
+template <class R>
+__global__ void dropout_apply_kernel(const R* in, const int* __restrict__ gather, const R* __restrict__ mask, R scale,
+                                     R* out, size_t total, int n) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const size_t b = e / (size_t)n; const int i = (int)(e - b * (size_t)n);
+    const size_t row = gather ? (size_t)gather[b] : b;
+    out[e] = in[row * (size_t)n + i] * (mask ? mask[i] : scale);
+}
+
 struct LaunchCtx {
     cudaStream_t stream;
     GemmWorkspace ws;

@@ -131,6 +131,11 @@ public:
     std::size_t param_count() { return (std::size_t)dlb_net_param_count(handle()); }
     std::string describe_plan() { char buf[512]; check(dlb_net_describe_plan(handle(), buf, sizeof buf)); return buf; }
 
+    // The keep_rate constructor argument of the reference's layers (CLayer.h:147, PLayer.h:105, NLayer.h:132; ALayer.inl:25-55):
+    // one minus the dropout rate of the layer's input.  Masks are drawn per mini-batch from ALayer's generator, which
+    // reset_random_generator(seed) seeds together with the permutation generator (Net.inl:620-624).
+    void set_keep_rate(std::size_t layer, Real keep_rate) { check(dlb_net_set_keep_rate(handle(), (int)layer, (double)keep_rate)); }
+
     // Parameters in the reference's container order (GpuDC::from_host / to_host on every container).
     void set_params(const std::vector<Real>& flat) {
         if (flat.size() != param_count()) throw std::runtime_error("Collections must be of the same size");

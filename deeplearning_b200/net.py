@@ -268,6 +268,22 @@ class Net:
         least 128 samples per GPU (the default), 2 = tcgen05 at every batch size."""
         _capi.check(self.lib.dlb_net_enable_tensor_cores(self._handle(), int(mode)))
 
+    def set_keep_rate(self, layer: int, keep_rate: float) -> None:
+        """ALayer::set_keep_rate / the keep_rate constructor argument of CLayer, PLayer and NLayer (one minus the dropout rate
+        of the layer's input, ALayer.inl:25-55)."""
+        _capi.check(self.lib.dlb_net_set_keep_rate(self._handle(), int(layer), float(keep_rate)))
+
+    @property
+    def mask_size(self) -> int:
+        return int(self.lib.dlb_net_mask_size(self._handle()))
+
+    def set_dropout_masks(self, masks) -> None:
+        """Explicit keep masks of one mini-batch for forward_backward() (layers with keep_rate < 1 in layer order)."""
+        m = np.ascontiguousarray(masks, self.dtype).ravel()
+        if m.size != self.mask_size:
+            raise ValueError(f"expected {self.mask_size} mask elements")
+        _capi.check(self.lib.dlb_net_set_dropout_masks(self._handle(), m.ctypes.data))
+
     def enable_graphs(self, on: bool) -> None:
         _capi.check(self.lib.dlb_net_enable_graphs(self._handle(), 1 if on else 0))
 
@@ -462,6 +478,17 @@ def nccl_unique_id() -> bytes:
 def shuffle_sequence(seed: int, n: int, epochs: int) -> np.ndarray:
     out = np.zeros((epochs, n), np.int64)
     _capi.check(_capi.load().dlb_shuffle_sequence(seed, n, epochs, out.ctypes.data))
+    return out
+
+
+def dropout_masks(seed: int, in_sizes, keep_rates, n_batches: int, real: str = "f32") -> np.ndarray:
+    """The keep masks the training entry points draw after reset_random_generator(seed): [n_batches, mask_size]."""
+    dtype = {"f32": np.float32, "f64": np.float64}[real]
+    sizes = np.asarray(in_sizes, np.int64); keep = np.asarray(keep_rates, np.float64)
+    width = int(sum(int(s) for s, k in zip(sizes, keep) if dtype(k) < 1))
+    out = np.zeros((n_batches, width), dtype)
+    _capi.check(_capi.load().dlb_dropout_masks(seed, sizes.ctypes.data, keep.ctypes.data, len(sizes), n_batches, np.dtype(dtype).itemsize,
+                                               out.ctypes.data))
     return out
 
 

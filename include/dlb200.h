@@ -122,6 +122,20 @@ DLB_API int dlb_net_set_dataset(dlb_net* net, const void* inputs, const void* re
 /* Net<D>::reset_random_generator(seed), Net.inl:599-603: seeds the generator that draws the epoch permutations. */
 DLB_API int dlb_net_reset_random_generator(dlb_net* net, unsigned seed);
 
+/* Dropout, ALayer.inl:25-55 (the keep_rate argument of the reference's CLayer / PLayer / NLayer constructors, CLayer.h:145-147,
+ * PLayer.h:104-105, NLayer.h:130-132; ALayer::set_keep_rate): a layer with keep_rate < 1 multiplies its input by a 0/1 keep
+ * mask (exactly floor(in_size * keep_rate) ones) that is redrawn for every mini-batch and shared by the batch's samples,
+ * multiplies its input gradient by the same mask, and scales its input by keep_rate at inference (dlb_net_eval_host,
+ * dlb_net_evaluate_host).  The masks are drawn like the reference draws them (Vector::fill_with_random_selection_map on
+ * ALayer's generator, which dlb_net_reset_random_generator seeds together with the permutation generator, Net.inl:620-624).
+ * A net with dropout runs the layer-by-layer operators (dlb_net_describe_plan says so). */
+DLB_API int dlb_net_set_keep_rate(dlb_net* net, int layer, double keep_rate);
+/* Elements of one mini-batch's masks: the input sizes of the layers with keep_rate < 1, in layer order. */
+DLB_API int64_t dlb_net_mask_size(const dlb_net* net);
+/* Explicit keep masks (host, the net's Real, dlb_net_mask_size elements) for dlb_net_forward_backward_host, which - like
+ * Net::act_bpg - applies whatever masks are currently set up; the training entry points draw their own per mini-batch. */
+DLB_API int dlb_net_set_dropout_masks(dlb_net* net, const void* masks_host);
+
 typedef void (*dlb_epoch_callback)(int64_t epoch, double scaled_l2_reg_factor, void* user);
 
 /* Net<D>::learn, Net.inl:193-324, on the resident data set: per epoch one std::ranges::shuffle of the index map,
@@ -227,6 +241,13 @@ DLB_API int dlb_net_set_distributed_p2p(dlb_net* net, int rank, int world_size, 
 /* The epoch permutations learn() would draw after reset_random_generator(seed): iota + one shuffle per epoch on
  * the same std::mt19937 (Net.inl:158-171, 223).  Host-only helper for tests and for reference-side callers. */
 DLB_API int dlb_shuffle_sequence(unsigned seed, int64_t n, int64_t epochs, int64_t* out);
+
+/* The keep masks the training entry points draw after dlb_net_reset_random_generator(seed): per mini-batch, per layer with
+ * keep_rate < 1 in layer order, Vector::fill_with_random_selection_map over the layer's input (ALayer.inl:26-35,
+ * Vector.cpp:208-233).  out: n_batches blocks of sum(in_sizes[l] for keep_rates[l] < 1) elements of float (real_bytes 4)
+ * or double (8).  Host-only helper for tests and for reference-side callers. */
+DLB_API int dlb_dropout_masks(unsigned seed, const int64_t* in_sizes, const double* keep_rates, int n_layers, int64_t n_batches,
+                              int real_bytes, void* out);
 
 #ifdef __cplusplus
 }

@@ -135,7 +135,14 @@ def _load(kind: str, real: str) -> C.CDLL:
     f = getattr(lib, p + "cost"); f.restype = dbl; f.argtypes = [vp, vp, i64, i32]
     if kind == "oracle":
         lib.orc_net_learn.argtypes = [vp, vp, vp, i64, i64, i64, dbl, i32, dbl, i32, vp]
+        lib.orc_net_learn_dropout.argtypes = [vp, vp, vp, i64, i64, i64, dbl, i32, dbl, i32, vp, vp]
+        lib.orc_net_set_keep_rate.argtypes = [vp, i32, dbl]
+        lib.orc_net_mask_size.restype = i64; lib.orc_net_mask_size.argtypes = [vp]
+        lib.orc_net_bind_masks.argtypes = [vp, vp]
     else:
+        lib.dlref_net_create_dropout.restype = vp
+        lib.dlref_net_create_dropout.argtypes = [C.POINTER(LayerSpec), i32, C.c_uint, vp]
+        lib.dlref_dropout_masks.argtypes = [C.c_uint, vp, vp, i32, i64, vp]
         lib.dlref_net_learn.argtypes = [vp, vp, vp, i64, i64, i64, dbl, i32, dbl, i32, i64, vp]
         lib.dlref_uniform_items.argtypes = [vp, i64, i32, i32, i32, dbl, dbl, C.c_uint]
         lib.dlref_reset_random_generator.argtypes = [C.c_uint]
@@ -152,19 +159,26 @@ class _NetBase:
     kind = ""
     prefix = ""
 
-    def __init__(self, specs: Sequence[LayerSpec], real: str = "f32", seed: int = 0):
+    def __init__(self, specs: Sequence[LayerSpec], real: str = "f32", seed: int = 0, keep_rates=None):
+        """keep_rates (optional): one keep_rate per layer (ALayer::_keep_rate, 1 = no dropout)."""
         self.real = real
         self.dtype = dtype_of(real)
         self.lib = _load(self.kind, real)
         assert getattr(self.lib, self.prefix + "real_bytes")() == np.dtype(self.dtype).itemsize
         self.specs = list(specs)
         arr = (LayerSpec * len(self.specs))(*self.specs)
+        self.keep_rates = [1.0] * len(self.specs) if keep_rates is None else [float(k) for k in keep_rates]
+        assert len(self.keep_rates) == len(self.specs)
         if self.kind == "ref":
-            self.h = self.lib.dlref_net_create(arr, len(self.specs), seed)
+            kr = np.asarray(self.keep_rates, np.float64)
+            self.h = self.lib.dlref_net_create_dropout(arr, len(self.specs), seed, _ptr(kr))
         else:
             self.h = self.lib.orc_net_create(arr, len(self.specs))
         if not self.h:
             raise ValueError(self._err())
+        if self.kind == "oracle":
+            for l, k in enumerate(self.keep_rates):
+                self._check(self.lib.orc_net_set_keep_rate(self.h, l, k))
         self.n_layers = len(self.specs)
         self.out_sizes = [self._f("net_layer_out_size")(self.h, l) for l in range(self.n_layers)]
         self.in_sizes = [self._f("net_layer_in_size")(self.h, l) for l in range(self.n_layers)]
@@ -228,12 +242,27 @@ class _NetBase:
 class OracleNet(_NetBase):
     kind, prefix = "oracle", "orc_"
 
-    def learn(self, inputs, refs, batch, epochs, lr, cost_id, lam, threads, perms):
+    def learn(self, inputs, refs, batch, epochs, lr, cost_id, lam, threads, perms, masks=None):
+        """masks: [n_batches, mask_size] keep masks (layers with keep_rate < 1 in layer order), one row per mini-batch."""
         inputs = np.ascontiguousarray(inputs, self.dtype).reshape(-1, self.in_sizes[0])
         refs = np.ascontiguousarray(refs, self.dtype).reshape(-1, self.out_sizes[-1])
         perms = np.ascontiguousarray(perms, np.int64).reshape(epochs, inputs.shape[0])
-        self._check(self.lib.orc_net_learn(self.h, _ptr(inputs), _ptr(refs), inputs.shape[0], batch, epochs, float(lr),
-                                           cost_id, float(lam), threads, _ptr(perms)))
+        if masks is not None:
+            masks = np.ascontiguousarray(masks, self.dtype)
+            assert masks.ndim == 2 and masks.shape[1] == self.mask_size
+        self._check(self.lib.orc_net_learn_dropout(self.h, _ptr(inputs), _ptr(refs), inputs.shape[0], batch, epochs, float(lr),
+                                                   cost_id, float(lam), threads, _ptr(perms), _ptr(masks)))
+
+    @property
+    def mask_size(self) -> int:
+        return int(self.lib.orc_net_mask_size(self.h))
+
+    def bind_masks(self, masks) -> None:
+        """One mini-batch's masks for trace(); kept alive here.  None clears them."""
+        self._masks = None if masks is None else np.ascontiguousarray(masks, self.dtype).ravel()
+        if self._masks is not None:
+            assert self._masks.size == self.mask_size
+        self._check(self.lib.orc_net_bind_masks(self.h, _ptr(self._masks)))
 
 
 class RefNet(_NetBase):
@@ -270,5 +299,26 @@ def ref_shuffle_sequence(seed: int, n: int, epochs: int) -> np.ndarray:
     lib = _load("ref", "f32")
     out = np.zeros((epochs, n), np.int64)
     if lib.dlref_shuffle_sequence(seed, n, epochs, _ptr(out)):
+        raise RuntimeError(lib.dlref_last_error().decode())
+    return out
+
+
+def count_batches(n: int, batch: int) -> int:
+    """Mini-batches per epoch under the tail rule of Net.inl:235-236."""
+    k, start = 0, 0
+    while start < n:
+        start = n if (n - start) < 1.5 * batch else start + batch
+        k += 1
+    return k
+
+
+def ref_dropout_masks(real: str, seed: int, in_sizes, keep_rates, n_batches: int) -> np.ndarray:
+    """The keep masks Net<CpuDC>::learn draws after reset_random_generator(seed): [n_batches, sum(in_size for keep < 1)]
+    from the reference's own Vector::fill_with_random_selection_map (libstdc++ mt19937 + uniform_real_distribution + sort)."""
+    lib = _load("ref", real)
+    sizes = np.asarray(in_sizes, np.int64); keep = np.asarray(keep_rates, np.float64)
+    width = int(sum(s for s, k in zip(in_sizes, keep_rates) if np.dtype(dtype_of(real)).type(k) < 1))
+    out = np.zeros((n_batches, width), dtype_of(real))
+    if lib.dlref_dropout_masks(seed, _ptr(sizes), _ptr(keep), len(in_sizes), n_batches, _ptr(out)):
         raise RuntimeError(lib.dlref_last_error().decode())
     return out

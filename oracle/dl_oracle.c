@@ -35,6 +35,7 @@ typedef struct {
     int out_c, out_h, out_w;
     int64_t in_n, out_n;
     int64_t param_off, bias_n, weight_n; /* weight_n: all weights of the layer (F filters together) */
+    R keep_rate;                         /* ALayer::_keep_rate, 1 = no dropout (ALayer.h:59) */
 } orc_layer;
 
 struct orc_net {
@@ -43,6 +44,7 @@ struct orc_net {
     int64_t n_params;
     int64_t act_total, in_total;
     R* params;
+    const R** mask;   /* per layer: the current batch's keep mask over the layer input (ALayer::_keep_mask), or NULL */
 };
 
 int orc_real_bytes(void) { return (int)sizeof(R); }
@@ -93,6 +95,7 @@ orc_net* orc_net_create(const dlb_layer_spec* specs, int n_layers) {
         default: ok = 0;
         }
         L->out_n = (int64_t)L->out_c * L->out_h * L->out_w;
+        L->keep_rate = (R)1;
         /* Net.inl:83-88 consistency of consecutive layers */
         if (ok && l > 0) {
             const orc_layer* P = &net->layers[l - 1];
@@ -109,10 +112,35 @@ orc_net* orc_net_create(const dlb_layer_spec* specs, int n_layers) {
     }
     net->n_params = off;
     net->params = (R*)calloc((size_t)(off > 0 ? off : 1), sizeof(R));
+    net->mask = (const R**)calloc((size_t)n_layers, sizeof(R*));
     return net;
 }
 
+/* ALayer<D>::set_keep_rate, ALayer.inl:154-157. */
+int orc_net_set_keep_rate(orc_net* net, int layer, double keep_rate) {
+    if (layer < 0 || layer >= net->n_layers) return fail("orc_net_set_keep_rate: no such layer");
+    net->layers[layer].keep_rate = (R)keep_rate;
+    return 0;
+}
+
+/* Number of mask elements one mini-batch consumes: the input sizes of the layers with keep_rate < 1, in layer order
+ * (Net.inl:229-230 calls SetUpDropoutMask on every layer, ALayer.inl:28 skips those that keep everything). */
+int64_t orc_net_mask_size(const orc_net* net) {
+    int64_t n = 0;
+    for (int l = 0; l < net->n_layers; ++l) if (net->layers[l].keep_rate < (R)1) n += net->layers[l].in_n;
+    return n;
+}
+
+/* Points the layers at their masks inside one batch's block of `masks` (NULL: no dropout). */
+static void bind_masks(orc_net* net, const R* masks) {
+    for (int l = 0; l < net->n_layers; ++l) {
+        net->mask[l] = NULL;
+        if (masks && net->layers[l].keep_rate < (R)1) { net->mask[l] = masks; masks += net->layers[l].in_n; }
+    }
+}
+
 void orc_net_destroy(orc_net* net) {
+    if (net) free((void*)net->mask);
     if (!net) return;
     free(net->params); free(net->layers); free(net);
 }
@@ -453,7 +481,11 @@ static void ws_destroy(const orc_net* net, orc_ws* w) {
 
 static void forward_traced(const orc_net* net, orc_ws* w, const R* input) {
     memcpy(w->input[0], input, (size_t)net->layers[0].in_n * sizeof(R)); /* gradient_cache[0].Input = input, Net.inl:123 */
-    for (int l = 0; l < net->n_layers; ++l) layer_act(net, l, w->input[l], w->input[l + 1], w->deriv[l], w->map[l]);
+    for (int l = 0; l < net->n_layers; ++l) {
+        if (net->mask[l])   /* ApplyDropout(gradient_cache[l].Input, true): hadamard_prod_in_place with the keep mask, Net.inl:126, ALayer.inl:46-55 */
+            for (int64_t i = 0; i < net->layers[l].in_n; ++i) w->input[l][i] = w->input[l][i] * net->mask[l][i];
+        layer_act(net, l, w->input[l], w->input[l + 1], w->deriv[l], w->map[l]);
+    }
 }
 
 /* deltas enter in w->delta_a (cost derivative); grads is the flat gradient buffer of one "thread". */
@@ -470,10 +502,15 @@ static void backward(const orc_net* net, orc_ws* w, R* grads, R scale, R* in_gra
         case DLB_LAYER_PULL: pool_backprop(Y, cur, w->map[l], ig); break;
         default: full_backprop(Y, net->params, cur, w->input[l], w->deriv[l], ig, grad, scale, w->g); break;
         }
+        if (ig && net->mask[l])   /* ApplyDropout(e_data.out(), true) on the input gradient, Net.inl:274-275 */
+            for (int64_t i = 0; i < Y->in_n; ++i) ig[i] = ig[i] * net->mask[l][i];
         if (ig && in_grads_out) memcpy(in_grads_out + in_off, ig, (size_t)Y->in_n * sizeof(R));
         R* t = cur; cur = nxt; nxt = t;
     }
 }
+
+/* Masks for orc_net_trace (one block as in orc_net_learn_dropout); NULL clears them.  The caller keeps the array alive. */
+int orc_net_bind_masks(orc_net* net, const orc_real* masks) { bind_masks(net, masks); return 0; }
 
 int orc_net_trace(const orc_net* net, const orc_real* input, const orc_real* target, int cost_id, double scale,
                   orc_real* acts, orc_real* derivs, int32_t* index_map, orc_real* grads, orc_real* in_grads,
@@ -519,7 +556,15 @@ static void update_params(orc_net* net, const R* grad, R l_rate, R reg_factor, R
 
 int orc_net_learn(orc_net* net, const orc_real* inputs, const orc_real* refs, int64_t n, int64_t batch, int64_t epochs,
                   double lr, int cost_id, double lambda, int threads, const int64_t* perms) {
+    return orc_net_learn_dropout(net, inputs, refs, n, batch, epochs, lr, cost_id, lambda, threads, perms, NULL);
+}
+
+int orc_net_learn_dropout(orc_net* net, const orc_real* inputs, const orc_real* refs, int64_t n, int64_t batch, int64_t epochs,
+                          double lr, int cost_id, double lambda, int threads, const int64_t* perms, const orc_real* masks) {
     if (n == 0 || batch == 0) return 0;                                  /* Net.inl:200-201 */
+    const int64_t mask_n = orc_net_mask_size(net);
+    if (mask_n > 0 && !masks) return fail("orc_net_learn: a layer drops inputs but no masks were supplied");
+    int64_t batch_no = 0;
     if (!perms) return fail("orc_net_learn: permutations are required");
     const R reg_factor = (R)lambda / (R)n;                               /* Net.inl:203 */
     int64_t T = threads <= 0 ? 1 : threads;
@@ -533,6 +578,8 @@ int orc_net_learn(orc_net* net, const orc_real* inputs, const orc_real* refs, in
         const int64_t* perm = perms + e * n;
         int64_t start = 0;
         while (start < n) {
+            bind_masks(net, mask_n > 0 ? masks + batch_no * mask_n : NULL);                         /* new masks per batch, Net.inl:228-230 */
+            ++batch_no;
             const int64_t end = (double)(n - start) < 1.5 * (double)batch ? n : start + batch;     /* Net.inl:235-236 */
             const int64_t ipt = (end - start + T - 1) / T;                                         /* Net.inl:238 */
             const int64_t expected = (end - start + ipt - 1) / ipt;                                /* Net.inl:242 */
@@ -557,6 +604,7 @@ int orc_net_learn(orc_net* net, const orc_real* inputs, const orc_real* refs, in
             update_params(net, G[0], -(R)lr, reg_factor, norm);                                    /* Net.inl:314-316 */
         }
     }
+    bind_masks(net, NULL);                                                                         /* DisposeDropoutMask, Net.inl:322-323 */
     ws_destroy(net, w);
     for (int64_t j = 0; j < T; ++j) free(G[j]);
     free(G);
@@ -568,7 +616,12 @@ int orc_net_eval(const orc_net* net, const orc_real* inputs, int64_t n, int32_t*
     const int64_t in_n = net->layers[0].in_n, out_n = net->layers[net->n_layers - 1].out_n;
     for (int64_t i = 0; i < n; ++i) {
         memcpy(w->input[0], inputs + i * in_n, (size_t)in_n * sizeof(R));
-        for (int l = 0; l < net->n_layers; ++l) layer_act(net, l, w->input[l], w->input[l + 1], NULL, NULL);
+        for (int l = 0; l < net->n_layers; ++l) {
+            const R keep = net->layers[l].keep_rate;
+            if (keep < (R)1)   /* ApplyDropout(eval_data.in(), false): input.mul(_keep_rate), Net.inl:143, ALayer.inl:53-54 */
+                for (int64_t k = 0; k < net->layers[l].in_n; ++k) w->input[l][k] = w->input[l][k] * keep;
+            layer_act(net, l, w->input[l], w->input[l + 1], NULL, NULL);
+        }
         const R* o = w->input[net->n_layers];
         if (outputs) memcpy(outputs + i * out_n, o, (size_t)out_n * sizeof(R));
         if (classes) { int64_t b = 0; for (int64_t k = 1; k < out_n; ++k) if (o[b] < o[k]) b = k; classes[i] = (int32_t)b; }

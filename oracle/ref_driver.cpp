@@ -83,7 +83,13 @@ const char* dlref_last_error() { return g_err.c_str(); }
 // Seeds Net's and ALayer's thread-local generators of the calling thread (Net.inl:599-603).
 void dlref_reset_random_generator(unsigned seed) { Net<CpuDC>::reset_random_generator(seed); }
 
-void* dlref_net_create(const dlb_layer_spec* specs, int n, unsigned seed) {
+void* dlref_net_create_dropout(const dlb_layer_spec* specs, int n, unsigned seed, const double* keep_rates);
+
+void* dlref_net_create(const dlb_layer_spec* specs, int n, unsigned seed) { return dlref_net_create_dropout(specs, n, seed, nullptr); }
+
+// keep_rates (nullable): the layers' keep_rate constructor argument (CLayer.h:145-147, PLayer.h:104-105, NLayer.h:130-132);
+// ALayer::set_keep_rate is protected, so the constructors are the only way in.
+void* dlref_net_create_dropout(const dlb_layer_spec* specs, int n, unsigned seed, const double* keep_rates) {
     RefNet* rn = nullptr;
     const int rc = guarded([&] {
         Net<CpuDC>::reset_random_generator(seed);
@@ -92,17 +98,18 @@ void* dlref_net_create(const dlb_layer_spec* specs, int n, unsigned seed) {
             const auto& s = specs[i];
             const Index3d in{ s.in_c, s.in_h, s.in_w };
             const auto act = static_cast<ActivationFunctionId>(s.activation);
+            const Real keep = keep_rates ? static_cast<Real>(keep_rates[i]) : Real(1);
             switch (s.type) {
             case DLB_LAYER_CONVOLUTION:
                 rn->net.append_layer<CLayer>(in, Index2d{ s.win_h, s.win_w }, static_cast<std::size_t>(s.out_c), act,
-                    Index3d{ 0, s.pad_h, s.pad_w }, Index3d{ 1, s.stride_h, s.stride_w });
+                    Index3d{ 0, s.pad_h, s.pad_w }, Index3d{ 1, s.stride_h, s.stride_w }, keep);
                 break;
             case DLB_LAYER_PULL:
-                rn->net.append_layer<PLayer>(in, Index2d{ s.win_h, s.win_w }, static_cast<PoolTypeId>(s.pool_type));
+                rn->net.append_layer<PLayer>(in, Index2d{ s.win_h, s.win_w }, static_cast<PoolTypeId>(s.pool_type), keep);
                 break;
             case DLB_LAYER_FULL:
                 rn->net.append_layer<NLayer>(static_cast<std::size_t>(in.coord_prod()), static_cast<std::size_t>(s.out_c), act,
-                    Real(-1), Real(1), true);
+                    Real(-1), Real(1), true, keep);
                 break;
             default: throw std::runtime_error("dlref_net_create: unknown layer type");
             }
@@ -209,6 +216,28 @@ int dlref_net_learn(void* h, const Real* inputs, const Real* refs, int64_t n, in
             static_cast<CostFunctionId>(cost_id), static_cast<Real>(lambda), [](auto, auto) {}, parallelism);
         const auto t1 = std::chrono::steady_clock::now();
         if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    });
+}
+
+// The keep masks Net<CpuDC>::learn draws after reset_random_generator(seed) (which seeds ALayer's generator with the same
+// seed, Net.inl:620-624): per mini-batch, per layer in order, SetUpDropoutMask (ALayer.inl:26-35) = the reference's own
+// Vector::fill_with_random_selection_map(size * keep_rate) on that generator.  sizes[l] = input size of layer l,
+// keep[l] >= 1 = the layer draws nothing.  out: n_batches blocks of sum(sizes[l] for keep[l] < 1) values.
+int dlref_dropout_masks(unsigned seed, const int64_t* sizes, const double* keep, int n_layers, int64_t n_batches, Real* out) {
+    return guarded([&] {
+        std::mt19937 g(seed);
+        std::vector<int> aux;
+        for (int64_t b = 0; b < n_batches; ++b)
+            for (int l = 0; l < n_layers; ++l) {
+                const Real k = static_cast<Real>(keep[l]);
+                if (!(k < Real(1))) continue;
+                const auto n = static_cast<std::size_t>(sizes[l]);
+                const auto selected = static_cast<std::size_t>(n * k);     // ALayer.inl:31
+                Vector v(n);
+                v.fill_with_random_selection_map(selected, aux, &g);
+                std::memcpy(out, v.begin(), n * sizeof(Real));
+                out += n;
+            }
     });
 }
 

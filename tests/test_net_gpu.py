@@ -291,3 +291,54 @@ def test_evaluate_cost_and_correct_answers(real):
     assert abs(got_cost - want_cost) <= (1e-4 if real == "f32" else 1e-10) * abs(want_cost)
     assert got_correct == want_correct
     assert gpu.count_correct_answers(x, y) == int(round(want_correct * 50))
+
+
+DROPOUT_NETS = {"mini_lenet": (MINI_LENET, [0.8, 1.0, 0.5, 0.9], ob.CROSS_ENTROPY),
+                "fixture": (FIXTURE_NET, [1.0, 0.7, 0.6, 1.0], ob.SQUARED_ERROR)}
+
+
+def make_dropout_pair(name, real):
+    specs, keep, cost = DROPOUT_NETS[name]
+    orc = ob.OracleNet(specs, real, keep_rates=keep)
+    params = H.synthetic_params(orc.param_count, specs, real, seed=5)
+    orc.set_params(params)
+    gpu = dl.Net([H.to_dl_spec(s) for s in specs], real=real)
+    gpu.set_params(params)
+    for l, k in enumerate(keep):
+        gpu.set_keep_rate(l, k)
+    assert gpu.mask_size == orc.mask_size > 0
+    assert gpu.describe_plan().startswith("unfused")
+    return orc, gpu, keep, cost
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+@pytest.mark.parametrize("name", list(DROPOUT_NETS))
+def test_dropout_traces_match_oracle(name, real):
+    """ALayer::ApplyDropout (ALayer.inl:46-55) in the batched operators: keep masks on layer inputs (Net.inl:126) and input
+    gradients (Net.inl:274-275), every trace buffer against the oracle under the same explicit masks; inference = inputs
+    times keep_rate (Net.inl:143), predicted classes exactly."""
+    orc, gpu, keep, cost = make_dropout_pair(name, real)
+    x, y = H.synthetic_batch(orc, 6, real, seed=21, one_hot=cost == ob.CROSS_ENTROPY)
+    masks = dl.dropout_masks(9, orc.in_sizes, keep, 1, real)[0]
+    orc.bind_masks(masks)
+    gpu.set_dropout_masks(masks)
+    compare_traces(orc, gpu, x, y, cost, real)
+    orc.bind_masks(None)
+    want_cls, want_out = orc.eval(x, True)
+    H.assert_close("inference outputs with keep rates", gpu.act(x), want_out, real, rtol_mult=5)
+    assert np.array_equal(gpu.predict(x), want_cls)
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_learn_with_dropout_matches_oracle(real):
+    """dlb_net_learn draws its own masks per mini-batch like Net::learn (Net.inl:228-230): after the same seed the updated
+    parameters must equal the oracle's, which is fed the mask stream (tests/test_oracle_vs_reference.py pins both the stream
+    and the oracle's dropout to the reference)."""
+    orc, gpu, keep, cost = make_dropout_pair("mini_lenet", real)
+    n, batch, epochs, seed = 60, 8, 2, 13
+    x, y = H.synthetic_batch(orc, n, real, seed=22, lo=0.0, hi=1.0)
+    gpu.reset_random_generator(seed)
+    gpu.learn(x, y, batch, epochs, 0.05, dl.CostFunctionId.CROSS_ENTROPY, 0.1)
+    masks = dl.dropout_masks(seed, orc.in_sizes, keep, ob.count_batches(n, batch) * epochs, real)
+    orc.learn(x, y, batch, epochs, 0.05, cost, 0.1, 1, dl.shuffle_sequence(seed, n, epochs), masks)
+    H.assert_close("parameters after learn with dropout", gpu.get_params(), orc.get_params(), real, rtol_mult=20)

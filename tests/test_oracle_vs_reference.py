@@ -77,3 +77,47 @@ def test_shuffle_sequence_is_the_reference_permutation():
     """dlb_shuffle_sequence (product, host-only) == the permutations Net::learn draws (same libstdc++ calls)."""
     import deeplearning_b200 as dl
     assert np.array_equal(dl.shuffle_sequence(5, 100, 3), ob.ref_shuffle_sequence(5, 100, 3))
+
+
+DROPOUT_KEEP = [0.8, 1.0, 0.5, 0.9]   # mini-LeNet: masks on the image, the first NLayer's input and the head's input
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_learn_with_dropout(real, threads):
+    """ALayer.inl:25-55 / Net.inl:126,228-230,274-275: per-mini-batch keep masks on the layer inputs and input gradients.
+    The reference draws the masks itself (reset_random_generator(seed) seeds ALayer's generator too); the oracle is fed the
+    same masks, produced by the reference's own Vector::fill_with_random_selection_map from that seed."""
+    specs = gc.MINI_LENET
+    n, batch, epochs, seed = 50, 8, 2, 11
+    ref = ob.RefNet(specs, real, seed=3, keep_rates=DROPOUT_KEEP)
+    orc = ob.OracleNet(specs, real, keep_rates=DROPOUT_KEEP)
+    orc.set_params(ref.get_params())
+    x = ob.ref_uniform_items(real, n, (1, 12, 12))
+    y = ob.one_hot_labels(real, n)
+    ref.learn(x, y, batch, epochs, 0.05, ob.CROSS_ENTROPY, 0.1, parallelism=threads, shuffle_seed=seed)
+    masks = ob.ref_dropout_masks(real, seed, orc.in_sizes, DROPOUT_KEEP, ob.count_batches(n, batch) * epochs)
+    assert masks.shape[1] == orc.mask_size == 144 + 100 + 16
+    assert np.all((masks == 0) | (masks == 1)) and np.all(masks[:, :144].sum(axis=1) == int(np.float32(144) * np.float32(0.8)))
+    orc.learn(x, y, batch, epochs, 0.05, ob.CROSS_ENTROPY, 0.1, threads, ob.ref_shuffle_sequence(seed, n, epochs), masks)
+    H.assert_close("parameters after learn with dropout", orc.get_params(), ref.get_params(), real, rtol_mult=20)
+    # inference scales the inputs of the dropping layers by keep_rate (Net.inl:143)
+    ca, oa = ref.eval(x[:9], True)
+    cb, ob_ = orc.eval(x[:9], True)
+    H.assert_close("inference outputs with keep rates", ob_, oa, real, rtol_mult=5)
+    assert np.array_equal(ca, cb)
+    # and dropout matters: the same run without masks ends elsewhere
+    plain = ob.OracleNet(specs, real)
+    plain.set_params(ob.RefNet(specs, real, seed=3).get_params())
+    plain.learn(x, y, batch, epochs, 0.05, ob.CROSS_ENTROPY, 0.1, threads, ob.ref_shuffle_sequence(seed, n, epochs))
+    assert np.abs(plain.get_params() - orc.get_params()).max() > 1e-3
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_dropout_masks_are_the_reference_masks(real):
+    """dlb_dropout_masks (product, host-only) == the reference's mask stream, bit for bit (same libstdc++ calls)."""
+    import deeplearning_b200 as dl
+    sizes, keep = [144, 400, 100, 16], [0.8, 1.0, 0.5, 0.37]
+    a = dl.dropout_masks(7, sizes, keep, 5, real)
+    b = ob.ref_dropout_masks(real, 7, sizes, keep, 5)
+    assert a.shape == b.shape == (5, 144 + 100 + 16) and np.array_equal(a, b)
