@@ -732,7 +732,13 @@ struct NetT final : dlb_net {
     // One fused forward + backward over `B` samples.  x / refs are the bases the (optional) gather indexes into;
     // `cursor` (device, nullable) is added to gather_base on the device, so that the launch sequence is identical
     // for every batch of an epoch (CUDA-graph friendly).
-    void train_forward_backward(int B, const R* x, const R* refs, const int* gather_base, const int* cursor, int cost) {
+    static const int* resolve_host_gather(const int* gather_base, const int* cursor) {
+        DLB_REQUIRE(cursor == nullptr, "the batch cost of a cursor-addressed batch is not available here");
+        return gather_base;
+    }
+
+    // want_cost: also sum the batch cost into cost_dev - on the head's side stream, off the critical path.
+    void train_forward_backward(int B, const R* x, const R* refs, const int* gather_base, const int* cursor, int cost, bool want_cost = false) {
         const LaunchCtx lc = ctx->lc();
         cudaStream_t st = ctx->stream;
         const int Ln = L();
@@ -815,6 +821,11 @@ struct NetT final : dlb_net {
 #endif
                 DLB_LAUNCH((batch_outer_partial_kernel<R>), dim3((unsigned)ceil_div(total, 128), (unsigned)head_chunks), dim3(128), hs,
                            (const R*)in_grad[(size_t)Ln], (const R*)out[(size_t)h - 1], head_partial, B, (int)Y.out_n, (int)Y.in_n, kHeadChunk);
+                if (want_cost) {   // the batch cost only needs the head's outputs: it rides the same side stream
+                    TagScope tag2_("cost_sum");
+                    DLB_LAUNCH((cost_sum_kernel<R>), dim3(1), dim3(256), hs, (const R*)out[(size_t)h], refs, resolve_host_gather(gather_base, cursor),
+                               B, (int)Y.out_n, cost, cost_dev);
+                }
             }
         }
         // hidden NLayers backward: in_grad[l + 1] holds g_l = dC/dz_l
@@ -1145,9 +1156,9 @@ struct NetT final : dlb_net {
         const bool want_cost = cost_out != nullptr;
         draw_masks();
         auto body = [&] {
-            if (plan.ok) train_forward_backward((int)n, sx, sy, nullptr, nullptr, cost);
+            if (plan.ok) train_forward_backward((int)n, sx, sy, nullptr, nullptr, cost, want_cost);
             else forward_backward((int)n, sx, sy, nullptr, cost, R(0));
-            if (want_cost) {
+            if (want_cost && !plan.ok) {
                 g_tag_layer = L();
                 TagScope tag_("cost_sum");
                 DLB_LAUNCH((cost_sum_kernel<R>), dim3(1), dim3(256), ctx->stream, (const R*)out[(size_t)L() - 1], (const R*)sy,
