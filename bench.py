@@ -350,6 +350,7 @@ def main():
     e0.record()
     for i in range(e2e_steps):   # every step: H2D copy of its batch from pinned memory, the step, D2H copy of its cost
         net.step_host_async(hx[i % n_host], hy[i % n_host], LR, cost_id, reg_factor, costs[i:i + 1])
+    ctx.synchronize()   # every step's cost has landed in host memory (the copies ride their own stream) before the clock stops
     e1.record()
     e2e_ms = max_over_ranks(e0.elapsed_ms(e1))
     barrier()

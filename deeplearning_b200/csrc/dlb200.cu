@@ -141,6 +141,7 @@ struct dlb_context {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     GemmWorkspace ws;
+    std::vector<cudaStream_t> aux_streams;   // streams of this context's nets that carry results back to the host (dlb_context_synchronize waits for them too)
 
     LaunchCtx lc() const { return LaunchCtx{stream, ws}; }
     void ensure_ws(size_t bytes) {
@@ -385,6 +386,13 @@ struct NetT final : dlb_net {
     // Host-buffer steps (dlb_net_step_host*): the next batch is copied on its own stream into the other half of a double
     // buffer while the current step computes.
     cudaStream_t side_copy = nullptr;
+    // ... and the batch cost travels back on its own stream from a per-half device slot, so that the main stream carries
+    // nothing but the step between two steps
+    cudaStream_t side_d2h = nullptr;
+    double* cost_slot[2] = {nullptr, nullptr};
+    cudaEvent_t ev_cost_read[2] = {nullptr, nullptr};
+    bool cost_read_pending[2] = {false, false};
+    double* cur_cost_dev = nullptr;        // where the cost kernel of the step being enqueued writes
     R* hstage_x[2] = {nullptr, nullptr}; R* hstage_y[2] = {nullptr, nullptr};
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     bool hbuf_used[2] = {false, false};
@@ -447,6 +455,9 @@ struct NetT final : dlb_net {
             DLB_CUDA(cudaMalloc(&ws_side.ptr, ws_side.bytes));
         }
         DLB_CUDA(cudaStreamCreateWithFlags(&side_copy, cudaStreamNonBlocking));
+        DLB_CUDA(cudaStreamCreateWithFlags(&side_d2h, cudaStreamNonBlocking));
+        ctx->aux_streams.push_back(side_d2h);
+        for (int i = 0; i < 2; ++i) { cost_slot[i] = dev_alloc<double>(1); DLB_CUDA(cudaEventCreateWithFlags(&ev_cost_read[i], cudaEventDisableTiming)); }
         for (int i = 0; i < 2; ++i) {
             DLB_CUDA(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
             DLB_CUDA(cudaEventCreateWithFlags(&ev_consumed[i], cudaEventDisableTiming));
@@ -493,6 +504,13 @@ struct NetT final : dlb_net {
         for (auto& e : fork_events) cudaEventDestroy(e);
         if (ws_side.ptr) cudaFree(ws_side.ptr);
         if (side_copy) { cudaStreamSynchronize(side_copy); cudaStreamDestroy(side_copy); }
+        if (side_d2h) {
+            cudaStreamSynchronize(side_d2h);
+            auto& aux = ctx->aux_streams;
+            aux.erase(std::remove(aux.begin(), aux.end(), side_d2h), aux.end());
+            cudaStreamDestroy(side_d2h);
+        }
+        for (int i = 0; i < 2; ++i) { if (ev_cost_read[i]) cudaEventDestroy(ev_cost_read[i]); dev_free(cost_slot[i]); }
         for (int i = 0; i < 2; ++i) { if (ev_copied[i]) cudaEventDestroy(ev_copied[i]); if (ev_consumed[i]) cudaEventDestroy(ev_consumed[i]); }
 #endif
         for (int i = 0; i < 2; ++i) { dev_free(hstage_x[i]); dev_free(hstage_y[i]); }
@@ -824,7 +842,7 @@ struct NetT final : dlb_net {
                 if (want_cost) {   // the batch cost only needs the head's outputs: it rides the same side stream
                     TagScope tag2_("cost_sum");
                     DLB_LAUNCH((cost_sum_kernel<R>), dim3(1), dim3(256), hs, (const R*)out[(size_t)h], refs, resolve_host_gather(gather_base, cursor),
-                               B, (int)Y.out_n, cost, cost_dev);
+                               B, (int)Y.out_n, cost, cur_cost_dev ? cur_cost_dev : cost_dev);
                 }
             }
         }
@@ -1146,6 +1164,8 @@ struct NetT final : dlb_net {
 #ifndef DLB_CUDA_EMU
         cs = side_copy;
         if (hbuf_used[buf]) DLB_CUDA(cudaStreamWaitEvent(cs, ev_consumed[buf], 0));   // the step that last read this half is done
+        if (cost_read_pending[buf]) DLB_CUDA(cudaStreamWaitEvent(cs, ev_cost_read[buf], 0));   // ... and its cost has left its slot
+        cur_cost_dev = cost_slot[buf];
 #endif
         DLB_CUDA(cudaMemcpyAsync(sx, x, (size_t)n * (size_t)in0() * sizeof(R), cudaMemcpyHostToDevice, cs));
         DLB_CUDA(cudaMemcpyAsync(sy, y, (size_t)n * (size_t)outN() * sizeof(R), cudaMemcpyHostToDevice, cs));
@@ -1162,7 +1182,7 @@ struct NetT final : dlb_net {
                 g_tag_layer = L();
                 TagScope tag_("cost_sum");
                 DLB_LAUNCH((cost_sum_kernel<R>), dim3(1), dim3(256), ctx->stream, (const R*)out[(size_t)L() - 1], (const R*)sy,
-                           (const int*)nullptr, (int)n, (int)outN(), cost, cost_dev);
+                           (const int*)nullptr, (int)n, (int)outN(), cost, cur_cost_dev ? cur_cost_dev : cost_dev);
             }
             if (world > 1) distributed_finish(plan.ok, lr, reg_factor, n * world, 0);
             else if (plan.ok) train_reduce_update(true, lr, reg_factor, n, 0);
@@ -1173,9 +1193,18 @@ struct NetT final : dlb_net {
 #ifndef DLB_CUDA_EMU
         DLB_CUDA(cudaEventRecord(ev_consumed[buf], ctx->stream));
         hbuf_used[buf] = true;
-#endif
+        if (cost_out) {   // off the main stream: the copy waits for this step, the next user of this half waits for the copy
+            DLB_CUDA(cudaStreamWaitEvent(side_d2h, ev_consumed[buf], 0));
+            DLB_CUDA(cudaMemcpyAsync(cost_out, cur_cost_dev, sizeof(double), cudaMemcpyDeviceToHost, side_d2h));
+            DLB_CUDA(cudaEventRecord(ev_cost_read[buf], side_d2h));
+            cost_read_pending[buf] = true;
+        }
+        cur_cost_dev = nullptr;
+        if (sync) { DLB_CUDA(cudaStreamSynchronize(ctx->stream)); DLB_CUDA(cudaStreamSynchronize(side_d2h)); }
+#else
         if (cost_out) DLB_CUDA(cudaMemcpyAsync(cost_out, cost_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (sync) DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+#endif
     }
 
     void forward_backward_host(const void* x, const void* y, int64_t n, int cost, double scale) override {
@@ -1383,7 +1412,13 @@ int dlb_context_destroy(dlb_context* ctx) {
     });
 }
 
-int dlb_context_synchronize(dlb_context* ctx) { return guarded([&] { DLB_REQUIRE(ctx, "null context"); DLB_CUDA(cudaStreamSynchronize(ctx->stream)); }); }
+int dlb_context_synchronize(dlb_context* ctx) {
+    return guarded([&] {
+        DLB_REQUIRE(ctx, "null context");
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (cudaStream_t s : ctx->aux_streams) DLB_CUDA(cudaStreamSynchronize(s));
+    });
+}
 void* dlb_context_stream(dlb_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t dlb_context_launch_count(dlb_context*) { return (int64_t)g_launch_count.load(); }
 
