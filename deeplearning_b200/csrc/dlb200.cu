@@ -1618,6 +1618,17 @@ int dlb_matmul_f32(dlb_context* ctx, int M, int N, int K, const float* A, int64_
     });
 }
 
+#ifdef DLB_TC_PROFILE
+// Development builds only (-DDLB_TC_PROFILE): reads and clears the phase clocks of tc_gemm_kernel (not part of the ABI).
+extern "C" __attribute__((visibility("default"))) int dlb_debug_tc_profile(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, tc::g_tc_prof, 16 * sizeof(unsigned long long));
+    unsigned long long zero[16] = {};
+    cudaMemcpyToSymbol(tc::g_tc_prof, zero, sizeof(zero));
+    return 0;
+}
+#endif
+
 int dlb_net_enable_graphs(dlb_net* net, int on) { return guarded([&] { DLB_REQUIRE(net, "null net"); net->enable_graphs(on != 0); }); }
 
 int dlb_net_train_steps(dlb_net* net, int64_t batch, int64_t n_steps, double lr, int cost, double lambda, int64_t* items_out) {

@@ -22,7 +22,12 @@
 // (CLayer.inl:108-197) all use the same K-major MMA.
 #pragma once
 
+#include <cstdlib>
 #include <type_traits>
+
+#ifndef DLB_CUDA_EMU
+#include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no link against libcuda)
+#endif
 
 #include "gemm.cuh"
 #include "tc_tiles.cuh"
@@ -106,8 +111,28 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// TMA: one elected thread fetches a whole operand tile (box {32 fp32, rows}) straight into the SWIZZLE_128B layout; the bytes
+// are counted on the slot's mbarrier (expect_tx / complete_tx).
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#ifdef DLB_TC_PROFILE
+// Development builds only (tools/dev_build.sh -DDLB_TC_PROFILE, read by tools/tc_prof.py through dlb_debug_tc_profile):
+// clock64 sums of the producer phases (thread 0) and of the MMA lane's wait, over all CTAs and launches.
+__device__ unsigned long long g_tc_prof[16];
+#define TC_PROF_T(var) const long long var = clock64()
+#define TC_PROF_ADD(slot, t0, t1) do { if (tid == prof_tid) prof_acc[slot] += (t1) - (t0); } while (0)
+#else
+#define TC_PROF_T(var)
+#define TC_PROF_ADD(slot, t0, t1)
+#endif
 
 // Decodes a linear tile index into output-tile coordinates and its slice of the reduction.
 struct TileCoord { int i0, j0, kb, ke, nkb, z; };
@@ -124,6 +149,35 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int tiles_m, int tiles_n
     return c;
 }
 
+// Host side of the TMA plan.  cuTensorMapEncodeTiled comes from the driver through the runtime (no libcuda link);
+// DLB_TC_TMA=0 in the environment keeps every contraction on the cp.async producers (A/B measurements).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q{};
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+inline bool tma_enabled() {
+    static const bool on = [] { const char* e = std::getenv("DLB_TC_TMA"); return !(e && e[0] == '0') && encode_tiled() != nullptr; }();
+    return on;
+}
+// value(outer, red) = base[outer * ld + red] as a 2-D tensor {red, outer}; false when the operand does not qualify.
+inline bool make_row_map(CUtensorMap& map, const TcOperand& op, int rows, int K, int box_rows) {
+    if (op.gather_base || (op.ld & 3) || (reinterpret_cast<uintptr_t>(op.base) & 15) || K <= 0 || rows <= 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)op.ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode_tiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(op.base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Persistent kernel: CTA c processes tiles c, c + gridDim.x, ...  Three roles run concurrently on different tiles:
 // producers fill the operand ring for tile j+1 while the MMA lane accumulates tile j+1 into one tensor-memory
 // accumulator and the epilogue warps drain tile j from the other one.
@@ -133,7 +187,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int tiles_m, int tiles_n
 template <class EP, int KA, int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, int n_tiles, int n_splits, int mma_n, TcOperand a, TcOperand b, EP ep,
-               float* __restrict__ partials) {
+               float* __restrict__ partials, int use_tma, const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b) {
     extern __shared__ unsigned char tc_smem_raw[];
     // 1024-byte alignment (SWIZZLE_128B atoms) by an OFFSET into the shared array, not by an integer round trip of the pointer:
     // the compiler then still knows these are shared-memory addresses and emits LDS / STS instead of generic LD / ST
@@ -145,7 +199,9 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
     // bars: full[kSlots] | empty[kSlots] | tmem_full[2] | tmem_empty[2]
     uint64_t* bar_full = bars; uint64_t* bar_empty = bars + kSlots;
     uint64_t* bar_tfull = bars + 2 * kSlots; uint64_t* bar_tempty = bars + 2 * kSlots + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 4);
+    uint64_t* bar_landed = bars + 2 * kSlots + 4;           // [kSlots] TMA plan: the slot's tiles have landed (1 arrival + transaction bytes)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_landed + kSlots);
+    static_assert((3 * kSlots + 4) * 8 + 8 <= 256, "barrier block");
     constexpr bool kDirect = KMajor<KA>::value && KMajor<KB>::value;     // the K-major plan
     constexpr int kRing = kDirect ? kSlots : kStages;         // operand stages the MMA lane cycles through
 
@@ -154,6 +210,7 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
     if (tid == 0) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(smem_u32(&bar_full[s]), kProducers); mbar_init(smem_u32(&bar_empty[s]), 1); }
         for (int q = 0; q < 2; ++q) { mbar_init(smem_u32(&bar_tfull[q]), 1); mbar_init(smem_u32(&bar_tempty[q]), 4); }
+        for (int s = 0; s < kSlots; ++s) mbar_init(smem_u32(&bar_landed[s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {   // the MMA warp owns the tensor-memory allocation: two accumulators of kBN fp32 columns x 128 lanes
@@ -165,8 +222,61 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
+#ifdef DLB_TC_PROFILE
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int prof_tid = warp < kProducerWarps ? 0 : kMmaWarp * 32;
+#endif
     if (warp < kProducerWarps) {
         // ---------------- producers: one continuous stream of k-blocks over all of this CTA's tiles ----------------
+        bool tma_done = false;
+        if constexpr (KA == kRedContig && KB == kRedContig) {
+            if (use_tma) {
+                // ---- TMA plan (dense, ungathered, 16-byte aligned operands): thread 0 asks the TMA unit for whole tiles, two
+                // k-blocks ahead; nobody issues per-chunk copies (the phase clocks showed 1 200 cycles per k-block inside that
+                // issue - per-warp LDGSTS back-pressure), all 256 threads only compute lo.
+                const uint32_t tile_bytes = (uint32_t)kTileBytes + (uint32_t)mma_n * 128u;
+                int it_tile = blockIdx.x, it_k = 0;
+                TileCoord ic{};
+                if (it_tile < n_tiles) ic = decode_tile(it_tile, tiles_m, tiles_n, K, k_per_split);
+                long long sent = 0;
+                auto send_next = [&]() {
+                    if (it_tile >= n_tiles) return;
+                    const int s = (int)(sent % kSlots);
+                    mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(((sent / kSlots) & 1) ^ 1));   // the MMAs of this slot's previous use are done
+                    const uint32_t bar = smem_u32(&bar_landed[s]);
+                    const uint32_t dst = smem_u32(smem + s * kStageBytes);
+                    const int r0 = ic.kb + it_k * kBK;
+                    mbar_expect_tx(bar, tile_bytes);
+                    tma_load_2d(dst, &tma_a, r0, ic.i0, bar);
+                    tma_load_2d(dst + 2 * kTileBytes, &tma_b, r0, ic.j0, bar);
+                    ++sent;
+                    if (++it_k == ic.nkb) { it_k = 0; it_tile += gridDim.x; if (it_tile < n_tiles) ic = decode_tile(it_tile, tiles_m, tiles_n, K, k_per_split); }
+                };
+                if (tid == 0) { send_next(); send_next(); }
+                long long git = 0;
+                for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                    const TileCoord c = decode_tile(t, tiles_m, tiles_n, K, k_per_split);
+                    for (int it = 0; it < c.nkb; ++it, ++git) {
+                        const int s = (int)(git % kSlots);
+                        unsigned char* st = smem + s * kStageBytes;
+                        TC_PROF_T(p0);
+                        mbar_wait(smem_u32(&bar_landed[s]), (uint32_t)((git / kSlots) & 1));
+                        TC_PROF_T(p1);
+                        lo_tile<KA>(tid, kBM, st, st + kTileBytes);
+                        lo_tile<KB>(tid, mma_n, st + 2 * kTileBytes, st + 3 * kTileBytes);
+                        TC_PROF_T(p2);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // lo stores -> async-proxy (UMMA) reads
+                        mbar_arrive(smem_u32(&bar_full[s]));
+                        TC_PROF_T(p3);
+                        if (tid == 0) send_next();                      // k-block git + 2
+                        TC_PROF_T(p4);
+                        TC_PROF_ADD(0, p0, p1); TC_PROF_ADD(4, p1, p2); TC_PROF_ADD(5, p2, p3); TC_PROF_ADD(2, p3, p4); TC_PROF_ADD(6, 0, 1);
+                    }
+                }
+                tma_done = true;
+            }
+        }
+        if (!tma_done) {
         int nt_tile = blockIdx.x;            // tile of the next k-block to issue
         int nt_k = 0;
         TileCoord nc{};
@@ -207,29 +317,47 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
                 const int s = (int)(git % kRing);
                 unsigned char* st = smem + s * kStageBytes;
                 if constexpr (kDirect) {
+                    TC_PROF_T(p0);
                     cp_async_wait<1>();                             // this thread's copies of the current k-block have landed (the next one may be in flight)
+                    TC_PROF_T(p1);
                     asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");   // ... and every other producer's
+                    TC_PROF_T(p2);
                     lo_tile<KA>(tid, kBM, st, st + kTileBytes);
                     lo_tile<KB>(tid, mma_n, st + 2 * kTileBytes, st + 3 * kTileBytes);
+                    TC_PROF_T(p3);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // landed copies and lo stores -> async-proxy (UMMA) reads
                     mbar_arrive(smem_u32(&bar_full[s]));
+                    TC_PROF_T(p4);
                     issue_next();                                   // k-block git + 2 into the slot the MMAs of k-block git - 1 are leaving
+                    TC_PROF_T(p5);
+                    TC_PROF_ADD(0, p0, p1); TC_PROF_ADD(1, p1, p2); TC_PROF_ADD(4, p2, p3); TC_PROF_ADD(5, p3, p4); TC_PROF_ADD(2, p4, p5);
+                    TC_PROF_ADD(6, 0, 1);
                 } else {
+                    TC_PROF_T(p0);
                     cp_async_wait<0>();                             // this thread's copies of the current k-block have landed
+                    TC_PROF_T(p1);
                     // every producer's copies have landed, and every producer is done reading the raw block refilled next
                     asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");
+                    TC_PROF_T(p2);
                     issue_next();
+                    TC_PROF_T(p3);
                     mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(((git / kStages) & 1) ^ 1));   // hi/lo stage free (first pass: returns at once)
+                    TC_PROF_T(p4);
                     const unsigned char* raw = raw_ring + (int)(git % kRaw) * kRawBytes;
                     const int r0 = c.kb + it * kBK;
                     transform_tile<KA>(a, c.i0, M, r0, c.ke, tid, kBM, raw, st, st + kTileBytes);
                     transform_tile<KB>(b, c.j0, N, r0, c.ke, tid, mma_n, raw + kTileBytes, st + 2 * kTileBytes, st + 3 * kTileBytes);
+                    TC_PROF_T(p5);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (UMMA) reads
                     mbar_arrive(smem_u32(&bar_full[s]));
+                    TC_PROF_T(p6);
+                    TC_PROF_ADD(0, p0, p1); TC_PROF_ADD(1, p1, p2); TC_PROF_ADD(2, p2, p3); TC_PROF_ADD(3, p3, p4); TC_PROF_ADD(4, p4, p5);
+                    TC_PROF_ADD(5, p5, p6); TC_PROF_ADD(6, 0, 1);
                 }
             }
         }
         cp_async_wait<0>();
+        }   // !tma_done
     } else if (warp == kMmaWarp) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
@@ -246,7 +374,10 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
                 for (int it = 0; it < c.nkb; ++it, ++git) {
                     const int s = (int)(git % kRing);
                     const uint32_t phase = (uint32_t)((git / kRing) & 1);
+                    TC_PROF_T(q0);
                     mbar_wait(smem_u32(&bar_full[s]), phase);
+                    TC_PROF_T(q1);
+                    TC_PROF_ADD(0, q0, q1); TC_PROF_ADD(1, 0, 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = smem_u32(smem + s * kStageBytes);
                     const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + kTileBytes);
@@ -339,6 +470,10 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
             }
         }
     }
+#ifdef DLB_TC_PROFILE
+    if (tid == 0) for (int i = 0; i < 7; ++i) atomicAdd(&g_tc_prof[i], (unsigned long long)prof_acc[i]);
+    if (tid == kMmaWarp * 32) for (int i = 0; i < 2; ++i) atomicAdd(&g_tc_prof[8 + i], (unsigned long long)prof_acc[i]);
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == kMmaWarp) {
@@ -374,10 +509,16 @@ void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcO
     const int tiles_m = ceil_div(M, tc::kBM), tiles_n = ceil_div(N, tc::kBN);
     const int n_tiles = tiles_m * tiles_n * splits;
     const int mma_n = tiles_n == 1 ? std::min(tc::kBN, ceil_div(N, 16) * 16) : tc::kBN;
+    // TMA for dense, ungathered, 16-byte aligned row operands (the NLayer forward): box {32 fp32, rows}, SWIZZLE_128B, zero fill
+    CUtensorMap map_a{}, map_b{};
+    int use_tma = 0;
+    if constexpr (KA == kRedContig && KB == kRedContig) {
+        use_tma = tc::tma_enabled() && tc::make_row_map(map_a, a, M, K, tc::kBM) && tc::make_row_map(map_b, b, N, K, mma_n);
+    }
     const dim3 grid((unsigned)std::min(n_tiles, kNumSMs));
     float* partials = static_cast<float*>(ws.ptr);
     DLB_LAUNCH_SMEM((tc::tc_gemm_kernel<EP, KA, KB>), grid, dim3(tc::kThreads), (size_t)tc::kSmemBytes, st, M, N, K, k_per_split, tiles_m, tiles_n,
-                    n_tiles, splits, mma_n, a, b, ep, partials);
+                    n_tiles, splits, mma_n, a, b, ep, partials, use_tma, map_a, map_b);
     if (splits > 1) {
         const size_t total = (size_t)M * N;
         DLB_LAUNCH((gemm_finalize_kernel<float, EP>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), st,

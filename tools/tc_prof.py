@@ -1,4 +1,5 @@
-"""Development only: phase clocks of tc_gemm_kernel (library built with -DDLB_TC_PROFILE) for the LeNet B=8192 step."""
+"""Development only: phase clocks of tc_gemm_kernel for the LeNet step; needs a library built with tools/dev_build.sh -DDLB_TC_PROFILE
+(the release build has no such hooks and no dlb_debug_tc_profile symbol)."""
 import ctypes, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,7 +12,7 @@ net = dl.lenet('f32'); net.init_params(0)
 x, y = bench.synthetic_data(32768, 784, 10, np.float32)
 net.set_dataset(x, y); net.reset_random_generator(0); net.enable_graphs(False)
 out = (ctypes.c_ulonglong * 16)()
-names = ["ld_wait_rawempty", "xf_wait_rawfull", "ld_issue", "xf_wait_empty", "transform", "fence+arrive", "kblocks", "-", "mma_wait_full", "mma_kblocks"]
+names = ["wait_copy", "barrier", "issue", "wait_empty", "transform", "fence+arrive", "kblocks", "-", "mma_wait_full", "mma_kblocks"]
 net.train_steps(B, 2, 0.01, dl.CostFunctionId.CROSS_ENTROPY, 0.1)
 lib.dlb_debug_tc_profile(out)
 net.train_steps(B, 4, 0.01, dl.CostFunctionId.CROSS_ENTROPY, 0.1)
