@@ -157,10 +157,11 @@ DLB_API int dlb_net_describe_plan(dlb_net* net, char* buf, int64_t cap);
 /* CUDA-graph replay of the step on the resident-data path (on by default); off = every step launches its kernels. */
 DLB_API int dlb_net_enable_graphs(dlb_net* net, int on);
 
-/* fp32 NLayer contractions of the fused path: mode 1 (default) = tcgen05 tensor cores with 3xTF32 operand splitting for
- * mini-batches that fill at least one 128-row tensor-core tile (128 samples per GPU) and the packed-FMA (FFMA2) kernels
- * below that; 0 = packed-FMA always; 2 = tcgen05 always.  Real = double always uses the
- * FMA path (tcgen05 has no fp64 kind). */
+/* fp32 contractions - the NLayer forward / weight-gradient / input-gradient products and, in the layer-by-layer path, the
+ * convolutions of multi-channel CLayers as implicit GEMM (forward, filter gradient, input gradient of stride-1 layers):
+ * mode 1 (default) = tcgen05 tensor cores with 3xTF32 operand splitting for mini-batches that fill at least one 128-row
+ * tensor-core tile (128 samples per GPU) and the packed-FMA (FFMA2) kernels below that; 0 = packed-FMA always; 2 = tcgen05
+ * always.  Real = double always uses the FMA path (tcgen05 has no fp64 kind). */
 DLB_API int dlb_net_enable_tensor_cores(dlb_net* net, int mode);
 
 /* Dense fp32 contraction C[M][N] = sum_k A(m,k) * B(n,k) (replaces CudaMatrix::mul_add / transpose_mul /
