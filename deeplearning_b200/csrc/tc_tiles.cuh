@@ -360,21 +360,15 @@ DLB_HD void split_store(Quad v, unsigned char* hi_tile, unsigned char* lo_tile, 
 template <int KIND>
 DLB_HD void lo_tile(int t, int rows, const unsigned char* raw_tile, unsigned char* lo_tile_) {
     static_assert(KIND != kOuterContig, "transposed operands go through transform_tile");
-    // all loads first, then the stores: the compiler cannot prove that the two tiles do not alias and would otherwise
-    // serialise load -> store -> load (ncu source page: every LOP3 of the split waiting on its own LDS)
-    Quad v[kOwned];
-#pragma unroll
-    for (int i = 0; i < kOwned; ++i) {
-        const int q = t + kProducers * i;
-        if ((q >> 3) < rows) v[i] = tile_load16(raw_tile + chunk_off(q >> 3, q & 7));
-    }
 #pragma unroll
     for (int i = 0; i < kOwned; ++i) {
         const int q = t + kProducers * i;
         if ((q >> 3) >= rows) continue;
+        const int off = chunk_off(q >> 3, q & 7);
+        const Quad v = tile_load16(raw_tile + off);
         Quad l;
-        l.x = v[i].x - tf32_hi(v[i].x); l.y = v[i].y - tf32_hi(v[i].y); l.z = v[i].z - tf32_hi(v[i].z); l.w = v[i].w - tf32_hi(v[i].w);
-        tile_store16(lo_tile_ + chunk_off(q >> 3, q & 7), l);
+        l.x = v.x - tf32_hi(v.x); l.y = v.y - tf32_hi(v.y); l.z = v.z - tf32_hi(v.z); l.w = v.w - tf32_hi(v.w);
+        tile_store16(lo_tile_ + off, l);
     }
 }
 
@@ -382,17 +376,12 @@ template <int KIND>
 DLB_HD void transform_tile(const TcOperand& op, int o0, int o_end, int r0, int r_end, int t, int rows,
                            const unsigned char* raw_tile, unsigned char* hi_tile, unsigned char* lo_tile) {
     if constexpr (KIND != kOuterContig) {
-        Quad v[kOwned];   // loads first, then stores (see lo_tile)
-#pragma unroll
-        for (int i = 0; i < kOwned; ++i) {
-            const int q = t + kProducers * i;
-            if ((q >> 3) < rows) v[i] = tile_load16(raw_tile + chunk_off(q >> 3, q & 7));
-        }
 #pragma unroll
         for (int i = 0; i < kOwned; ++i) {
             const int q = t + kProducers * i;
             if ((q >> 3) >= rows) continue;
-            split_store(v[i], hi_tile, lo_tile, chunk_off(q >> 3, q & 7));
+            const int off = chunk_off(q >> 3, q & 7);
+            split_store(tile_load16(raw_tile + off), hi_tile, lo_tile, off);
         }
     } else {
         // thread t produces half of tile row t & 127 (outer index o0 + (t & 127)): a column of the raw [k][o] block
@@ -400,21 +389,19 @@ DLB_HD void transform_tile(const TcOperand& op, int o0, int o_end, int r0, int r
         const int tt = t & 127, c0 = (t >> 7) * (8 * 128 / kProducers);
         if (tt >= rows) return;
         const bool ones = (o0 + tt < o_end) && (o0 + tt == op.ones_col);
-        constexpr int kCols = 8 * 128 / kProducers;
-        Quad v[kCols];    // loads first, then stores (see lo_tile)
 #pragma unroll
-        for (int cc = 0; cc < kCols; ++cc) {
+        for (int cc = 0; cc < 8 * 128 / kProducers; ++cc) {
             const int c = c0 + cc;
+            Quad v;
             if (ones) {
-                v[cc].x = r0 + 4 * c < r_end ? 1.f : 0.f; v[cc].y = r0 + 4 * c + 1 < r_end ? 1.f : 0.f;
-                v[cc].z = r0 + 4 * c + 2 < r_end ? 1.f : 0.f; v[cc].w = r0 + 4 * c + 3 < r_end ? 1.f : 0.f;
+                v.x = r0 + 4 * c < r_end ? 1.f : 0.f; v.y = r0 + 4 * c + 1 < r_end ? 1.f : 0.f;
+                v.z = r0 + 4 * c + 2 < r_end ? 1.f : 0.f; v.w = r0 + 4 * c + 3 < r_end ? 1.f : 0.f;
             } else {
-                v[cc].x = tile_load4(raw_tile + ((4 * c) * 128 + tt) * 4); v[cc].y = tile_load4(raw_tile + ((4 * c + 1) * 128 + tt) * 4);
-                v[cc].z = tile_load4(raw_tile + ((4 * c + 2) * 128 + tt) * 4); v[cc].w = tile_load4(raw_tile + ((4 * c + 3) * 128 + tt) * 4);
+                v.x = tile_load4(raw_tile + ((4 * c) * 128 + tt) * 4); v.y = tile_load4(raw_tile + ((4 * c + 1) * 128 + tt) * 4);
+                v.z = tile_load4(raw_tile + ((4 * c + 2) * 128 + tt) * 4); v.w = tile_load4(raw_tile + ((4 * c + 3) * 128 + tt) * 4);
             }
+            split_store(v, hi_tile, lo_tile, chunk_off(tt, c));
         }
-#pragma unroll
-        for (int cc = 0; cc < kCols; ++cc) split_store(v[cc], hi_tile, lo_tile, chunk_off(tt, c0 + cc));
     }
 }
 
