@@ -342,3 +342,24 @@ def test_learn_with_dropout_matches_oracle(real):
     masks = dl.dropout_masks(seed, orc.in_sizes, keep, ob.count_batches(n, batch) * epochs, real)
     orc.learn(x, y, batch, epochs, 0.05, cost, 0.1, 1, dl.shuffle_sequence(seed, n, epochs), masks)
     H.assert_close("parameters after learn with dropout", gpu.get_params(), orc.get_params(), real, rtol_mult=20)
+
+
+# Geometries on the edge of what the tensor-core convolutions accept (tc_conv_ok, layers.cuh): a strided CLayer behind another
+# layer (its input gradient stays on the FMA contraction, forward and filter gradient go to tcgen05), a 16-tap window (beyond
+# the 15-bit tap masks: the whole layer stays on the FMA path), a 15-tap window with heavy padding (the largest masks).
+EDGE_NETS = {
+    "strided_inner": [ob.conv((1, 11, 10), (3, 3), 3, ob.TANH, pad=(1, 1)), ob.conv((3, 11, 10), (3, 2), 4, ob.SIGMOID, pad=(1, 0), stride=(2, 2)),
+                      ob.full((4, 6, 5), 5, ob.LINEAR)],
+    "window_16": [ob.conv((2, 18, 4), (16, 1), 3, ob.TANH, pad=(2, 0)), ob.conv((3, 7, 4), (2, 2), 2, ob.RELU), ob.full((2, 6, 3), 4, ob.LINEAR)],
+    "window_15": [ob.conv((2, 9, 17), (3, 15), 3, ob.TANH, pad=(1, 7)), ob.conv((3, 9, 17), (15, 3), 2, ob.TANH, pad=(7, 1)),
+                  ob.full((2, 9, 17), 4, ob.LINEAR)],
+}
+
+
+@pytest.mark.parametrize("name", list(EDGE_NETS))
+@pytest.mark.parametrize("batch", [2, 9])
+def test_tensor_core_convolution_edge_geometries(name, batch):
+    specs = EDGE_NETS[name]
+    orc, gpu = H.make_pair(specs, "f32", seed=31, tc_mode=2)
+    x, y = H.synthetic_batch(orc, batch, "f32", seed=32, one_hot=False)
+    compare_traces(orc, gpu, x, y, ob.SQUARED_ERROR, "f32")
