@@ -201,17 +201,18 @@ __global__ void gemm_finalize_kernel(const R* __restrict__ partials, int splits,
     const size_t total = (size_t)M * N;
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
-    // fixed association (four interleaved running sums, then a fixed combine): deterministic, four loads in flight
-    R s0 = R(0), s1 = R(0), s2 = R(0), s3 = R(0);
-    int z = 0;
-    for (; z + 3 < splits; z += 4) {
-        s0 += partials[(size_t)z * total + e];
-        s1 += partials[(size_t)(z + 1) * total + e];
-        s2 += partials[(size_t)(z + 2) * total + e];
-        s3 += partials[(size_t)(z + 3) * total + e];
+    // fixed association (eight interleaved running sums, then a fixed combine): deterministic, eight loads in flight - each
+    // load is a separate L2 round trip (the partials of one element lie M * N elements apart), and at mini-batch 256 this
+    // kernel sits on the step's critical path
+    R s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = R(0);
+    for (int z = 0; z < splits; z += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (z + j < splits) s[j] += partials[(size_t)(z + j) * total + e];
     }
-    for (; z < splits; ++z) s0 += partials[(size_t)z * total + e];
-    ep((int)(e / N), (int)(e % N), (s0 + s1) + (s2 + s3));
+    ep((int)(e / N), (int)(e % N), ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
 }
 
 struct GemmWorkspace {

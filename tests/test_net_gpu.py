@@ -363,3 +363,28 @@ def test_tensor_core_convolution_edge_geometries(name, batch):
     orc, gpu = H.make_pair(specs, "f32", seed=31, tc_mode=2)
     x, y = H.synthetic_batch(orc, batch, "f32", seed=32, one_hot=False)
     compare_traces(orc, gpu, x, y, ob.SQUARED_ERROR, "f32")
+
+
+def test_cifar_deep_full_size_steps_tensor_cores_vs_fma_and_determinism():
+    """BASELINE configs[2] at its full mini-batch (1024): two regularised training steps with the contractions on tcgen05 and
+    on the FMA path end at the same parameters within the float bar (the FMA path is pinned to the oracle at small sizes),
+    the predicted classes of a sample agree, and a repeated run from the same state is bit-identical (every reduction is
+    ordered)."""
+    rng = np.random.default_rng(5)
+    n = 2048
+    x = rng.uniform(0, 1, (n, 3 * 32 * 32)).astype(np.float32)
+    y = np.zeros((n, 10), np.float32); y[np.arange(n), rng.integers(0, 10, n)] = 1
+    results = []
+    for tc_mode in (0, 1, 1):
+        net = dl.cifar_deep("f32")
+        net.init_params(seed=3)
+        net.enable_tensor_cores(tc_mode)
+        net.set_dataset(x, y)
+        net.reset_random_generator(9)
+        net.train_steps(1024, 2, 0.01, dl.CostFunctionId.CROSS_ENTROPY, 0.1)
+        results.append((net.get_params(), net.predict(x[:256])))
+        net.close()
+    (p_fma, c_fma), (p_tc, c_tc), (p_tc2, c_tc2) = results
+    assert np.array_equal(p_tc, p_tc2) and np.array_equal(c_tc, c_tc2), "the tensor-core path is not deterministic"
+    H.assert_close("parameters after two full-size steps", p_tc, p_fma, "f32", rtol_mult=20)
+    assert np.mean(c_tc != c_fma) <= 0.01
