@@ -94,6 +94,18 @@ __device__ __forceinline__ f32x2 ffma2_bcast(f32x2 a, float w, f32x2 c) {
 #endif
 struct alignas(16) f32x2_quad { f32x2 a, b; };   // two pairs = one 16-byte shared-memory load
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start while
+// its predecessor in the stream is still running; it must not touch the predecessor's results before pdl_wait().  A
+// predecessor calls pdl_trigger() as soon as the successor's prologue may begin (here: at once - the successor's CTAs only
+// get an SM when this grid's CTAs leave it).  Both are no-ops in launches without the attribute.
+#ifndef DLB_CUDA_EMU
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+#endif
+
 template <class T> __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
 constexpr int kNumSMs = 148;  // B200

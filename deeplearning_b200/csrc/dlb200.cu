@@ -405,6 +405,7 @@ struct NetT final : dlb_net {
     bool p2p_on = false;
     R* publish_buf(int parity) { return reinterpret_cast<R*>(p2p_region + (size_t)parity * p2p_publish_bytes); }
     bool overlap_enabled = true;
+    bool pdl_enabled = [] { const char* e = std::getenv("DLB_PDL"); return !(e && e[0] == '0'); }();   // programmatic dependent launches (DLB_PDL=0: off, for A/B runs)
     const void* ws_stamp = nullptr;   // the context scratch the captured graphs point into
     bool graphs_enabled = true;
     // fp32 NLayer contractions: 0 = packed-FMA path (gemm.cuh), 1 = tcgen05 3xTF32 (tc_gemm.cuh) for mini-batches that fill
@@ -786,7 +787,9 @@ struct NetT final : dlb_net {
                 if (tc_for(B)) {   // y = act(X W^T + b): both operands reduction-contiguous
                     const TcOperand A{l == 0 ? x : out[(size_t)l - 1], (long long)Y.in_n, 0, l == 0 ? gather_base : nullptr, l == 0 ? cursor : nullptr, -1};
                     const TcOperand Bo{bias + Y.bias_n, (long long)Y.in_n, 0, nullptr, nullptr, -1};
-                    tc_gemm<kRedContig, kRedContig>(st, B, (int)Y.out_n, (int)Y.in_n, A, Bo, EpiFullForward<float>{out[(size_t)l], nullptr, bias, (int)Y.out_n, Y.s.activation}, lc.ws);
+                    // behind the fused conv + pool kernel (which triggers early) the contraction is launched programmatically
+                    tc_gemm<kRedContig, kRedContig>(st, B, (int)Y.out_n, (int)Y.in_n, A, Bo, EpiFullForward<float>{out[(size_t)l], nullptr, bias, (int)Y.out_n, Y.s.activation}, lc.ws,
+                                                    /*pdl*/ plan.has_cp && l == 2 && pdl_enabled);
                     continue;
                 }
             }
@@ -878,7 +881,8 @@ struct NetT final : dlb_net {
                         const TcOperand A{gl, (long long)Y.out_n, 0, nullptr, nullptr, -1};
                         const TcOperand Bo{params + Y.param_off + Y.bias_n, (long long)Y.in_n, 1, nullptr, nullptr, -1};
                         tc_gemm<kRedContig, kOuterContig>(st, B, (int)Y.in_n, (int)Y.out_n, A, Bo,
-                                EpiStoreTimesDeriv<float>{in_grad[(size_t)l], (size_t)Y.in_n, out[(size_t)l - 1], prev_act}, lc.ws);
+                                EpiStoreTimesDeriv<float>{in_grad[(size_t)l], (size_t)Y.in_n, out[(size_t)l - 1], prev_act}, lc.ws,
+                                /*pdl: the head kernel is the previous kernel on this stream and triggers early*/ l == Ln - 2 && pdl_enabled);
                     }
                     done_tc = true;
                 }

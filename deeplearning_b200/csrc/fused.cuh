@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(kX2Threads, sizeof(R) == 4 ? 2 : 1) conv_pool_
     using P = PairOf<R>;
     using pair_t = typename P::type;
     DLB_DYNAMIC_SMEM(R, smem);
+    pdl_trigger();   // the NLayer contraction that follows may set itself up (barriers, tensor memory) while this grid runs
     const int Fp = nfg * 4;
     const int img_stride = g.C * g.Hp * RS * 2;   // floats per image buffer (a multiple of 4: RS is even)
     R* filt_s = smem;                 // [K][Fp], zero padded filters
@@ -728,6 +729,7 @@ __global__ void full_head_kernel(const R* __restrict__ x, const R* __restrict__ 
                                  const int* __restrict__ gather_base, const int* __restrict__ cursor, R* __restrict__ out,
                                  R* __restrict__ g_out, R* __restrict__ dx, int B, int in_n, int n, int act, int cost_id, int prev_act) {
     DLB_DYNAMIC_SMEM(R, W_s);
+    pdl_trigger();   // the input-gradient contraction that follows may set itself up while this grid runs
     const int* gather = resolve_gather(gather_base, cursor);
     const int lane = threadIdx.x % 32, wpb = blockDim.x / 32;
     // the first sample's operands are requested before the weights are staged: their latencies overlap

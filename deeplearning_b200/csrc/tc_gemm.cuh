@@ -221,6 +221,7 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above ran beside the previous kernel of the stream (if launched programmatically); its results are visible from here
 
 #ifdef DLB_TC_PROFILE
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -487,7 +488,7 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
 // Host launcher, instantiated per pair of operand kinds (the kernel carries only the producers it needs).  Falls back to
 // nothing: callers decide (by Real type and shape) whether to use this or gemm<R>.
 template <int KA, int KB, class EP>
-void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcOperand& b, EP ep, const GemmWorkspace& ws) {
+void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcOperand& b, EP ep, const GemmWorkspace& ws, bool pdl = false) {
     if (M <= 0 || N <= 0) return;
     if (a.kind != KA || b.kind != KB) throw std::logic_error("tc_gemm: operand kind does not match the instantiation");
     if (a.ld >= (1LL << 31) || b.ld >= (1LL << 31)) throw std::invalid_argument("tc_gemm: leading dimension exceeds the 32-bit range");
@@ -517,8 +518,21 @@ void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcO
     }
     const dim3 grid((unsigned)std::min(n_tiles, kNumSMs));
     float* partials = static_cast<float*>(ws.ptr);
-    DLB_LAUNCH_SMEM((tc::tc_gemm_kernel<EP, KA, KB>), grid, dim3(tc::kThreads), (size_t)tc::kSmemBytes, st, M, N, K, k_per_split, tiles_m, tiles_n,
-                    n_tiles, splits, mma_n, a, b, ep, partials, use_tma, map_a, map_b);
+    if (pdl && !g_timing_on) {   // programmatic dependent launch: the prologue overlaps the previous kernel of the stream (common.cuh)
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        auto kernel = tc::tc_gemm_kernel<EP, KA, KB>;
+        allow_big_smem((const void*)kernel, (size_t)tc::kSmemBytes);
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(tc::kThreads); cfg.dynamicSmemBytes = (size_t)tc::kSmemBytes; cfg.stream = st;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        DLB_CUDA(cudaLaunchKernelEx(&cfg, kernel, M, N, K, k_per_split, tiles_m, tiles_n, n_tiles, splits, mma_n, a, b, ep, partials, use_tma, map_a, map_b));
+    } else {
+        DLB_LAUNCH_SMEM((tc::tc_gemm_kernel<EP, KA, KB>), grid, dim3(tc::kThreads), (size_t)tc::kSmemBytes, st, M, N, K, k_per_split, tiles_m, tiles_n,
+                        n_tiles, splits, mma_n, a, b, ep, partials, use_tma, map_a, map_b);
+    }
     if (splits > 1) {
         const size_t total = (size_t)M * N;
         DLB_LAUNCH((gemm_finalize_kernel<float, EP>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), st,
