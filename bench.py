@@ -316,6 +316,54 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = dl.Event(ctx), dl.Event(ctx)
 
+    # ---------------- data-parallel parity (N > 1), before anything is timed --------------------------------------------
+    # The first PARITY_STEPS global mini-batches through the sharded path must leave bit-identical parameters on every
+    # rank, equal (within the float bar of tests/helpers.py times 20, as tests/test_distributed_gpu.py) to the same steps
+    # replayed by rank 0 alone on one GPU.  Only a few steps are replayed: float SGD trajectories with different summation
+    # orders drift apart chaotically over thousands of steps.  After the timed regions the ranks are compared again, bit
+    # for bit, over the whole history.
+    dp_parity = None
+    scaling_base = None
+    PARITY_STEPS = 8
+
+    def ranks_identical() -> bool:
+        import hashlib
+        digest = hashlib.sha256(net.get_params().tobytes()).hexdigest()
+        all_d = [None] * world
+        dist.all_gather_object(all_d, digest)
+        return all(d == all_d[0] for d in all_d)
+
+    if world > 1:
+        from tests import helpers as H
+        p_init = net.get_params()
+        net.train_steps(batch, PARITY_STEPS, LR, cost_id, LAMBDA)
+        same = ranks_identical()
+        dp_params = net.get_params()
+        if rank == 0:
+            solo_ctx = dl.Context(device=local_rank)   # its own stream and scratch
+            solo = dl.lenet(real=args.real, context=solo_ctx)
+            solo.set_params(p_init)
+            if args.real == "f32" and args.tc != 1:
+                solo.enable_tensor_cores(args.tc)
+            solo.set_dataset(x, y)
+            solo.reset_random_generator(0)
+            solo.train_steps(batch, PARITY_STEPS, LR, cost_id, LAMBDA)
+            want = solo.get_params()
+            H.assert_close("data-parallel parameters vs the single-GPU replay of the same global batches", dp_params, want, args.real, rtol_mult=20)
+            scale = float(np.max(np.abs(want)))
+            dp_parity = {"ranks_identical": bool(same), "replayed_steps": PARITY_STEPS,
+                         "max_rel_err": float(np.max(np.abs(dp_params.astype(np.float64) - want) / (np.abs(want) + scale))),
+                         "tolerance": H.RTOL[args.real] * 20, "update_norm": float(np.linalg.norm(want.astype(np.float64) - p_init))}
+            # the same workload on ONE GPU (the base the scaling series is read against)
+            solo.train_steps(batch, 3, LR, cost_id, LAMBDA)
+            solo_ctx.synchronize()
+            s0, s1 = dl.Event(solo_ctx), dl.Event(solo_ctx)
+            s0.record(); it = solo.train_steps(batch, 16, LR, cost_id, LAMBDA); s1.record()
+            scaling_base = {"value": it / (s0.elapsed_ms(s1) / 1e3), "unit": "samples/s", "what": f"global mini-batch {batch} on 1 GPU of this box, resident data"}
+            solo.close()
+        assert same, "data-parallel ranks ended the parity steps with different parameters"
+        barrier()
+
     # resident-data throughput
     net.train_steps(batch, warmup, LR, cost_id, LAMBDA)
     barrier()
@@ -414,6 +462,32 @@ def main():
         r = run_reference(args.real, 256, 64, 2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                                 "cpu": cpu_model()}
+    if world > 1:
+        same_after = ranks_identical()
+        # per-kernel table of this rank at N > 1 (instrumented pass on every rank at once: the exchange kernel waits for its peers)
+        dl.timing_enable(True)
+        t_steps = 16
+        net.train_steps(batch, t_steps, LR, cost_id, LAMBDA)
+        rep = dl.timing_report()
+        dl.timing_enable(False)
+        barrier()
+        if rank == 0:
+            dp_parity["ranks_identical_after_timed_regions"] = bool(same_after)
+            line["dp_parity"] = dp_parity
+            line["scaling_base"] = scaling_base
+            total_ms = sum(v[1] for v in rep.values()) or 1.0
+            peak, _ = hbm_peak()
+            kernels = []
+            for k, (n, t) in sorted(rep.items(), key=lambda kv: -kv[1][1])[:10]:
+                ab = algorithmic_bytes(net, k, mine, sz)
+                us = 1e3 * t / n
+                kernels.append({"kernel": k, "launches_per_step": n / t_steps, "us_per_launch": us, "share": t / total_ms,
+                                "gbs": (ab / (us * 1e-6) / 1e9) if ab else None, "frac_of_hbm_peak": (ab / (us * 1e-6) / 1e9 / peak) if ab else None})
+            line["kernels"] = kernels
+            line["serial_kernel_us_per_step"] = 1e3 * total_ms / t_steps
+            if kernels:
+                line["limiter"] = {"kernel": kernels[0]["kernel"], "us_per_launch": kernels[0]["us_per_launch"], "share": kernels[0]["share"]}
+        assert same_after, "data-parallel ranks hold different parameters after the timed regions"
     if sampler:
         line["clocks"] = sampler.stop()
     if rank == 0:

@@ -101,7 +101,7 @@ def test_lenet_step_full_size(real, tc_mode):
     kernels (mode 0)."""
     specs = ob.lenet_specs()
     orc, gpu = H.make_pair(specs, real, seed=21, tc_mode=tc_mode)
-    n = 256 if real == "f32" else 64
+    n = 256
     x, y = H.synthetic_batch(orc, n, real, seed=22, lo=0.0, hi=1.0)
     want = H.oracle_batch_trace(orc, x, y, ob.CROSS_ENTROPY)
     gpu.forward_backward(x, y, dl.CostFunctionId.CROSS_ENTROPY)
