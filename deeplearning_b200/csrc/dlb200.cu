@@ -23,6 +23,7 @@
 
 #include "../../include/dlb200.h"
 #include "fused.cuh"
+#include "mega.h"
 #include "tc_gemm.cuh"
 
 namespace dlb {
@@ -322,6 +323,17 @@ struct NetT final : dlb_net {
         ConvPoolPlan cp;
         int head_nmax = 16;
     } plan;
+    // ---- the step megakernel (mega.cu): LeNet-shaped float nets run the whole step as ONE cooperative kernel ----
+    struct MegaState {
+        bool ok = false;            // the net has the shape the kernel covers
+        bool enabled = [] { const char* e = std::getenv("DLB_MEGA"); return !(e && e[0] == '0'); }();
+        bool split = [] { const char* e = std::getenv("DLB_MEGA_SPLIT"); return e && e[0] == '1'; }();   // one launch per phase (debugging / per-phase timing)
+        mega::Shape shape{};
+        mega::Layout lay{};
+        int cap = 0;
+        unsigned char* sel = nullptr; float* z1part = nullptr; float* g1 = nullptr; float* dw1part = nullptr; float* db1part = nullptr;
+        float* convpart = nullptr; float* headpart = nullptr; double* costpart = nullptr; unsigned long long* barrier = nullptr;
+    } mg;
     R* cp_partial = nullptr; int cp_grid = 0;          // [cp_grid][cp.n_par] per-CTA partial gradients of the conv stage
     R* head_partial = nullptr; int head_chunks = 0;     // [head_chunks][n * (in_n + 1)]
     int head_chunk_cap = 0;
@@ -491,6 +503,25 @@ struct NetT final : dlb_net {
         if (H.out_n > 32 || (size_t)H.out_n * (size_t)H.in_n * sizeof(R) > 96 * 1024) return;
         plan.head_nmax = H.out_n <= 10 ? 10 : H.out_n <= 16 ? 16 : 32;
         plan.ok = true;
+        plan_mega();
+    }
+
+    // Which nets the step megakernel covers (mega.h): CLayer 5x5 over one 28x28 channel, stride 1, no padding, an even number
+    // of filters -> PLayer 2x2 max|min -> NLayer (<= 104 outputs, element-wise activation) -> NLayer head (<= 16 outputs).
+    void plan_mega() {
+        mg.ok = false;
+#ifndef DLB_CUDA_EMU
+        if constexpr (std::is_same_v<R, float>) {
+            if (L() != 4 || !plan.has_cp) return;
+            const auto& c = layers[0].s; const auto& p = layers[1].s;
+            if (c.in_c != 1 || c.in_h != 28 || c.in_w != 28 || c.win_h != 5 || c.win_w != 5 || c.stride_h != 1 || c.stride_w != 1 || c.pad_h != 0 || c.pad_w != 0) return;
+            if (c.out_c < 2 || (c.out_c & 1) || c.out_c > 64 || c.activation == DLB_ACT_SOFTMAX) return;
+            if (p.win_h != 2 || p.win_w != 2 || (p.pool_type != DLB_POOL_MAX && p.pool_type != DLB_POOL_MIN)) return;
+            if (layers[2].out_n > 104 || layers[2].s.activation == DLB_ACT_SOFTMAX || layers[3].out_n > 16) return;
+            mg.shape = mega::Shape{c.out_c, (int)layers[2].out_n, (int)layers[3].out_n};
+            mg.ok = true;
+        }
+#endif
     }
 
     ~NetT() override {
@@ -522,13 +553,85 @@ struct NetT final : dlb_net {
         if (p2p_region) cudaFree(p2p_region);
         dev_free(d_p2p_step);
         dev_free(cp_partial); dev_free(head_partial); dev_free(d_cursor); dev_free(mask_dev);
+        free_mega();
         if (own_data) { dev_free(data_x); dev_free(data_y); }
 #ifndef DLB_CUDA_EMU
         if (comm) NcclApi::get().CommDestroy(comm);
 #endif
     }
 
+    void free_mega() {
+        dev_free(mg.sel); dev_free(mg.z1part); dev_free(mg.g1); dev_free(mg.dw1part); dev_free(mg.db1part); dev_free(mg.convpart);
+        dev_free(mg.headpart); dev_free(mg.costpart); dev_free(mg.barrier);
+        mg.cap = 0;
+    }
+
+    bool mega_for(int64_t B) const { return mg.ok && mg.enabled && plan.ok && B > 0 && (world <= 1); }
+
+    void ensure_mega() {
+#ifndef DLB_CUDA_EMU
+        if (mg.cap >= cap && mg.barrier) return;
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        free_mega();
+        int n_sms = kNumSMs;
+        DLB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        mg.lay = mega::make_layout(mg.shape, cap, n_sms);
+        mg.sel = dev_alloc<unsigned char>(mg.lay.sel);
+        mg.z1part = dev_alloc<float>(mg.lay.z1part);
+        mg.g1 = dev_alloc<float>(mg.lay.g1);
+        mg.dw1part = dev_alloc<float>(mg.lay.dw1part);
+        mg.db1part = dev_alloc<float>(mg.lay.db1part);
+        mg.convpart = dev_alloc<float>(mg.lay.convpart);
+        mg.headpart = dev_alloc<float>(mg.lay.headpart);
+        mg.costpart = dev_alloc<double>(mg.lay.costpart);
+        mg.barrier = dev_alloc<unsigned long long>(1);
+        DLB_CUDA(cudaMemsetAsync(mg.g1, 0, mg.lay.g1 * sizeof(float), ctx->stream));   // columns >= H1 stay zero for good
+        DLB_CUDA(cudaMemsetAsync(mg.barrier, 0, sizeof(unsigned long long), ctx->stream));
+        mg.cap = cap;
+#endif
+    }
+
+    // One whole training step (forward, backward, ordered sums, update) in the megakernel.
+    void mega_step(int B, const R* x, const R* refs, const int* gather_base, const int* cursor, int advance, int cost, double lr, double reg_factor,
+                   int64_t batch_items, double* cost_dst) {
+#ifndef DLB_CUDA_EMU
+        if constexpr (std::is_same_v<R, float>) {
+            ensure_mega();
+            mega::Args a{};
+            a.x = x; a.refs = refs; a.gather_base = gather_base; a.cursor = cursor; a.cursor_rw = advance ? d_cursor : nullptr; a.advance = advance; a.B = B;
+            a.F = mg.shape.F; a.H1 = mg.shape.H1; a.n_out = mg.shape.n_out;
+            a.act0 = layers[0].s.activation; a.is_max = layers[1].s.pool_type == DLB_POOL_MAX; a.act1 = layers[2].s.activation; a.act2 = layers[3].s.activation;
+            a.cost_id = cost;
+            a.params = params; a.grads = grads; a.n_params = n_params;
+            a.off_b0 = layers[0].param_off; a.off_k0 = a.off_b0 + layers[0].bias_n;
+            a.off_b1 = layers[2].param_off; a.off_w1 = a.off_b1 + layers[2].bias_n;
+            a.off_b2 = layers[3].param_off; a.off_w2 = a.off_b2 + layers[3].bias_n;
+            a.pooled = out[1]; a.sel = mg.sel; a.z1part = mg.z1part; a.g1 = mg.g1; a.dpool = in_grad[2];
+            a.dw1part = mg.dw1part; a.db1part = mg.db1part; a.convpart = mg.convpart; a.headpart = mg.headpart; a.costpart = mg.costpart;
+            a.cost_out = cost_dst; a.barrier = mg.barrier;
+            a.grid = mg.lay.grid; a.groups_c = mg.lay.groups_c; a.groups_f = mg.lay.groups_f;
+            const float l_rate = -static_cast<float>(lr), reg = static_cast<float>(reg_factor);
+            a.param_scale = 1.f + reg * l_rate; a.grad_scale = l_rate * (1.f / static_cast<float>(batch_items));
+            a.nontrivial_reg = reg > 0.f ? 1 : 0; a.do_update = 1;
+            a.world = 1; a.rank = 0;
+            g_tag_layer = -1;
+            if (mg.split || g_timing_on) {
+                static const char* names[6] = {"mega_conv_fwd", "mega_fc1_fwd", "mega_head", "mega_fc1_bwd", "mega_conv_bwd", "mega_update"};
+                for (int ph = 0; ph < 6; ++ph) { TagScope tag_(names[ph]); a.phase_mask = 1 << ph; mega::launch(a, ctx->stream); }
+            } else {
+                TagScope tag_("mega_step");
+                a.phase_mask = mega::kAll;
+                mega::launch(a, ctx->stream);
+            }
+            last_B = B;
+        }
+#else
+        (void)B; (void)x; (void)refs; (void)gather_base; (void)cursor; (void)advance; (void)cost; (void)lr; (void)reg_factor; (void)batch_items; (void)cost_dst;
+#endif
+    }
+
     void free_workspace() {
+        mg.cap = 0;   // the megakernel's buffers follow the batch capacity
         for (auto& p : out) dev_free(p);
         for (auto& p : deriv) dev_free(p);
         for (auto& p : in_grad) dev_free(p);
@@ -1021,6 +1124,11 @@ struct NetT final : dlb_net {
     void step_device(const R* x, const R* refs, const int* gather_base, const int* cursor, int advance, int64_t mine, int64_t global,
                      double lr, int cost, double reg_factor) {
         draw_masks();   // one set of keep masks per (global) mini-batch; every rank draws the same ones from the same seed
+        if (mega_for(mine)) {
+            ensure_capacity(mine);
+            mega_step((int)mine, x, refs, gather_base, cursor, advance, cost, lr, reg_factor, global, nullptr);
+            return;
+        }
         if (plan.ok && mine > 0) {
             ensure_capacity(mine);
             auto body = [&] {
@@ -1192,7 +1300,8 @@ struct NetT final : dlb_net {
             else if (plan.ok) train_reduce_update(true, lr, reg_factor, n, 0);
             else update(lr, reg_factor, n);
         };
-        if (plan.ok) run_graphed(StepKey{n, n * world, lr, reg_factor, cost, sx, want_cost ? 1 : 2}, body);
+        if (mega_for(n)) mega_step((int)n, sx, sy, nullptr, nullptr, 0, cost, lr, reg_factor, n, want_cost ? (cur_cost_dev ? cur_cost_dev : cost_dev) : nullptr);
+        else if (plan.ok) run_graphed(StepKey{n, n * world, lr, reg_factor, cost, sx, want_cost ? 1 : 2}, body);
         else body();
 #ifndef DLB_CUDA_EMU
         DLB_CUDA(cudaEventRecord(ev_consumed[buf], ctx->stream));
@@ -1231,10 +1340,18 @@ struct NetT final : dlb_net {
         case DLB_BUF_INPUT_GRAD: check_layer(1); src = in_grad[(size_t)layer]; need = b * (size_t)layers[(size_t)layer].in_n * sizeof(R); break;
         case DLB_BUF_COST_GRAD: src = in_grad[(size_t)L()]; need = b * (size_t)outN() * sizeof(R); break;
         case DLB_BUF_GRADIENT: src = grads; need = (size_t)n_params * sizeof(R); break;
+        // development only (tools/mega_debug.py): the megakernel's scratch, whole buffers
+        case 101: src = mg.z1part; need = mg.lay.z1part * 4; break;
+        case 102: src = mg.g1; need = (size_t)mg.cap * 128 * 4; break;
+        case 103: src = mg.dw1part; need = mg.lay.dw1part * 4; break;
+        case 104: src = mg.convpart; need = mg.lay.convpart * 4; break;
+        case 105: src = mg.headpart; need = mg.lay.headpart * 4; break;
+        case 106: src = mg.db1part; need = mg.lay.db1part * 4; break;
         default: throw arg_error("Unknown buffer id");
         }
         DLB_REQUIRE(what == DLB_BUF_GRADIENT || last_B > 0, "No forward/backward pass has run yet");
-        DLB_REQUIRE((size_t)bytes >= need, "Destination buffer too small");
+        if (what > 100) need = std::min(need, (size_t)bytes);
+        DLB_REQUIRE(src != nullptr && (size_t)bytes >= need, "Destination buffer too small");
         DLB_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
         DLB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
@@ -1285,6 +1402,7 @@ struct NetT final : dlb_net {
 
     std::string describe_plan() override {
         if (!plan.ok) return "unfused: every layer runs the generic operators (layers.cuh)";
+        if (mega_for(1)) return "fused: one cooperative kernel per step (mega.cu): conv_pool(5x5) + hidden NLayer on tcgen05 + head + update";
         std::string d = "fused:";
         if (plan.has_cp)
             d += " conv_pool(" + std::to_string(plan.cp.KH) + "x" + std::to_string(plan.cp.KW) + ", fpt " + std::to_string(plan.cp.fpt) +

@@ -972,7 +972,7 @@ struct PeerTable {
 // The step counter lives on the device so that a captured CUDA graph of the step stays valid from step to step: the
 // publish kernel and the peer kernel read it (parity = which half is published, value + 1 = the barrier ticket) and this
 // one-thread kernel, ordered after them in the stream, advances it.
-__global__ void p2p_advance_kernel(unsigned long long* counter) { *counter += 1; }
+static __global__ void p2p_advance_kernel(unsigned long long* counter) { *counter += 1; }
 
 template <class R>
 __global__ void p2p_reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads_total, size_t n, PeerTable peers, int world, int rank,

@@ -501,7 +501,7 @@ struct EpiAccumulateT {  // out[j][i] = scale != 0 ? scale * out[j][i] + acc : a
 };
 
 // filters[f][c][q] -> out[c][f * KK + q]
-__global__ void filters_channel_major_kernel(const float* __restrict__ filt, float* __restrict__ out, int F, int C, int KK) {
+static __global__ void filters_channel_major_kernel(const float* __restrict__ filt, float* __restrict__ out, int F, int C, int KK) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= F * C * KK) return;
     const int q = e % KK, fc = e / KK;

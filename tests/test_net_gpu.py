@@ -159,7 +159,8 @@ def test_argument_errors_are_loud():
 
 def test_plans():
     """LeNet and the MLP take the fused path; nets outside its grammar take the generic operators."""
-    assert dl.lenet("f32").describe_plan().startswith("fused: conv_pool(5x5")
+    assert dl.lenet("f32").describe_plan().startswith("fused: one cooperative kernel per step")
+    assert dl.lenet("f64").describe_plan().startswith("fused: conv_pool(5x5")
     assert dl.Net([H.to_dl_spec(s) for s in MINI_MLP], real="f64").describe_plan().startswith("fused:")
     assert dl.Net([H.to_dl_spec(s) for s in MINI_LENET], real="f32").describe_plan().startswith("fused: conv_pool(3x3")
     assert dl.Net([H.to_dl_spec(s) for s in FIXTURE_NET], real="f32").describe_plan().startswith("unfused")
