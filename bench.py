@@ -187,10 +187,23 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def measured_peaks():
+    """Arithmetic peaks measured on this pool's B200 by tools/peaks.cu (profiles/peaks_r2.json): TF32 tcgen05, FFMA2, DFMA."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "peaks_r2.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+CIFAR_FLOP_PER_SAMPLE = 119_946_240      # SURVEY.md section 8(d), config 3
+CIFAR_BYTES_PER_SAMPLE_F32 = 1_826_370
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline
 # ------------------------------------------------------------------------------------------------------------------
-def run_reference(real: str, batch: int, steps: int, warmup: int):
+def run_reference(real: str, batch: int, steps: int, warmup: int, parallelism: int = -1):
     """Net<CpuDC>::learn of the UNMODIFIED reference (oracle/_ref) with all host threads; falls back to the C port of it
     (one thread) when the prebuilt library is missing.  One step = one mini-batch."""
     from oracle import binding as ob
@@ -201,9 +214,9 @@ def run_reference(real: str, batch: int, steps: int, warmup: int):
     x, y = synthetic_data(n_w + n_t, 784, 10, dtype)
     if ob.ref_available():
         net = ob.RefNet(specs, real, seed=0)
-        net.learn(x[:n_w], y[:n_w], batch, 1, LR, CROSS_ENTROPY, LAMBDA, parallelism=-1, shuffle_seed=1)
-        sec = net.learn(x[n_w:], y[n_w:], batch, 1, LR, CROSS_ENTROPY, LAMBDA, parallelism=-1, shuffle_seed=2)
-        kind, used = "reference", min(cores, batch)
+        net.learn(x[:n_w], y[:n_w], batch, 1, LR, CROSS_ENTROPY, LAMBDA, parallelism=parallelism, shuffle_seed=1)
+        sec = net.learn(x[n_w:], y[n_w:], batch, 1, LR, CROSS_ENTROPY, LAMBDA, parallelism=parallelism, shuffle_seed=2)
+        kind, used = "reference", (min(cores, batch) if parallelism < 0 else parallelism)
     else:
         from tests import helpers as H
         net = ob.OracleNet(specs, real)
@@ -459,9 +472,81 @@ def main():
         big["step_roofline_frac"] = big["value"] / (peak * 1e9 / bps8)
         line["config5_on_1_gpu"] = big
 
+        pk = measured_peaks()
+        # ---- BASELINE configs[2]: CIFAR-deep (3 conv + pool stages, ReLU, L2), mini-batch 1024, every contraction on tcgen05 (3xTF32)
+        if args.real == "f32":
+            try:
+                net3 = dl.cifar_deep("f32", context=ctx)
+                net3.init_params(seed=0)
+                n3 = 4096
+                x3, y3 = synthetic_data(n3, 3 * 32 * 32, 10, np.float32, seed=9)
+                net3.set_dataset(x3, y3)
+                net3.reset_random_generator(0)
+                net3.train_steps(1024, 3, LR, cost_id, LAMBDA)
+                ctx.synchronize()
+                e0.record(); it3 = net3.train_steps(1024, 12, LR, cost_id, LAMBDA); e1.record()
+                ms3 = e0.elapsed_ms(e1)
+                v3 = it3 / (ms3 / 1e3)
+                c3 = {"workload": "CIFAR-deep: C5x5x32 -> P2 -> C5x5x64 -> P2 -> C3x3x128 -> P2 -> N256 -> softmax 10, ReLU, L2, mini-batch 1024 (BASELINE configs[2])",
+                      "value": v3, "unit": "samples/s", "ms_per_step": ms3 / 12, "plan": net3.describe_plan(),
+                      "fp32_equivalent_tflops": v3 * CIFAR_FLOP_PER_SAMPLE / 1e12,
+                      "hbm_roofline_samples_per_s": peak * 1e9 / CIFAR_BYTES_PER_SAMPLE_F32, "frac_of_hbm_roofline": v3 / (peak * 1e9 / CIFAR_BYTES_PER_SAMPLE_F32)}
+                if pk.get("tf32_3x_equivalent_fp32_tflops"):
+                    c3["tensor_roofline_tflops_3xtf32"] = pk["tf32_3x_equivalent_fp32_tflops"]
+                    c3["frac_of_3xtf32_roofline"] = c3["fp32_equivalent_tflops"] / pk["tf32_3x_equivalent_fp32_tflops"]
+                dl.timing_enable(True)
+                net3.train_steps(1024, 2, LR, cost_id, LAMBDA)
+                rep3 = dl.timing_report()
+                dl.timing_enable(False)
+                tot3 = sum(v[1] for v in rep3.values()) or 1.0
+                c3["kernels"] = [{"kernel": k, "launches_per_step": n / 2, "us_per_launch": 1e3 * t / n, "share": t / tot3}
+                                 for k, (n, t) in sorted(rep3.items(), key=lambda kv: -kv[1][1])[:8]]
+                line["config3"] = c3
+                net3.close()
+            except Exception as exc:   # never lose the headline line to a secondary workload
+                line["config3"] = {"error": str(exc)[:200]}
+            # ---- Real = double (the reference's default Real, defs.h:25-29) on the same LeNet workload
+            try:
+                net64 = dl.lenet(real="f64", context=ctx)
+                net64.init_params(seed=0)
+                n64 = 16384
+                net64.set_dataset(x[:n64].astype(np.float64), y[:n64].astype(np.float64))
+                net64.reset_random_generator(0)
+                net64.train_steps(256, 8, LR, cost_id, LAMBDA)
+                ctx.synchronize()
+                e0.record(); it64 = net64.train_steps(256, 56, LR, cost_id, LAMBDA); e1.record()
+                ms64 = e0.elapsed_ms(e1)
+                line["f64"] = {"workload": "LeNet, Real = double, mini-batch 256", "value": it64 / (ms64 / 1e3), "unit": "samples/s", "ms_per_step": ms64 / 56,
+                               "contractions": "DFMA (tcgen05 has no fp64 kind)", "dfma_peak_tflops": pk.get("dfma_tflops")}
+                net64.close()
+            except Exception as exc:
+                line["f64"] = {"error": str(exc)[:200]}
+            # ---- the same headline workload through the single-kernel step (dlb_net_enable_step_kernel; not the default)
+            try:
+                netm = dl.lenet(real="f32", context=ctx)
+                netm.init_params(seed=0)
+                netm.enable_step_kernel(True)
+                netm.set_dataset(x, y)
+                netm.reset_random_generator(0)
+                netm.train_steps(256, 16, LR, cost_id, LAMBDA)
+                ctx.synchronize()
+                l0 = ctx.launch_count()
+                e0.record(); itm = netm.train_steps(256, 200, LR, cost_id, LAMBDA); e1.record()
+                msm = e0.elapsed_ms(e1)
+                line["step_kernel"] = {"what": "LeNet B=256 with the whole step as one persistent cooperative kernel (csrc/mega.cu), all steps of the call in one launch",
+                                       "value": itm / (msm / 1e3), "unit": "samples/s", "ms_per_step": msm / 200, "launches": int(ctx.launch_count() - l0),
+                                       "plan": netm.describe_plan()}
+                netm.close()
+            except Exception as exc:
+                line["step_kernel"] = {"error": str(exc)[:200]}
+
         r = run_reference(args.real, 256, 64, 2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                                 "cpu": cpu_model()}
+        r1 = run_reference(args.real, 256, 8, 1, parallelism=1)
+        line["cpu_baseline"]["one_thread"] = {"value": r1["value"], "unit": "samples/s", "cores": 1, "sample": r1["sample"]}
+        if pk:
+            line["measured_peaks"] = {k: pk[k] for k in ("tf32_tcgen05_cta1_m128_n256_tflops", "tf32_3x_equivalent_fp32_tflops", "ffma2_tflops", "dfma_tflops") if k in pk}
     if world > 1:
         same_after = ranks_identical()
         # per-kernel table of this rank at N > 1 (instrumented pass on every rank at once: the exchange kernel waits for its peers)

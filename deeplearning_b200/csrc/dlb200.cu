@@ -280,6 +280,7 @@ struct dlb_net {
     virtual std::string describe_plan() = 0;
     virtual void enable_graphs(bool on) = 0;
     virtual void enable_tensor_cores(int mode) = 0;
+    virtual void enable_step_kernel(int mode) = 0;
     virtual void set_keep_rate(int layer, double keep_rate) = 0;
     virtual int64_t mask_size() const = 0;
     virtual void set_dropout_masks(const void* masks_host) = 0;
@@ -326,13 +327,13 @@ struct NetT final : dlb_net {
     // ---- the step megakernel (mega.cu): LeNet-shaped float nets run the whole step as ONE cooperative kernel ----
     struct MegaState {
         bool ok = false;            // the net has the shape the kernel covers
-        bool enabled = [] { const char* e = std::getenv("DLB_MEGA"); return !(e && e[0] == '0'); }();
+        bool enabled = [] { const char* e = std::getenv("DLB_MEGA"); return e && e[0] == '1'; }();   // dlb_net_enable_step_kernel; DLB_MEGA=1 turns it on for every net
         bool split = [] { const char* e = std::getenv("DLB_MEGA_SPLIT"); return e && e[0] == '1'; }();   // one launch per phase (debugging / per-phase timing)
+        bool multi = [] { const char* e = std::getenv("DLB_MEGA_MULTI"); return !(e && e[0] == '0'); }();   // train_steps: consecutive steps in one launch
         mega::Shape shape{};
-        mega::Layout lay{};
-        int cap = 0;
-        unsigned char* sel = nullptr; float* z1part = nullptr; float* g1 = nullptr; float* dw1part = nullptr; float* db1part = nullptr;
-        float* convpart = nullptr; float* headpart = nullptr; double* costpart = nullptr; unsigned long long* barrier = nullptr;
+#ifndef DLB_CUDA_EMU
+        mega::Runner* runner = nullptr;
+#endif
     } mg;
     R* cp_partial = nullptr; int cp_grid = 0;          // [cp_grid][cp.n_par] per-CTA partial gradients of the conv stage
     R* head_partial = nullptr; int head_chunks = 0;     // [head_chunks][n * (in_n + 1)]
@@ -517,7 +518,10 @@ struct NetT final : dlb_net {
             if (c.in_c != 1 || c.in_h != 28 || c.in_w != 28 || c.win_h != 5 || c.win_w != 5 || c.stride_h != 1 || c.stride_w != 1 || c.pad_h != 0 || c.pad_w != 0) return;
             if (c.out_c < 2 || (c.out_c & 1) || c.out_c > 64 || c.activation == DLB_ACT_SOFTMAX) return;
             if (p.win_h != 2 || p.win_w != 2 || (p.pool_type != DLB_POOL_MAX && p.pool_type != DLB_POOL_MIN)) return;
-            if (layers[2].out_n > 104 || layers[2].s.activation == DLB_ACT_SOFTMAX || layers[3].out_n > 16) return;
+            if (layers[2].out_n > 104 || (layers[2].out_n & 3) || layers[2].s.activation == DLB_ACT_SOFTMAX || layers[3].out_n > 16) return;
+            // 16-byte copies / vector loads of the hidden layer's parameters: its bias and weight blocks must start 16-byte aligned in the
+            // flat parameter buffer (F * (576 + 25) and the hidden width multiples of 4; LeNet: 12 020 and 100)
+            if ((layers[2].param_off & 3) || ((layers[2].param_off + layers[2].bias_n) & 3)) return;
             mg.shape = mega::Shape{c.out_c, (int)layers[2].out_n, (int)layers[3].out_n};
             mg.ok = true;
         }
@@ -561,77 +565,43 @@ struct NetT final : dlb_net {
     }
 
     void free_mega() {
-        dev_free(mg.sel); dev_free(mg.z1part); dev_free(mg.g1); dev_free(mg.dw1part); dev_free(mg.db1part); dev_free(mg.convpart);
-        dev_free(mg.headpart); dev_free(mg.costpart); dev_free(mg.barrier);
-        mg.cap = 0;
+#ifndef DLB_CUDA_EMU
+        if (mg.runner) { mega::runner_destroy(mg.runner); mg.runner = nullptr; }
+#endif
     }
 
     bool mega_for(int64_t B) const { return mg.ok && mg.enabled && plan.ok && B > 0 && (world <= 1); }
 
-    void ensure_mega() {
-#ifndef DLB_CUDA_EMU
-        if (mg.cap >= cap && mg.barrier) return;
-        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
-        free_mega();
-        int n_sms = kNumSMs;
-        DLB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
-        mg.lay = mega::make_layout(mg.shape, cap, n_sms);
-        mg.sel = dev_alloc<unsigned char>(mg.lay.sel);
-        mg.z1part = dev_alloc<float>(mg.lay.z1part);
-        mg.g1 = dev_alloc<float>(mg.lay.g1);
-        mg.dw1part = dev_alloc<float>(mg.lay.dw1part);
-        mg.db1part = dev_alloc<float>(mg.lay.db1part);
-        mg.convpart = dev_alloc<float>(mg.lay.convpart);
-        mg.headpart = dev_alloc<float>(mg.lay.headpart);
-        mg.costpart = dev_alloc<double>(mg.lay.costpart);
-        mg.barrier = dev_alloc<unsigned long long>(1);
-        DLB_CUDA(cudaMemsetAsync(mg.g1, 0, mg.lay.g1 * sizeof(float), ctx->stream));   // columns >= H1 stay zero for good
-        DLB_CUDA(cudaMemsetAsync(mg.barrier, 0, sizeof(unsigned long long), ctx->stream));
-        mg.cap = cap;
-#endif
-    }
-
-    // One whole training step (forward, backward, ordered sums, update) in the megakernel.
+    // `n_steps` whole training steps (forward, backward, ordered sums, update) in the megakernel.
     void mega_step(int B, const R* x, const R* refs, const int* gather_base, const int* cursor, int advance, int cost, double lr, double reg_factor,
-                   int64_t batch_items, double* cost_dst) {
+                   int64_t batch_items, double* cost_dst, int n_steps = 1) {
 #ifndef DLB_CUDA_EMU
         if constexpr (std::is_same_v<R, float>) {
-            ensure_mega();
-            mega::Args a{};
-            a.x = x; a.refs = refs; a.gather_base = gather_base; a.cursor = cursor; a.cursor_rw = advance ? d_cursor : nullptr; a.advance = advance; a.B = B;
-            a.F = mg.shape.F; a.H1 = mg.shape.H1; a.n_out = mg.shape.n_out;
-            a.act0 = layers[0].s.activation; a.is_max = layers[1].s.pool_type == DLB_POOL_MAX; a.act1 = layers[2].s.activation; a.act2 = layers[3].s.activation;
-            a.cost_id = cost;
-            a.params = params; a.grads = grads; a.n_params = n_params;
-            a.off_b0 = layers[0].param_off; a.off_k0 = a.off_b0 + layers[0].bias_n;
-            a.off_b1 = layers[2].param_off; a.off_w1 = a.off_b1 + layers[2].bias_n;
-            a.off_b2 = layers[3].param_off; a.off_w2 = a.off_b2 + layers[3].bias_n;
-            a.pooled = out[1]; a.sel = mg.sel; a.z1part = mg.z1part; a.g1 = mg.g1; a.dpool = in_grad[2];
-            a.dw1part = mg.dw1part; a.db1part = mg.db1part; a.convpart = mg.convpart; a.headpart = mg.headpart; a.costpart = mg.costpart;
-            a.cost_out = cost_dst; a.barrier = mg.barrier;
-            a.grid = mg.lay.grid; a.groups_c = mg.lay.groups_c; a.groups_f = mg.lay.groups_f;
-            const float l_rate = -static_cast<float>(lr), reg = static_cast<float>(reg_factor);
-            a.param_scale = 1.f + reg * l_rate; a.grad_scale = l_rate * (1.f / static_cast<float>(batch_items));
-            a.nontrivial_reg = reg > 0.f ? 1 : 0; a.do_update = 1;
-            a.world = 1; a.rank = 0;
-            g_tag_layer = -1;
-            if (mg.split || g_timing_on) {
-                static const char* names[6] = {"mega_conv_fwd", "mega_fc1_fwd", "mega_head", "mega_fc1_bwd", "mega_conv_bwd", "mega_update"};
-                for (int ph = 0; ph < 6; ++ph) { TagScope tag_(names[ph]); a.phase_mask = 1 << ph; mega::launch(a, ctx->stream); }
-            } else {
-                TagScope tag_("mega_step");
-                a.phase_mask = mega::kAll;
-                mega::launch(a, ctx->stream);
-            }
+            if (!mg.runner) mg.runner = mega::runner_create(mg.shape, ctx->device);
+            mega::StepIn in{};
+            in.stream = ctx->stream;
+            in.x = x; in.refs = refs; in.gather_base = gather_base; in.cursor = cursor; in.cursor_rw = advance ? d_cursor : nullptr; in.advance = advance;
+            in.B = B; in.cap = cap;
+            in.act0 = layers[0].s.activation; in.is_max = layers[1].s.pool_type == DLB_POOL_MAX; in.act1 = layers[2].s.activation; in.act2 = layers[3].s.activation;
+            in.cost_id = cost;
+            in.params = params; in.grads = grads; in.n_params = n_params;
+            in.off_b0 = layers[0].param_off; in.off_k0 = in.off_b0 + layers[0].bias_n;
+            in.off_b1 = layers[2].param_off; in.off_w1 = in.off_b1 + layers[2].bias_n;
+            in.off_b2 = layers[3].param_off; in.off_w2 = in.off_b2 + layers[3].bias_n;
+            in.pooled = out[1]; in.dpool = in_grad[2];
+            in.lr = lr; in.reg_factor = reg_factor; in.batch_items = batch_items; in.cost_out = cost_dst;
+            in.n_steps = n_steps;
+            in.world = 1; in.rank = 0;
+            in.split_phases = mg.split ? 1 : 0;
+            mega::runner_step(mg.runner, in);
             last_B = B;
         }
 #else
-        (void)B; (void)x; (void)refs; (void)gather_base; (void)cursor; (void)advance; (void)cost; (void)lr; (void)reg_factor; (void)batch_items; (void)cost_dst;
+        (void)B; (void)x; (void)refs; (void)gather_base; (void)cursor; (void)advance; (void)cost; (void)lr; (void)reg_factor; (void)batch_items; (void)cost_dst; (void)n_steps;
 #endif
     }
 
     void free_workspace() {
-        mg.cap = 0;   // the megakernel's buffers follow the batch capacity
         for (auto& p : out) dev_free(p);
         for (auto& p : deriv) dev_free(p);
         for (auto& p : in_grad) dev_free(p);
@@ -1083,9 +1053,8 @@ struct NetT final : dlb_net {
             g_tag_layer = -1;
             TagScope tag_("p2p_reduce_update");
             DLB_LAUNCH((p2p_reduce_update_kernel<R>), dim3(2 * kNumSMs), dim3(256), ctx->stream, params, grads, (size_t)n_params, pt, world, rank,
-                       (const unsigned long long*)d_p2p_step, segs, static_cast<R>(1) + reg * l_rate, l_rate * grad_norm,
+                       d_p2p_step, reinterpret_cast<unsigned int*>(d_p2p_step + 1), segs, static_cast<R>(1) + reg * l_rate, l_rate * grad_norm,
                        reg > static_cast<R>(0) ? 1 : 0, advance ? d_cursor : (int*)nullptr, advance);
-            DLB_LAUNCH((p2p_advance_kernel), dim3(1), dim3(1), ctx->stream, d_p2p_step);
             return;
         }
 #endif
@@ -1185,6 +1154,14 @@ struct NetT final : dlb_net {
             while (start < n_items) {
                 // Net.inl:235-236: fewer than 1.5 * batch_size remaining items are taken as one batch
                 const int64_t end = (double)(n_items - start) < 1.5 * (double)batch ? n_items : start + batch;
+                if (mega_for(end - start) && mg.multi && end - start == batch) {   // all full mini-batches of the epoch in ONE launch of the step kernel
+                    int64_t k = 1;
+                    while ((double)(n_items - (start + k * batch)) >= 1.5 * (double)batch) ++k;
+                    ensure_capacity(batch);
+                    mega_step((int)batch, data_x, data_y, perm_dev, d_cursor, (int)batch, cost, lr, (double)reg_factor, batch, nullptr, (int)k);
+                    start += k * batch;
+                    continue;
+                }
                 run_batch(start, end, lr, cost, (double)reg_factor);
                 start = end;
             }
@@ -1218,6 +1195,17 @@ struct NetT final : dlb_net {
             }
             const int64_t start = ts_cursor;
             const int64_t end = (double)(n_items - start) < 1.5 * (double)batch ? n_items : start + batch;
+            if (mega_for(end - start) && mg.multi && end - start == batch) {
+                // consecutive full mini-batches of this epoch run inside ONE launch of the step kernel (the batch position lives in d_cursor)
+                int64_t k = 1;
+                while (s + k < n_steps && (double)(n_items - (start + k * batch)) >= 1.5 * (double)batch) ++k;
+                ensure_capacity(batch);
+                mega_step((int)batch, data_x, data_y, perm_dev, d_cursor, (int)batch, cost, lr, (double)reg_factor, batch, nullptr, (int)k);
+                consumed += k * batch;
+                ts_cursor = start + k * batch;
+                s += k - 1;
+                continue;
+            }
             run_batch(start, end, lr, cost, (double)reg_factor);
             consumed += end - start;
             ts_cursor = end;
@@ -1333,6 +1321,13 @@ struct NetT final : dlb_net {
         size_t need = 0;
         const size_t b = (size_t)last_B;
         auto check_layer = [&](int lo) { DLB_REQUIRE(layer >= lo && layer < L(), "Invalid layer index"); };
+#ifndef DLB_CUDA_EMU
+        if (what > 100) {   // development only (tools/mega_debug.py): the megakernel's scratch buffers
+            DLB_REQUIRE(mg.runner != nullptr, "the megakernel has not run");
+            mega::runner_debug_read(mg.runner, what, dst, (size_t)bytes, ctx->stream);
+            return;
+        }
+#endif
         switch (what) {
         case DLB_BUF_OUTPUT: check_layer(0); src = out[(size_t)layer]; need = b * (size_t)layers[(size_t)layer].out_n * sizeof(R); break;
         case DLB_BUF_DERIVATIVES: check_layer(0); src = deriv[(size_t)layer]; need = b * (size_t)layers[(size_t)layer].out_n * sizeof(R); break;
@@ -1340,18 +1335,10 @@ struct NetT final : dlb_net {
         case DLB_BUF_INPUT_GRAD: check_layer(1); src = in_grad[(size_t)layer]; need = b * (size_t)layers[(size_t)layer].in_n * sizeof(R); break;
         case DLB_BUF_COST_GRAD: src = in_grad[(size_t)L()]; need = b * (size_t)outN() * sizeof(R); break;
         case DLB_BUF_GRADIENT: src = grads; need = (size_t)n_params * sizeof(R); break;
-        // development only (tools/mega_debug.py): the megakernel's scratch, whole buffers
-        case 101: src = mg.z1part; need = mg.lay.z1part * 4; break;
-        case 102: src = mg.g1; need = (size_t)mg.cap * 128 * 4; break;
-        case 103: src = mg.dw1part; need = mg.lay.dw1part * 4; break;
-        case 104: src = mg.convpart; need = mg.lay.convpart * 4; break;
-        case 105: src = mg.headpart; need = mg.lay.headpart * 4; break;
-        case 106: src = mg.db1part; need = mg.lay.db1part * 4; break;
         default: throw arg_error("Unknown buffer id");
         }
         DLB_REQUIRE(what == DLB_BUF_GRADIENT || last_B > 0, "No forward/backward pass has run yet");
-        if (what > 100) need = std::min(need, (size_t)bytes);
-        DLB_REQUIRE(src != nullptr && (size_t)bytes >= need, "Destination buffer too small");
+        DLB_REQUIRE((size_t)bytes >= need, "Destination buffer too small");
         DLB_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
         DLB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
@@ -1412,6 +1399,7 @@ struct NetT final : dlb_net {
     }
     void enable_graphs(bool on) override { graphs_enabled = on; if (!on) drop_graphs(); }
     void enable_tensor_cores(int mode) override { tc_mode = mode; drop_graphs(); }
+    void enable_step_kernel(int mode) override { mg.enabled = mode != 0; }
 
     // Allocates the shared region [publish 0 | publish 1 | flags] and returns its CUDA IPC handle (64 bytes).
     void p2p_export(void* handle64) override {
@@ -1424,8 +1412,8 @@ struct NetT final : dlb_net {
             const size_t total = 2 * p2p_publish_bytes + kMaxPeers * sizeof(unsigned long long);
             DLB_CUDA(cudaMalloc((void**)&p2p_region, total));
             DLB_CUDA(cudaMemset(p2p_region, 0, total));
-            d_p2p_step = dev_alloc<unsigned long long>(1);
-            DLB_CUDA(cudaMemset(d_p2p_step, 0, sizeof(unsigned long long)));
+            d_p2p_step = dev_alloc<unsigned long long>(2);   // [step counter | blocks-done counter of the peer kernel]
+            DLB_CUDA(cudaMemset(d_p2p_step, 0, 2 * sizeof(unsigned long long)));
         }
         cudaIpcMemHandle_t h;
         DLB_CUDA(cudaIpcGetMemHandle(&h, p2p_region));
@@ -1452,7 +1440,7 @@ struct NetT final : dlb_net {
             DLB_CUDA(cudaIpcOpenMemHandle(&p2p_peer_regions[(size_t)r], h, cudaIpcMemLazyEnablePeerAccess));
         }
         rank = rank_; world = world_; p2p_on = world_ > 1; p2p_step = 0;
-        DLB_CUDA(cudaMemset(d_p2p_step, 0, sizeof(unsigned long long)));
+        DLB_CUDA(cudaMemset(d_p2p_step, 0, 2 * sizeof(unsigned long long)));
         DLB_CUDA(cudaMemset(p2p_region + 2 * p2p_publish_bytes, 0, kMaxPeers * sizeof(unsigned long long)));
 #endif
     }
@@ -1750,6 +1738,14 @@ extern "C" __attribute__((visibility("default"))) int dlb_debug_tc_profile(unsig
     return 0;
 }
 #endif
+
+int dlb_net_enable_step_kernel(dlb_net* net, int mode) {
+    return guarded([&] {
+        DLB_REQUIRE(net, "null net");
+        DLB_REQUIRE(mode == 0 || mode == 1, "step-kernel mode must be 0 (off) or 1 (on)");
+        net->enable_step_kernel(mode);
+    });
+}
 
 int dlb_net_enable_graphs(dlb_net* net, int on) { return guarded([&] { DLB_REQUIRE(net, "null net"); net->enable_graphs(on != 0); }); }
 

@@ -970,14 +970,15 @@ struct PeerTable {
 };
 
 // The step counter lives on the device so that a captured CUDA graph of the step stays valid from step to step: the
-// publish kernel and the peer kernel read it (parity = which half is published, value + 1 = the barrier ticket) and this
-// one-thread kernel, ordered after them in the stream, advances it.
-static __global__ void p2p_advance_kernel(unsigned long long* counter) { *counter += 1; }
+// publish kernel and the peer kernel read it (parity = which half is published, value + 1 = the barrier ticket); the LAST
+// block of the peer kernel to finish advances it (a block-completion counter), so no extra one-thread launch is needed.
+template <class R> struct alignas(16) Vec16 { R v[16 / sizeof(R)]; };
 
 template <class R>
-__global__ void p2p_reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads_total, size_t n, PeerTable peers, int world, int rank,
-                                         const unsigned long long* __restrict__ counter, UpdateSegments segs, R param_scale, R grad_scale,
-                                         int nontrivial_reg, int* __restrict__ cursor, int advance) {
+__global__ void __launch_bounds__(256) p2p_reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads_total, size_t n, PeerTable peers, int world, int rank,
+                                         unsigned long long* __restrict__ counter, unsigned int* __restrict__ blocks_done, UpdateSegments segs,
+                                         R param_scale, R grad_scale, int nontrivial_reg, int* __restrict__ cursor, int advance) {
+    constexpr int V = 16 / (int)sizeof(R);
     const unsigned long long t = *counter;
     const unsigned long long step = t + 1;
     const size_t half = (size_t)(t & 1) * peers.publish_bytes;
@@ -997,16 +998,45 @@ __global__ void p2p_reduce_update_kernel(R* __restrict__ p, R* __restrict__ grad
     }
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0 && cursor) *cursor += advance;
-    // (2) + (3)
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-        R gsum = R(0);
-        for (int r = 0; r < world; ++r) gsum += reinterpret_cast<const R*>(peers.region[r] + half)[e];   // rank order: identical on every rank
+    // (2) + (3): 16 bytes per thread and rank, the loads of ALL ranks in flight together (one NVLink round trip, not `world` of them),
+    // then the sum in rank order (identical on every rank) and the update
+    auto update_one = [&](size_t e, R gsum) {
         grads_total[e] = gsum;
         int s = 0;
         while (s < segs.count - 1 && (long long)e >= segs.end[s]) ++s;
         const bool reg = nontrivial_reg && segs.regularised[s];
         const R xv = p[e];
         p[e] = reg ? xv * param_scale + gsum * grad_scale : xv + gsum * grad_scale;
+    };
+    const size_t nv = n / V;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+        Vec16<R> acc;
+#pragma unroll
+        for (int q = 0; q < V; ++q) acc.v[q] = R(0);
+        for (int r0 = 0; r0 < world; r0 += 8) {
+            Vec16<R> v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = reinterpret_cast<const Vec16<R>*>(peers.region[min(r0 + r, world - 1)] + half)[i];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r0 + r < world) {
+#pragma unroll
+                    for (int q = 0; q < V; ++q) acc.v[q] += v[r].v[q];
+                }
+        }
+#pragma unroll
+        for (int q = 0; q < V; ++q) update_one(i * V + q, acc.v[q]);
+    }
+    for (size_t e = nv * V + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        R gsum = R(0);
+        for (int r = 0; r < world; ++r) gsum += reinterpret_cast<const R*>(peers.region[r] + half)[e];
+        update_one(e, gsum);
+    }
+    // (4) the last block out advances the step counter (every block read it at the top)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(blocks_done, 1u) == gridDim.x - 1) { *blocks_done = 0u; *counter = step; }
     }
 }
 

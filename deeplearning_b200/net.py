@@ -268,6 +268,10 @@ class Net:
         least 128 samples per GPU (the default), 2 = tcgen05 at every batch size."""
         _capi.check(self.lib.dlb_net_enable_tensor_cores(self._handle(), int(mode)))
 
+    def enable_step_kernel(self, on: bool = True) -> None:
+        """The whole step as one persistent cooperative kernel (csrc/mega.cu) where the net qualifies (LeNet-shaped float nets)."""
+        _capi.check(self.lib.dlb_net_enable_step_kernel(self._handle(), 1 if on else 0))
+
     def set_keep_rate(self, layer: int, keep_rate: float) -> None:
         """ALayer::set_keep_rate / the keep_rate constructor argument of CLayer, PLayer and NLayer (one minus the dropout rate
         of the layer's input, ALayer.inl:25-55)."""

@@ -164,6 +164,13 @@ DLB_API int dlb_net_enable_graphs(dlb_net* net, int on);
  * always.  Real = double always uses the FMA path (tcgen05 has no fp64 kind). */
 DLB_API int dlb_net_enable_tensor_cores(dlb_net* net, int mode);
 
+/* The whole mini-batch step of Net<D>::learn (Net.inl:226-317) as ONE persistent cooperative kernel (csrc/mega.cu) for float nets of
+ * LeNet's shape (CLayer 5x5 over one 28x28 channel -> PLayer 2x2 max|min -> NLayer -> NLayer head); dlb_net_train_steps / dlb_net_learn
+ * then run all consecutive full mini-batches of an epoch inside a single launch.  mode 0 (default) = the multi-kernel CUDA-graph step,
+ * 1 = the step kernel where the net qualifies.  Same results within the parity bar either way; measured on B200 the two are within
+ * 5 % of each other at mini-batch 256, so the graph path stays the default. */
+DLB_API int dlb_net_enable_step_kernel(dlb_net* net, int mode);
+
 /* Dense fp32 contraction C[M][N] = sum_k A(m,k) * B(n,k) (replaces CudaMatrix::mul_add / transpose_mul /
  * vector_col_times_vector_row style products, CudaMatrix.cu:227-498, for whole batches).  a_transposed / b_transposed:
  * the operand is stored [K][M] / [K][N] with leading dimension lda / ldb.  use_tensor_cores selects tcgen05 (3xTF32). */

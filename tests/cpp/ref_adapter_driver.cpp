@@ -1,0 +1,129 @@
+// tests/cpp/ref_adapter_driver.cpp — the reference's own Net template driving libdlb200 through the binding of
+// deeplearning_b200/host/gpu_dc.hpp (TEST INFRASTRUCTURE; built by tests/cpp/Makefile against /root/reference, with the
+// shim headers of oracle/shim/; the resulting tests/cpp/_build/libref_adapter_{f32,f64}.so travels to the GPU box).
+//
+// rad_run: builds TWO identical reference nets (Net<CpuDC>, same seed -> same random weights from the reference's own
+// initialisers), trains one with the reference's own Net<CpuDC>::learn on the host and the other through the GpuDC binding
+// (data set in GpuDC tensors on the device, DeepLearning::learn -> dlb_net_learn), and hands both parameter vectors and both
+// nets' predicted classes (computed by the reference's own act on the two trained nets) back to the test.
+#include <gpu_dc.hpp>
+
+#include <cstdint>
+#include <string>
+
+using namespace DeepLearning;
+
+namespace {
+thread_local std::string g_err;
+
+void build(Net<CpuDC>& net, const dlb_layer_spec* specs, int n) {
+    for (int i = 0; i < n; ++i) {
+        const auto& s = specs[i];
+        const Index3d in{ s.in_c, s.in_h, s.in_w };
+        const auto act = static_cast<ActivationFunctionId>(s.activation);
+        switch (s.type) {
+        case DLB_LAYER_CONVOLUTION:
+            net.append_layer<CLayer>(in, Index2d{ s.win_h, s.win_w }, static_cast<std::size_t>(s.out_c), act, Index3d{ 0, s.pad_h, s.pad_w },
+                                     Index3d{ 1, s.stride_h, s.stride_w });
+            break;
+        case DLB_LAYER_PULL: net.append_layer<PLayer>(in, Index2d{ s.win_h, s.win_w }, static_cast<PoolTypeId>(s.pool_type)); break;
+        case DLB_LAYER_FULL:
+            net.append_layer<NLayer>(static_cast<std::size_t>(in.coord_prod()), static_cast<std::size_t>(s.out_c), act, Real(-1), Real(1), true);
+            break;
+        default: throw std::runtime_error("unknown layer type");
+        }
+    }
+}
+
+std::vector<Tensor> to_tensors(const Real* data, int64_t n, const Index3d& size) {
+    std::vector<Tensor> out;
+    const auto sz = static_cast<std::size_t>(size.coord_prod());
+    for (int64_t i = 0; i < n; ++i) { Tensor t(size, false); std::memcpy(t.begin(), data + i * sz, sz * sizeof(Real)); out.push_back(std::move(t)); }
+    return out;
+}
+}  // namespace
+
+extern "C" {
+
+int rad_real_bytes() { return static_cast<int>(sizeof(Real)); }
+const char* rad_last_error() { return g_err.c_str(); }
+
+// Round trip of the binding's converters: specs recovered from the reference layers must equal the specs the net was built from, and
+// flatten -> scatter -> flatten must be the identity.  Returns 0 when everything matches.
+int rad_check_converters(const dlb_layer_spec* specs, int n_layers, unsigned seed) {
+    try {
+        Net<CpuDC>::reset_random_generator(seed);
+        Net<CpuDC> net;
+        build(net, specs, n_layers);
+        for (int l = 0; l < n_layers; ++l) {
+            const dlb_layer_spec got = dlb200_binding::to_spec(net[l]);
+            const dlb_layer_spec& want = specs[l];
+            // an NLayer only knows its flat input dimension
+            const bool same_in = want.type == DLB_LAYER_FULL ? got.in_c * got.in_h * got.in_w == want.in_c * want.in_h * want.in_w
+                                                            : got.in_c == want.in_c && got.in_h == want.in_h && got.in_w == want.in_w;
+            const bool same = got.type == want.type && same_in &&
+                (want.type == DLB_LAYER_PULL || got.activation == want.activation) && got.out_c == (want.type == DLB_LAYER_PULL ? 0 : want.out_c) &&
+                (want.type == DLB_LAYER_FULL || (got.win_h == want.win_h && got.win_w == want.win_w)) &&
+                (want.type != DLB_LAYER_CONVOLUTION || (got.pad_h == want.pad_h && got.pad_w == want.pad_w && got.stride_h == want.stride_h && got.stride_w == want.stride_w)) &&
+                (want.type != DLB_LAYER_PULL || got.pool_type == want.pool_type);
+            if (!same) { g_err = "to_spec mismatch at layer " + std::to_string(l); return 1; }
+        }
+        auto flat = dlb200_binding::flatten_params(net);
+        for (auto& v : flat) v = v * Real(0.5) + Real(0.25);
+        dlb200_binding::scatter_params(net, flat);
+        if (dlb200_binding::flatten_params(net) != flat) { g_err = "scatter_params / flatten_params are not inverse"; return 1; }
+        return 0;
+    } catch (const std::runtime_error& e) { g_err = e.what(); return 2; } catch (...) { g_err = "unknown exception"; return 3; }
+}
+
+int rad_run(const dlb_layer_spec* specs, int n_layers, unsigned init_seed, unsigned learn_seed, const Real* x, const Real* y, int64_t n_items,
+            int64_t batch, int64_t epochs, double lr, int cost_id, double lambda, int cpu_threads, Real* params_cpu, Real* params_gpu,
+            int32_t* classes_cpu, int32_t* classes_gpu, int32_t* epochs_seen_gpu, double* eval_cost_gpu, double* eval_correct_gpu) {
+    try {
+        const Index3d in{ specs[0].in_c, specs[0].in_h, specs[0].in_w };
+        Net<CpuDC> net_cpu, net_gpu;
+        Net<CpuDC>::reset_random_generator(init_seed); build(net_cpu, specs, n_layers);
+        Net<CpuDC>::reset_random_generator(init_seed); build(net_gpu, specs, n_layers);
+        const Index3d out = net_cpu[net_cpu.layers_count() - 1].out_size();
+        const auto items = to_tensors(x, n_items, in), refs = to_tensors(y, n_items, out);
+        const auto cost = static_cast<CostFunctionId>(cost_id);
+
+        // (1) the reference, on the host
+        Net<CpuDC>::reset_random_generator(learn_seed);
+        net_cpu.learn(items, refs, static_cast<std::size_t>(batch), static_cast<std::size_t>(epochs), static_cast<Real>(lr), cost,
+                      static_cast<Real>(lambda), [](const auto, const auto) {}, cpu_threads);
+
+        // (2) the same net through the GpuDC binding: the data set goes to the device as GpuDC tensors (GpuDC::from_host), the model stays
+        // in the reference's Net object and comes back trained
+        std::vector<GpuDC::tensor_t> d_items, d_refs;
+        for (const auto& t : items) d_items.push_back(GpuDC::from_host(t));
+        for (const auto& t : refs) d_refs.push_back(GpuDC::from_host(t));
+        int32_t seen = 0;
+        DeepLearning::learn(net_gpu, d_items, d_refs, static_cast<std::size_t>(batch), static_cast<std::size_t>(epochs), static_cast<Real>(lr), cost,
+                            static_cast<Real>(lambda), [&](const std::size_t, const Real) { ++seen; }, learn_seed);
+        *epochs_seen_gpu = seen;
+        // the device tensors convert back unchanged (GpuDC::to_host)
+        const Tensor back = GpuDC::to_host(d_items[0]);
+        if (!(back == items[0])) throw std::runtime_error("GpuDC::to_host(GpuDC::from_host(t)) != t");
+
+        const auto pc = dlb200_binding::flatten_params(net_cpu), pg = dlb200_binding::flatten_params(net_gpu);
+        std::memcpy(params_cpu, pc.data(), pc.size() * sizeof(Real));
+        std::memcpy(params_gpu, pg.data(), pg.size() * sizeof(Real));
+        for (int64_t i = 0; i < n_items; ++i) {   // predictions of both trained nets by the reference's own inference
+            classes_cpu[i] = static_cast<int32_t>(net_cpu.act(items[i]).max_element_id());
+            classes_gpu[i] = static_cast<int32_t>(net_gpu.act(items[i]).max_element_id());
+        }
+        const auto ev = DeepLearning::evaluate_cost_function_and_correct_answers(net_gpu, items, refs, cost, Real(0));
+        *eval_cost_gpu = ev.Cost; *eval_correct_gpu = ev.CorrectAnswers;
+        return 0;
+    } catch (const std::runtime_error& e) { g_err = e.what(); return 2; } catch (...) { g_err = "unknown exception"; return 3; }
+}
+
+int64_t rad_param_count(const dlb_layer_spec* specs, int n_layers) {
+    try {
+        Net<CpuDC> net; build(net, specs, n_layers);
+        return static_cast<int64_t>(dlb200_binding::flatten_params(net).size());
+    } catch (const std::runtime_error& e) { g_err = e.what(); return -1; } catch (...) { g_err = "unknown exception"; return -1; }
+}
+
+}  // extern "C"

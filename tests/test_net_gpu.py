@@ -159,8 +159,11 @@ def test_argument_errors_are_loud():
 
 def test_plans():
     """LeNet and the MLP take the fused path; nets outside its grammar take the generic operators."""
-    assert dl.lenet("f32").describe_plan().startswith("fused: one cooperative kernel per step")
-    assert dl.lenet("f64").describe_plan().startswith("fused: conv_pool(5x5")
+    assert dl.lenet("f32").describe_plan().startswith("fused: conv_pool(5x5")
+    net = dl.lenet("f32"); net.enable_step_kernel(True)
+    assert net.describe_plan().startswith("fused: one cooperative kernel per step")
+    net64 = dl.lenet("f64"); net64.enable_step_kernel(True)      # the step kernel is float-only: nothing changes
+    assert net64.describe_plan().startswith("fused: conv_pool(5x5")
     assert dl.Net([H.to_dl_spec(s) for s in MINI_MLP], real="f64").describe_plan().startswith("fused:")
     assert dl.Net([H.to_dl_spec(s) for s in MINI_LENET], real="f32").describe_plan().startswith("fused: conv_pool(3x3")
     assert dl.Net([H.to_dl_spec(s) for s in FIXTURE_NET], real="f32").describe_plan().startswith("unfused")

@@ -99,7 +99,52 @@ def run(batch: int):
     print(f"batch cost via step_host {cost:.6f} (oracle on the updated net {orc2_cost:.6f})")
 
 
+def profile(batch: int, steps: int = 20):
+    """DLB_MEGA_PROF=1: per-CTA clock64 stamps at the phase boundaries of the last step."""
+    import deeplearning_b200 as dl
+    from deeplearning_b200 import _capi
+    net = dl.lenet("f32")
+    net.init_params(seed=0)
+    rng = np.random.default_rng(1)
+    n = max(4096, 4 * batch)
+    x = rng.random((n, 784), dtype=np.float32); y = np.zeros((n, 10), np.float32); y[np.arange(n), np.arange(n) % 10] = 1
+    net.set_dataset(x, y)
+    net.reset_random_generator(0)
+    ctx = net.ctx
+    net.train_steps(batch, 5, 0.01, dl.CostFunctionId.CROSS_ENTROPY, 0.1)
+    ctx.synchronize()
+    e0, e1 = dl.Event(ctx), dl.Event(ctx)
+    e0.record(); net.train_steps(batch, steps, 0.01, dl.CostFunctionId.CROSS_ENTROPY, 0.1); e1.record()
+    ms = e0.elapsed_ms(e1)
+    print(f"batch {batch}: {1e3 * ms / steps:.2f} us/step over {steps} steps")
+    a = np.zeros(148 * 40, np.int64)
+    _capi.check(net.lib.dlb_net_read(net._handle(), 107, 0, a.ctypes.data, a.nbytes))
+    a = a.reshape(148, 40)
+    a = a[a[:, 1] != 0]
+    names = ["setup", "conv_fwd", "barrier", "fc1_fwd", "barrier", "head", "barrier", "fc1_bwd(+dW)", "barrier wait", "conv_bwd", "barrier", "update"]
+    d = np.diff(a[:, :13], axis=1) / 1965.0
+    print(f"  {len(a)} CTAs; per-CTA intervals in us (mean / min / max), SM clock assumed 1965 MHz")
+    for i, nm in enumerate(names):
+        print(f"  {nm:14s} {d[:, i].mean():7.2f} {d[:, i].min():7.2f} {d[:, i].max():7.2f}")
+    print(f"  total          {((a[:, 12] - a[:, 0]) / 1965.0).mean():7.2f}")
+    c0 = a[0]
+    def rel(slot, base): return (c0[slot] - c0[base]) / 1965.0
+    print("  CTA 0 inside conv_fwd (us after phase start): copies landed %.2f, synced %.2f, FFMA loop done %.2f, phase end %.2f" % (rel(13, 1), rel(14, 1), rel(15, 1), rel(2, 1)))
+    print("  CTA 0 inside conv_bwd (us after phase start): staged %.2f, landed+synced %.2f, FFMA loop done %.2f, bias sums done %.2f, phase end %.2f" %
+          (rel(28, 9), rel(29, 9), rel(30, 9), rel(31, 9), rel(10, 9)))
+    print("  CTA 0 inside head (us after phase start): operands staged %.2f, synced %.2f, forward+cost done %.2f, gradient+partials done %.2f, phase end %.2f" %
+          (rel(16, 5), rel(17, 5), rel(18, 5), rel(19, 5), rel(6, 5)))
+    if c0[35]: print("  head run a second time (warm instruction cache): %.2f us" % ((c0[35] - c0[34]) / 1965.0))
+    print("  CTA 0 inside fc1_bwd (us after phase start): start %.2f, operands landed %.2f, mma issue %.2f, dX mma done %.2f, dX stored %.2f, arrived %.2f, dW issued %.2f, dW done %.2f, phase end %.2f" %
+          tuple(rel(k, 7) for k in (20, 21, 22, 23, 24, 25, 26, 27, 8)))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "prof":
+        os.environ["DLB_MEGA_PROF"] = "1"
+        for b in [int(v) for v in sys.argv[2:]] or [256]:
+            profile(b)
+        sys.exit(0)
     batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     if os.environ.get("MEGA_DEBUG_CHILD"):
         run(batch)
