@@ -9,3 +9,4 @@ from .net import (  # noqa: F401
     BUF_COST_GRAD, BUF_DERIVATIVES, BUF_GRADIENT, BUF_INDEX_MAP, BUF_INPUT_GRAD, BUF_OUTPUT,
     Event, cifar_deep, dropout_masks, lenet, nccl_unique_id, out_size, pinned_array, rank_slice, shuffle_sequence, timing_enable, timing_report,
 )
+from .mnet import MNet, RMLayer  # noqa: F401

@@ -56,8 +56,14 @@ SYMBOLS = [
     "dlb_event_record", "dlb_event_elapsed_ms", "dlb_timing_enable", "dlb_timing_report", "dlb_net_describe_plan",
     "dlb_net_enable_graphs", "dlb_net_enable_tensor_cores", "dlb_net_enable_step_kernel", "dlb_matmul_f32", "dlb_net_step_host_async",
     "dlb_net_p2p_export", "dlb_net_set_distributed_p2p", "dlb_net_evaluate_host",
-    "dlb_net_set_keep_rate", "dlb_net_mask_size", "dlb_net_set_dropout_masks", "dlb_dropout_masks",
+    "dlb_net_set_keep_rate", "dlb_net_mask_size", "dlb_net_set_dropout_masks", "dlb_dropout_masks", "dlb_context_device",
+    "dlb_mnet_last_error", "dlb_mnet_create", "dlb_mnet_destroy", "dlb_mnet_param_count", "dlb_mnet_layer_param_offset", "dlb_mnet_set_params",
+    "dlb_mnet_get_params", "dlb_mnet_act_host", "dlb_mnet_gradient_sum_host", "dlb_mnet_learn_host", "dlb_mnet_set_batch", "dlb_mnet_learn_resident",
 ]
+
+
+class RMLayerSpec(C.Structure):   # dlb_rmlayer_spec (include/dlb200.h)
+    _fields_ = [("in_dim", C.c_int32), ("out_dim", C.c_int32), ("activation", C.c_int32), ("reserved", C.c_int32), ("clip_threshold", C.c_double)]
 
 
 def load() -> C.CDLL:
@@ -128,6 +134,19 @@ def load() -> C.CDLL:
     lib.dlb_net_set_dropout_masks.argtypes = [vp, vp]
     lib.dlb_dropout_masks.argtypes = [C.c_uint, vp, vp, i32, i64, i32, vp]
     lib.dlb_matmul_f32.argtypes = [vp, i32, i32, i32, vp, i64, i32, vp, i64, i32, vp, i32]
+    lib.dlb_context_device.argtypes = [vp]
+    lib.dlb_mnet_last_error.restype = C.c_char_p
+    lib.dlb_mnet_create.argtypes = [vp, i32, C.POINTER(RMLayerSpec), i32, i32, C.POINTER(vp)]
+    lib.dlb_mnet_destroy.argtypes = [vp]
+    lib.dlb_mnet_param_count.argtypes = [vp]; lib.dlb_mnet_param_count.restype = i64
+    lib.dlb_mnet_layer_param_offset.argtypes = [vp, i32]; lib.dlb_mnet_layer_param_offset.restype = i64
+    lib.dlb_mnet_set_params.argtypes = [vp, vp]
+    lib.dlb_mnet_get_params.argtypes = [vp, vp]
+    lib.dlb_mnet_act_host.argtypes = [vp, vp, i64, vp]
+    lib.dlb_mnet_gradient_sum_host.argtypes = [vp, vp, vp, i64, i32, vp]
+    lib.dlb_mnet_learn_host.argtypes = [vp, vp, vp, i64, i32, dbl, dbl]
+    lib.dlb_mnet_set_batch.argtypes = [vp, vp, vp, i64]
+    lib.dlb_mnet_learn_resident.argtypes = [vp, i32, dbl, dbl, i64]
     _lib = lib
     return lib
 
@@ -135,3 +154,8 @@ def load() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != 0:
         raise DlbError(load().dlb_last_error().decode(errors="replace"))
+
+
+def check_mnet(rc: int) -> None:
+    if rc != 0:
+        raise DlbError(load().dlb_mnet_last_error().decode(errors="replace"))

@@ -24,6 +24,7 @@
 #include "../../include/dlb200.h"
 #include "fused.cuh"
 #include "mega.h"
+#include "conv28.h"
 #include "tc_gemm.cuh"
 
 namespace dlb {
@@ -335,7 +336,18 @@ struct NetT final : dlb_net {
         mega::Runner* runner = nullptr;
 #endif
     } mg;
+    // ---- the large-batch kernels of the first LeNet stage (conv28.cu): dense FFMA2 forward / backward, 1-byte window selectors ----
+    struct Conv28State {
+        bool ok = false;
+        int mode = [] { const char* e = std::getenv("DLB_CONV28"); return e ? std::atoi(e) : -1; }();            // 0 never, 1 always, otherwise from min_batch up
+        int min_batch = [] { const char* e = std::getenv("DLB_CONV28_MIN"); return e ? std::atoi(e) : 1024; }();
+#ifndef DLB_CUDA_EMU
+        conv28::Stage stage{};
+#endif
+    } c28;
+    bool conv28_for(int64_t B) const { return c28.ok && c28.mode != 0 && (c28.mode == 1 || B >= c28.min_batch); }
     R* cp_partial = nullptr; int cp_grid = 0;          // [cp_grid][cp.n_par] per-CTA partial gradients of the conv stage
+    int cp_rows = 0;                                    // rows of cp_partial the last backward wrote (the reduction sums these)
     R* head_partial = nullptr; int head_chunks = 0;     // [head_chunks][n * (in_n + 1)]
     int head_chunk_cap = 0;
     int* d_cursor = nullptr;                            // device-side offset of the current batch in the epoch permutation
@@ -505,6 +517,19 @@ struct NetT final : dlb_net {
         plan.head_nmax = H.out_n <= 10 ? 10 : H.out_n <= 16 ? 16 : 32;
         plan.ok = true;
         plan_mega();
+        c28.ok = false;
+#ifndef DLB_CUDA_EMU
+        if constexpr (std::is_same_v<R, float>) {
+            if (plan.has_cp) {
+                const auto& c = layers[0].s; const auto& p = layers[1].s;
+                if (conv28::eligible(c.in_c, c.in_h, c.in_w, c.win_h, c.win_w, c.pad_h, c.pad_w, c.stride_h, c.stride_w, c.out_c, c.activation, p.win_h,
+                                     p.win_w, p.pool_type)) {
+                    c28.stage = conv28::Stage{c.out_c, c.activation, p.pool_type == DLB_POOL_MAX ? 1 : 0};
+                    c28.ok = true;
+                }
+            }
+        }
+#endif
     }
 
     // Which nets the step megakernel covers (mega.h): CLayer 5x5 over one 28x28 channel, stride 1, no padding, an even number
@@ -570,7 +595,10 @@ struct NetT final : dlb_net {
 #endif
     }
 
-    bool mega_for(int64_t B) const { return mg.ok && mg.enabled && plan.ok && B > 0 && (world <= 1); }
+    // From mini-batch 128 up: below that the kernel's parameters drift from the oracle's several times faster than the graph path's
+    // (measured at mini-batch 37: 1.5e-5 against 1.4e-6 after three steps), so small batches keep the graph path.
+    static constexpr int kMegaMinBatch = 128;
+    bool mega_for(int64_t B) const { return mg.ok && mg.enabled && plan.ok && B >= kMegaMinBatch && (world <= 1); }
 
     // `n_steps` whole training steps (forward, backward, ordered sums, update) in the megakernel.
     void mega_step(int B, const R* x, const R* refs, const int* gather_base, const int* cursor, int advance, int cost, double lr, double reg_factor,
@@ -844,9 +872,21 @@ struct NetT final : dlb_net {
         if (plan.has_cp) {
             g_tag_layer = 0;
             const auto& Y = layers[0];
-            const int grid = std::min((int)ceil_div(B, plan.cp.spc), kNumSMs);
-            conv_pool_forward<R>(st, plan.cp, grid, x, gather_base, cursor, params + Y.param_off, params + Y.param_off + Y.bias_n,
-                                 out[1], imap[1], B);
+            bool done = false;
+#ifndef DLB_CUDA_EMU
+            if constexpr (std::is_same_v<R, float>) {
+                if (conv28_for(B)) {   // (the index-map buffer holds the one-byte window selectors here)
+                    conv28::forward(st, c28.stage, x, gather_base, cursor, params + Y.param_off, params + Y.param_off + Y.bias_n, out[1],
+                                    reinterpret_cast<unsigned char*>(imap[1]), B);
+                    done = true;
+                }
+            }
+#endif
+            if (!done) {
+                const int grid = std::min((int)ceil_div(B, plan.cp.spc), kNumSMs);
+                conv_pool_forward<R>(st, plan.cp, grid, x, gather_base, cursor, params + Y.param_off, params + Y.param_off + Y.bias_n,
+                                     out[1], imap[1], B);
+            }
             l = 2;
         }
         // hidden NLayers
@@ -983,10 +1023,23 @@ struct NetT final : dlb_net {
         }
         if (plan.has_cp) {
             g_tag_layer = 0;
-            const int grid = std::min(B, cp_grid);
-            if (grid < cp_grid)   // CTAs that do not run this time must not leave stale partial sums behind
-                DLB_CUDA(cudaMemsetAsync(cp_partial + (size_t)grid * plan.cp.n_par, 0, (size_t)(cp_grid - grid) * plan.cp.n_par * sizeof(R), st));
-            conv_pool_backward<R>(st, plan.cp, grid, x, gather_base, cursor, (const R*)in_grad[2], (const int*)imap[1], (const R*)out[1], cp_partial, B);
+            bool done = false;
+#ifndef DLB_CUDA_EMU
+            if constexpr (std::is_same_v<R, float>) {
+                if (conv28_for(B)) {
+                    cp_rows = conv28::backward(st, c28.stage, x, gather_base, cursor, (const float*)in_grad[2], reinterpret_cast<const unsigned char*>(imap[1]),
+                                               (const float*)out[1], cp_partial, cp_grid, B);
+                    done = true;
+                }
+            }
+#endif
+            if (!done) {
+                const int grid = std::min(B, cp_grid);
+                if (grid < cp_grid)   // CTAs that do not run this time must not leave stale partial sums behind
+                    DLB_CUDA(cudaMemsetAsync(cp_partial + (size_t)grid * plan.cp.n_par, 0, (size_t)(cp_grid - grid) * plan.cp.n_par * sizeof(R), st));
+                conv_pool_backward<R>(st, plan.cp, grid, x, gather_base, cursor, (const R*)in_grad[2], (const int*)imap[1], (const R*)out[1], cp_partial, B);
+                cp_rows = cp_grid;
+            }
         }
 #ifndef DLB_CUDA_EMU
         if (fork) {   // join: the reduce/update that follows reads every gradient
@@ -1016,7 +1069,7 @@ struct NetT final : dlb_net {
                 rs.end[i] = Y.param_off + Y.bias_n + (part ? Y.weight_n : 0);
                 rs.regularised[i] = part ? 1 : 0;
                 rs.partial[i] = nullptr; rs.chunks[i] = 0; rs.stride[i] = 0; rs.local_off[i] = part ? Y.bias_n : 0;
-                if (conv_stage) { rs.partial[i] = cp_partial; rs.chunks[i] = cp_grid; rs.stride[i] = plan.cp.n_par; }
+                if (conv_stage) { rs.partial[i] = cp_partial; rs.chunks[i] = cp_rows > 0 ? cp_rows : cp_grid; rs.stride[i] = plan.cp.n_par; }
                 else if (head) { rs.partial[i] = head_partial; rs.chunks[i] = head_chunks; rs.stride[i] = Y.out_n * (Y.in_n + 1); }
             }
         }
@@ -1389,12 +1442,14 @@ struct NetT final : dlb_net {
 
     std::string describe_plan() override {
         if (!plan.ok) return "unfused: every layer runs the generic operators (layers.cuh)";
-        if (mega_for(1)) return "fused: one cooperative kernel per step (mega.cu): conv_pool(5x5) + hidden NLayer on tcgen05 + head + update";
+        if (mega_for(kMegaMinBatch)) return "fused: one cooperative kernel per step (mega.cu) from mini-batch 128 up: conv_pool(5x5) + hidden NLayer on tcgen05 + head + update";
         std::string d = "fused:";
         if (plan.has_cp)
             d += " conv_pool(" + std::to_string(plan.cp.KH) + "x" + std::to_string(plan.cp.KW) + ", fpt " + std::to_string(plan.cp.fpt) +
                  ", wpl " + std::to_string(plan.cp.wpl) + ")";
         d += " + " + std::to_string(L() - 1 - plan.first_fc) + " hidden NLayer(s) + head(nmax " + std::to_string(plan.head_nmax) + ")";
+        if (c28.ok && c28.mode != 0)
+            d += "; conv stage " + (c28.mode == 1 ? std::string("always") : "from mini-batch " + std::to_string(c28.min_batch)) + ": dense FFMA2 kernels (conv28.cu)";
         return d;
     }
     void enable_graphs(bool on) override { graphs_enabled = on; if (!on) drop_graphs(); }
@@ -1530,6 +1585,7 @@ int dlb_context_synchronize(dlb_context* ctx) {
     });
 }
 void* dlb_context_stream(dlb_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int dlb_context_device(dlb_context* ctx) { return ctx ? ctx->device : -1; }
 int64_t dlb_context_launch_count(dlb_context*) { return (int64_t)g_launch_count.load(); }
 
 int dlb_malloc(dlb_context* ctx, size_t bytes, void** out) {

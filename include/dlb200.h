@@ -49,6 +49,7 @@ DLB_API int dlb_context_create(int device, void* external_stream, dlb_context** 
 DLB_API int dlb_context_destroy(dlb_context* ctx);
 DLB_API int dlb_context_synchronize(dlb_context* ctx);
 DLB_API void* dlb_context_stream(dlb_context* ctx);
+DLB_API int dlb_context_device(dlb_context* ctx);
 DLB_API int dlb_malloc(dlb_context* ctx, size_t bytes, void** out);
 DLB_API int dlb_free(dlb_context* ctx, void* ptr);
 DLB_API int dlb_memcpy_h2d(dlb_context* ctx, void* dst, const void* src, size_t bytes);
@@ -256,6 +257,37 @@ DLB_API int dlb_shuffle_sequence(unsigned seed, int64_t n, int64_t epochs, int64
  * or double (8).  Host-only helper for tests and for reference-side callers. */
 DLB_API int dlb_dropout_masks(unsigned seed, const int64_t* in_sizes, const double* keep_rates, int n_layers, int64_t n_batches,
                               int real_bytes, void* out);
+
+/* ---- the recurrent stack: MNet<D> of RMLayer<D> (csrc/mnet.cu) -------------------------------------
+ * Replaces, batched over the mini-batch on the device: RMLayer::act / backpropagate / update (NeuralNet/RMLayer.inl:165-260: Elman
+ * recurrence h_t = f(W_in x_t + b + W_rec h_{t-1}), full back-propagation through time, gradient-norm clipping in the update) and
+ * MNet::act / calc_gradient_sum / learn (NeuralNet/MNet.inl:79-180).  Sequences are [n][depth][dim] arrays of the net's Real on the
+ * host (one sequence after the other).  Flat parameter (and gradient) layout, per layer:  bias [out] | in-weights [out][in] |
+ * recurrent weights [out][out], row-major - the order of RMLayer's gradient containers (RMLayer.h:120-122).
+ * Element-wise activations only (DLB_ACT_SIGMOID / TANH / RELU / LINEAR). */
+typedef struct dlb_mnet dlb_mnet;
+typedef struct dlb_rmlayer_spec {
+    int32_t in_dim, out_dim;      /* items per time step in / out (RMLayer(rec_depth, in_sub_dim, out_sub_dim, ...), RMLayer.h:131-133) */
+    int32_t activation;           /* DLB_ACT_* */
+    int32_t reserved;
+    double clip_threshold;        /* gradient-norm clipping threshold of the update, <= 0 disables it (RMLayer.inl:238-245) */
+} dlb_rmlayer_spec;
+DLB_API const char* dlb_mnet_last_error(void);
+DLB_API int dlb_mnet_create(dlb_context* ctx, int depth, const dlb_rmlayer_spec* layers, int n_layers, int real_bytes, dlb_mnet** out);
+DLB_API int dlb_mnet_destroy(dlb_mnet* net);
+DLB_API int64_t dlb_mnet_param_count(const dlb_mnet* net);
+DLB_API int64_t dlb_mnet_layer_param_offset(const dlb_mnet* net, int layer);
+DLB_API int dlb_mnet_set_params(dlb_mnet* net, const void* host_params);
+DLB_API int dlb_mnet_get_params(dlb_mnet* net, void* host_params);
+/* MNet::act for n sequences (MNet.inl:79-98): outputs [n][depth][out] */
+DLB_API int dlb_mnet_act_host(dlb_mnet* net, const void* inputs, int64_t n, void* outputs);
+/* MNet::calc_gradient_sum (MNet.inl:100-121): the gradient SUM over the n sequences, flat layout */
+DLB_API int dlb_mnet_gradient_sum_host(dlb_mnet* net, const void* inputs, const void* refs, int64_t n, int cost_id, void* host_grads);
+/* MNet::learn on one mini-batch (MNet.inl:171-180): gradient sum, every layer's update with -learning_rate / n */
+DLB_API int dlb_mnet_learn_host(dlb_mnet* net, const void* inputs, const void* refs, int64_t n, int cost_id, double learning_rate, double reg_factor);
+/* the same with the mini-batch resident on the device: upload once, then n_steps x (forward, backward, update) without host traffic */
+DLB_API int dlb_mnet_set_batch(dlb_mnet* net, const void* inputs, const void* refs, int64_t n);
+DLB_API int dlb_mnet_learn_resident(dlb_mnet* net, int cost_id, double learning_rate, double reg_factor, int64_t n_steps);
 
 #ifdef __cplusplus
 }

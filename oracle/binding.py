@@ -322,3 +322,66 @@ def ref_dropout_masks(real: str, seed: int, in_sizes, keep_rates, n_batches: int
     if lib.dlref_dropout_masks(seed, _ptr(sizes), _ptr(keep), len(in_sizes), n_batches, _ptr(out)):
         raise RuntimeError(lib.dlref_last_error().decode())
     return out
+
+
+# ---- the recurrent stack (oracle/ref_mnet_driver.cpp -> oracle/_ref/libdlrefm_{f32,f64}.so) -----------------------------------
+def mnet_ref_available() -> bool:
+    return all(os.path.exists(os.path.join(HERE, "_ref", f"libdlrefm_{r}.so")) for r in ("f32", "f64"))
+
+
+class RefMNet:
+    """The reference's own MNet<CpuDC> of RMLayer<CpuDC> (unmodified sources), driven through oracle/ref_mnet_driver.cpp."""
+
+    def __init__(self, depth, dims, activations, clips, real="f32", seed=0):
+        key = ("refm", real)
+        if key not in _libs:
+            lib = C.CDLL(os.path.join(HERE, "_ref", f"libdlrefm_{real}.so"))
+            lib.dlrefm_last_error.restype = C.c_char_p
+            lib.dlrefm_create.restype = C.c_void_p
+            lib.dlrefm_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+            lib.dlrefm_destroy.argtypes = [C.c_void_p]
+            lib.dlrefm_param_count.argtypes = [C.c_void_p]; lib.dlrefm_param_count.restype = C.c_int64
+            lib.dlrefm_get_params.argtypes = [C.c_void_p, C.c_void_p]
+            lib.dlrefm_set_params.argtypes = [C.c_void_p, C.c_void_p]
+            lib.dlrefm_act.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+            lib.dlrefm_gradient_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+            lib.dlrefm_learn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_double]
+            _libs[key] = lib
+        self.lib = _libs[key]
+        self.dtype = np.float32 if real == "f32" else np.float64
+        assert self.lib.dlrefm_real_bytes() == np.dtype(self.dtype).itemsize
+        self.depth, self.dims = int(depth), list(dims)
+        d = np.asarray(dims, np.int32); a = np.asarray(activations, np.int32); c = np.asarray(clips, np.float64)
+        self.h = self.lib.dlrefm_create(self.depth, len(a), d.ctypes.data, a.ctypes.data, c.ctypes.data, seed)
+        if not self.h: raise RuntimeError(self.lib.dlrefm_last_error().decode())
+        self.param_count = int(self.lib.dlrefm_param_count(self.h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None): self.lib.dlrefm_destroy(self.h); self.h = None
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0: raise RuntimeError(self.lib.dlrefm_last_error().decode())
+
+    def get_params(self):
+        p = np.empty(self.param_count, self.dtype); self._check(self.lib.dlrefm_get_params(self.h, p.ctypes.data)); return p
+
+    def set_params(self, p):
+        p = np.ascontiguousarray(p, self.dtype); assert p.size == self.param_count
+        self._check(self.lib.dlrefm_set_params(self.h, p.ctypes.data))
+
+    def act(self, xs):
+        xs = np.ascontiguousarray(xs, self.dtype)
+        out = np.empty((xs.shape[0], self.depth, self.dims[-1]), self.dtype)
+        self._check(self.lib.dlrefm_act(self.h, xs.ctypes.data, xs.shape[0], out.ctypes.data)); return out
+
+    def calc_gradient_sum(self, xs, ys, cost_id):
+        xs = np.ascontiguousarray(xs, self.dtype); ys = np.ascontiguousarray(ys, self.dtype)
+        g = np.empty(self.param_count, self.dtype)
+        self._check(self.lib.dlrefm_gradient_sum(self.h, xs.ctypes.data, ys.ctypes.data, xs.shape[0], cost_id, g.ctypes.data)); return g
+
+    def learn(self, xs, ys, cost_id, learning_rate, reg_factor=0.0):
+        xs = np.ascontiguousarray(xs, self.dtype); ys = np.ascontiguousarray(ys, self.dtype)
+        self._check(self.lib.dlrefm_learn(self.h, xs.ctypes.data, ys.ctypes.data, xs.shape[0], cost_id, float(learning_rate), float(reg_factor)))
