@@ -121,12 +121,13 @@ def algorithmic_bytes(net, key: str, batch: int, sz: int) -> float | None:
     spec = net._specs[l]
     bias_n = out_n if spec.type != 3 else 0
     weight_n = n_par - bias_n
+    sel = 1 if kernel.startswith("conv28") else 4   # csrc/conv28.cu keeps one-byte window selectors instead of the int32 index map
     if tag == "conv_pool_fwd":   # fused CLayer + PLayer forward: input, pooled output, index map, parameters
         o1 = net.layer_out_size(l + 1)
-        return batch * (in_n * sz + o1 * sz + o1 * 4) + n_par * sz
+        return batch * (in_n * sz + o1 * sz + o1 * sel) + n_par * sz
     if tag == "conv_pool_bwd":   # pooled gradient, index map, pooled values, input; bias + filter gradient out
         o1 = net.layer_out_size(l + 1)
-        return batch * (o1 * sz + o1 * 4 + o1 * sz + in_n * sz) + n_par * sz
+        return batch * (o1 * sz + o1 * sel + o1 * sz + in_n * sz) + n_par * sz
     if tag == "head":            # x, reference, g, dx
         return batch * (in_n + 2 * out_n + in_n) * sz + n_par * sz
     if tag == "head_dW":
@@ -539,6 +540,48 @@ def main():
                 netm.close()
             except Exception as exc:
                 line["step_kernel"] = {"error": str(exc)[:200]}
+
+            # ---- BASELINE configs[3]: recurrent net (MNet of RMLayer), sequences of length 64, hidden size 256, mini-batch 512
+            try:
+                import time as _time
+                depth, dims4 = 64, [64, 256, 16]
+                rm = dl.MNet(depth, [dl.RMLayer(dims4[0], dims4[1]), dl.RMLayer(dims4[1], dims4[2])], real="f32", context=ctx)
+                p4 = rm.init_params(seed=0, scale=0.05)
+                rng4 = np.random.default_rng(5)
+                x4 = rng4.standard_normal((512, depth, dims4[0])).astype(np.float32); y4 = (rng4.random((512, depth, dims4[2])) * 2 - 1).astype(np.float32)
+                sq = dl.CostFunctionId.SQUARED_ERROR
+                rm.set_batch(x4, y4); rm.learn_resident(sq, 0.01, 0.0, 2); ctx.synchronize()
+                l0 = ctx.launch_count()
+                e0.record(); rm.learn_resident(sq, 0.01, 0.0, 8); e1.record()
+                ms4 = e0.elapsed_ms(e1) / 8
+                launches4 = (ctx.launch_count() - l0) / 8
+                t0 = _time.perf_counter()
+                for _ in range(4): rm.learn(x4, y4, sq, 0.01, 0.0)
+                ctx.synchronize()
+                ms4_host = (_time.perf_counter() - t0) * 1e3 / 4
+                flop4 = 0
+                for l in range(2):   # multiply-adds x 2, forward + the three backward contractions per weight matrix
+                    i_, h_ = dims4[l], dims4[l + 1]
+                    flop4 += 2 * depth * (i_ * h_ + h_ * h_) * (3 if l > 0 else 2) + 2 * depth * h_ * h_
+                c4 = {"workload": "MNet: RMLayer 64 -> 256 (tanh) -> RMLayer 256 -> 16 (tanh), sequences of length 64, squared error, gradient clipping 5, mini-batch 512 (BASELINE configs[3])",
+                      "value": 512 / (ms4 / 1e3), "unit": "sequences/s", "ms_per_step": ms4, "launches_per_step": launches4,
+                      "e2e": {"value": 512 / (ms4_host / 1e3), "unit": "sequences/s", "h2d_bytes_per_step": int(x4.nbytes + y4.nbytes), "d2h_bytes_per_step": 0,
+                              "api": "dlb_mnet_learn_host (pageable host batch in, timed by the host clock around 4 calls + synchronize)"},
+                      "fp32_tflops": 512 * flop4 / (ms4 / 1e3) / 1e12, "contractions": "gemm.cuh FFMA2 (the recurrence is 2 x 63 chained [512 x 256] x [256 x 256] contractions per layer)"}
+                try:
+                    from oracle import binding as _ob   # cpu_baseline leg: the reference's own MNet<CpuDC>::learn (sequential over the items)
+                    if _ob.mnet_ref_available():
+                        refm = _ob.RefMNet(depth, dims4, [_ob.TANH, _ob.TANH], [5.0, 5.0], "f32", seed=0)
+                        refm.set_params(p4)
+                        nref = 8
+                        t0 = _time.perf_counter(); refm.learn(x4[:nref], y4[:nref], _ob.SQUARED_ERROR, 0.01, 0.0); dt = _time.perf_counter() - t0
+                        c4["cpu_baseline"] = {"value": nref / dt, "unit": "sequences/s", "cores": 1, "kind": "reference",
+                                              "sample": f"MNet<CpuDC>::learn on {nref} of the 512 sequences (the reference walks the items sequentially, MNet.inl:106-121)"}
+                except Exception as exc:
+                    c4["cpu_baseline"] = {"error": str(exc)[:200]}
+                line["config4"] = c4
+            except Exception as exc:
+                line["config4"] = {"error": str(exc)[:200]}
 
         r = run_reference(args.real, 256, 64, 2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],

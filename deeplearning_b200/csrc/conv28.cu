@@ -27,6 +27,7 @@
 #include "conv28.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "fused.cuh"
@@ -35,12 +36,14 @@ namespace dlb {
 namespace conv28 {
 
 constexpr int IW = 28, OHW = 24, PHW = 12, NPOS = 144, NPIX = 576, IMG = 784, KK = 25;
+// (A bank-conflict-free swizzled image layout - 32-float rows, chunk c of row y rotated by 3 (y >> 2) + ... - was measured: the 3-way
+// conflicts of the 16-byte image loads in this natural layout are NOT what limits these kernels, 137.3 vs 138.5 us forward at 8192.)
 constexpr int kTasks = 18;                    // 6 x 3 blocks of 4 x 8 convolution outputs per sample
-constexpr int kBiasBlk = 33;                  // float2 slots per block in the staged untied bias (32 + 1: bank spread)
-constexpr int kFT = 384, kFS = kFT / kTasks;  // forward: threads, samples per pass (21)
+constexpr int kBiasBlk = 34;                  // float2 slots per block in the staged untied bias (32 + 2: 16-byte aligned blocks, 4 banks apart)
+constexpr int kFTBig = 512, kFTSmall = 384;   // forward: threads per CTA (512: 128 registers, 4 warps per scheduler - from mini-batch 2048 up; 384: finer passes)
 constexpr int kBT = 352, kBS = 19;            // backward: threads (342 compute), samples per pass
 constexpr int kMaxFpItem = 10;                // filter pairs a forward CTA keeps biases and taps for
-constexpr int kFwdSmem = 2 * kFS * IMG * 4 + kMaxFpItem * kTasks * kBiasBlk * 8 + kMaxFpItem * 2 * KK * 4;
+constexpr int fwd_smem(int threads) { return 2 * (threads / kTasks) * IMG * 4 + kMaxFpItem * kTasks * kBiasBlk * 8 + kMaxFpItem * 2 * KK * 4; }
 constexpr int kBwdBuf = kBS * (IMG * 4 + 2 * NPOS * 4 * 2 + 2 * NPOS);   // images | pooled values | pooled gradients | selectors
 constexpr int kBwdSmem = 2 * kBwdBuf;
 static_assert(kBwdBuf % 16 == 0, "staging buffers must stay 16-byte aligned");
@@ -75,11 +78,37 @@ struct FwdArgs {
     int B, F, act, is_max, n_fsplit, fp_per_item, n_pass;
 };
 
-template <bool RELU>
+// One 2 x 2 window of one filter: activation + strict first-wins extremum (Tensor.cpp:700-709).  RELU_MAX is the benchmark's pair
+// (ReLU, max): the comparison chain runs on the rectified values directly; the general form compares sign * value and knows "no candidate".
+template <bool RELU_MAX>
+__device__ __forceinline__ void pool_window(const float (&z)[4], int act, float sign, float& value, unsigned& sel) {
+    if (RELU_MAX) {
+        const float v0 = fmaxf(z[0], 0.f), v1 = fmaxf(z[1], 0.f), v2 = fmaxf(z[2], 0.f), v3 = fmaxf(z[3], 0.f);
+        float m = v0; unsigned q = 0u;
+        if (m < v1) { m = v1; q = 1u; }
+        if (m < v2) { m = v2; q = 2u; }
+        if (m < v3) { m = v3; q = 3u; }
+        value = m; sel = q;
+    } else {
+        float best = -real_limits<float>::max(), bestv = 0.f;
+        unsigned bid = 255u;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            float d; const float v = apply_activation<float>(act, z[qd], d);
+            const float key = v * sign;
+            if (best < key) { best = key; bestv = v; bid = (unsigned)qd; }
+        }
+        value = bid == 255u ? (sign > 0.f ? -real_limits<float>::max() : real_limits<float>::max()) : bestv;
+        sel = bid;
+    }
+}
+
+template <bool RELU_MAX, int kFT>
 __global__ void __launch_bounds__(kFT, 1) conv28_forward_kernel(const FwdArgs a) {
+    constexpr int kFS = kFT / kTasks;   // samples per pass (28 | 21)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* img = reinterpret_cast<float*>(smem_raw);                                         // [2][kFS][784]
-    float2* bias2 = reinterpret_cast<float2*>(smem_raw + 2 * kFS * IMG * 4);                 // [pairs][18 blocks][33] (filter 2p, filter 2p + 1)
+    float2* bias2 = reinterpret_cast<float2*>(smem_raw + 2 * kFS * IMG * 4);                 // [pairs][18 blocks][34] (filter 2p, filter 2p + 1)
     float* wsm = reinterpret_cast<float*>(bias2 + kMaxFpItem * kTasks * kBiasBlk);           // [pairs][2][25]
     const int* gather = resolve_gather(a.gather_base, a.cursor);
     const int tid = threadIdx.x;
@@ -89,7 +118,7 @@ __global__ void __launch_bounds__(kFT, 1) conv28_forward_kernel(const FwdArgs a)
     if (nfp <= 0 || col >= a.n_pass) return;
     load_images<kFT / 32>(a.x, gather, img, col * kFS, min(kFS, a.B - col * kFS));
     cp_commit();
-    {   // the subset's untied biases, staged per 4 x 8 block of outputs (blocks 33 pairs apart: the lanes of a warp hit distinct banks), and taps
+    {   // the subset's untied biases, staged per 4 x 8 block of outputs (blocks 34 pairs apart: 16-byte aligned, the lanes of a warp hit distinct banks), and taps
         const float* bias = a.bias + (size_t)(2 * fp0) * NPIX;
         for (int i = tid; i < nfp * NPIX; i += kFT) {
             const int p = i / NPIX, pos = i - p * NPIX;
@@ -138,34 +167,27 @@ __global__ void __launch_bounds__(kFT, 1) conv28_forward_kernel(const FwdArgs a)
                         for (int c = 0; c < 8; ++c) acc[dy][c] = ffma2_bcast(w[ky * 5 + kx], xr[c + kx], acc[dy][c]);
                 }
             }
-            // bias (CLayer.inl:130), activation, 2 x 2 window with the strict first-wins compare; min pooling compares -v
-            const float2* bz2 = bias2 + (p * kTasks + blk) * kBiasBlk;
+            // bias last (CLayer.inl:130; same bits as the small-batch kernel), activation, 2 x 2 window
+            const float4* bz4 = reinterpret_cast<const float4*>(bias2 + (p * kTasks + blk) * kBiasBlk);   // [4 rows][4 column pairs] of (f0, f1, f0, f1)
             const int f0 = 2 * (fp0 + p);
+            const size_t o0 = ((size_t)(s0 + s) * a.F + f0) * NPOS + (2 * by) * PHW + 4 * bx;
 #pragma unroll
-            for (int fi = 0; fi < 2; ++fi) {
+            for (int wy = 0; wy < 2; ++wy) {
+                float vals[2][4]; unsigned sb[2][4];
 #pragma unroll
-                for (int wy = 0; wy < 2; ++wy) {
-                    float vals[4]; unsigned sb[4];
+                for (int wx = 0; wx < 4; ++wx) {
+                    const float4 bt = bz4[(2 * wy) * 4 + wx], bb = bz4[(2 * wy + 1) * 4 + wx];
+                    const f32x2 a00 = acc[2 * wy][2 * wx], a01 = acc[2 * wy][2 * wx + 1], a10 = acc[2 * wy + 1][2 * wx], a11 = acc[2 * wy + 1][2 * wx + 1];
+                    const float za[4] = {lo_of(a00) + bt.x, lo_of(a01) + bt.z, lo_of(a10) + bb.x, lo_of(a11) + bb.z};
+                    const float zb[4] = {hi_of(a00) + bt.y, hi_of(a01) + bt.w, hi_of(a10) + bb.y, hi_of(a11) + bb.w};
+                    pool_window<RELU_MAX>(za, a.act, sign, vals[0][wx], sb[0][wx]);
+                    pool_window<RELU_MAX>(zb, a.act, sign, vals[1][wx], sb[1][wx]);
+                }
 #pragma unroll
-                    for (int wx = 0; wx < 4; ++wx) {
-                        float best = -real_limits<float>::max(), bestv = 0.f;
-                        unsigned bid = 255u;
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) {
-                            const int rr = 2 * wy + (qd >> 1), cc = 2 * wx + (qd & 1);
-                            const float2 bz = bz2[rr * 8 + cc];
-                            const float z = (fi ? hi_of(acc[rr][cc]) : lo_of(acc[rr][cc])) + (fi ? bz.y : bz.x);
-                            float v, d;
-                            if (RELU) v = z > 0.f ? z : 0.f; else v = apply_activation<float>(a.act, z, d);
-                            const float key = v * sign;
-                            if (best < key) { best = key; bestv = v; bid = (unsigned)qd; }
-                        }
-                        vals[wx] = bid == 255u ? (sign > 0.f ? -real_limits<float>::max() : real_limits<float>::max()) : bestv;
-                        sb[wx] = bid;
-                    }
-                    const size_t o = ((size_t)(s0 + s) * a.F + f0 + fi) * NPOS + (2 * by + wy) * PHW + 4 * bx;
-                    *reinterpret_cast<float4*>(a.pooled + o) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-                    *reinterpret_cast<uchar4*>(a.sel + o) = make_uchar4((unsigned char)sb[0], (unsigned char)sb[1], (unsigned char)sb[2], (unsigned char)sb[3]);
+                for (int fi = 0; fi < 2; ++fi) {
+                    const size_t o = o0 + (size_t)fi * NPOS + wy * PHW;
+                    *reinterpret_cast<float4*>(a.pooled + o) = make_float4(vals[fi][0], vals[fi][1], vals[fi][2], vals[fi][3]);
+                    *reinterpret_cast<unsigned*>(a.sel + o) = sb[fi][0] | (sb[fi][1] << 8) | (sb[fi][2] << 16) | (sb[fi][3] << 24);
                 }
             }
         }
@@ -178,7 +200,7 @@ __global__ void __launch_bounds__(kFT, 1) conv28_forward_kernel(const FwdArgs a)
 // ---------------------------------------------------------------------------------------------------------------
 struct BwdArgs {
     const float* x; const int* gather_base; const int* cursor; const float* dpool; const unsigned char* sel; const float* pooled; float* partial;
-    int B, F, act, G, n_par;
+    int B, F, act, G, n_par, stagger;
 };
 
 __global__ void __launch_bounds__(kBT, 1) conv28_backward_kernel(const BwdArgs a) {
@@ -216,6 +238,7 @@ __global__ void __launch_bounds__(kBT, 1) conv28_backward_kernel(const BwdArgs a
 #pragma unroll
     for (int t = 0; t < KK; ++t) dk[t] = pack2(0.f, 0.f);
     float db[4] = {0.f, 0.f, 0.f, 0.f};   // threads < 288: the untied-bias gradient of the four positions of window tid of the pair
+    const bool bias_first = warp >= 4 && a.stagger;
     for (int p = 0; p < n_pass; ++p) {
         cp_wait_all();
         __syncthreads();
@@ -227,6 +250,19 @@ __global__ void __launch_bounds__(kBT, 1) conv28_backward_kernel(const BwdArgs a
         const float* pv = reinterpret_cast<const float*>(buf + kOffPv);
         const float* gv = reinterpret_cast<const float*>(buf + kOffGv);
         const unsigned char* sb = buf + kOffSb;
+        // untied bias: window tid of the pair, the samples in order.  Warps 4 and up run it BEFORE their multiply-adds, warps 0-3 after:
+        // out of the barrier the FMA pipe of a scheduler then serves one warp while the other two are in their latency-bound parts.
+        auto bias_sums = [&] {
+            if (tid < 2 * NPOS) {
+                for (int ss = 0; ss < ns; ++ss) {
+                    const unsigned q = sb[ss * 2 * NPOS + tid];
+                    const float gz = deriv_from_value<float>(a.act, pv[ss * 2 * NPOS + tid]) * gv[ss * 2 * NPOS + tid];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) db[k] += q == (unsigned)k ? gz : 0.f;
+                }
+            }
+        };
+        if (bias_first) bias_sums();
         if (s < ns) {
             // the thread's 4 x 8 positions of dC/dz as (filter f0, filter f0 + 1) pairs: the pooled gradient times the derivative
             // recomputed from the pooled value, at the window's arg-max position, zero elsewhere
@@ -267,14 +303,7 @@ __global__ void __launch_bounds__(kBT, 1) conv28_backward_kernel(const BwdArgs a
                 }
             }
         }
-        if (tid < 2 * NPOS) {   // untied bias: window tid of the pair, the samples in order
-            for (int ss = 0; ss < ns; ++ss) {
-                const unsigned q = sb[ss * 2 * NPOS + tid];
-                const float gz = deriv_from_value<float>(a.act, pv[ss * 2 * NPOS + tid]) * gv[ss * 2 * NPOS + tid];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) db[k] += q == (unsigned)k ? gz : 0.f;
-            }
-        }
+        if (!bias_first) bias_sums();
     }
     cp_wait_all();
     __syncthreads();
@@ -327,6 +356,8 @@ void forward(cudaStream_t st, const Stage& s, const float* x, const int* gather_
     FwdArgs a{};
     a.x = x; a.gather_base = gather_base; a.cursor = cursor; a.bias = bias; a.filt = filt; a.pooled = pooled; a.sel = sel;
     a.B = B; a.F = s.F; a.act = s.act; a.is_max = s.is_max;
+    const bool big = B > 1024;
+    const int kFS = (big ? kFTBig : kFTSmall) / kTasks;
     a.n_pass = ceil_div(B, kFS);
     const int NFP = s.F / 2;
     // split of the filter pairs over CTAs: the fewest rounds of (passes per CTA column) x (pairs per CTA); ties go to the fewer splits
@@ -341,8 +372,15 @@ void forward(cudaStream_t st, const Stage& s, const float* x, const int* gather_
     if (best_cost < 0) throw std::runtime_error("conv28::forward: no decomposition");
     const int cols = std::min(a.n_pass, kNumSMs / a.n_fsplit);
     TagScope tag_("conv_pool_fwd");
-    if (s.act == DLB_ACT_RELU) DLB_LAUNCH_SMEM((conv28_forward_kernel<true>), dim3((unsigned)(cols * a.n_fsplit)), dim3(kFT), kFwdSmem, st, a);
-    else DLB_LAUNCH_SMEM((conv28_forward_kernel<false>), dim3((unsigned)(cols * a.n_fsplit)), dim3(kFT), kFwdSmem, st, a);
+    const dim3 grid((unsigned)(cols * a.n_fsplit));
+    const bool relu_max = s.act == DLB_ACT_RELU && s.is_max;
+    if (big) {
+        if (relu_max) DLB_LAUNCH_SMEM((conv28_forward_kernel<true, kFTBig>), grid, dim3(kFTBig), fwd_smem(kFTBig), st, a);
+        else DLB_LAUNCH_SMEM((conv28_forward_kernel<false, kFTBig>), grid, dim3(kFTBig), fwd_smem(kFTBig), st, a);
+    } else {
+        if (relu_max) DLB_LAUNCH_SMEM((conv28_forward_kernel<true, kFTSmall>), grid, dim3(kFTSmall), fwd_smem(kFTSmall), st, a);
+        else DLB_LAUNCH_SMEM((conv28_forward_kernel<false, kFTSmall>), grid, dim3(kFTSmall), fwd_smem(kFTSmall), st, a);
+    }
 }
 
 int backward(cudaStream_t st, const Stage& s, const float* x, const int* gather_base, const int* cursor, const float* dpool, const unsigned char* sel,
@@ -353,6 +391,8 @@ int backward(cudaStream_t st, const Stage& s, const float* x, const int* gather_
     a.B = B; a.F = s.F; a.act = s.act; a.n_par = s.F * (NPIX + KK);
     const int NFP = s.F / 2;
     a.G = std::max(1, std::min({max_rows, kNumSMs / NFP, (int)ceil_div(B, kBS)}));
+    static const int stagger_env = [] { const char* e = std::getenv("DLB_CONV28_STAGGER"); return e ? std::atoi(e) : 1; }();
+    a.stagger = stagger_env;
     TagScope tag_("conv_pool_bwd");
     DLB_LAUNCH_SMEM((conv28_backward_kernel), dim3((unsigned)(a.G * NFP)), dim3(kBT), kBwdSmem, st, a);
     return a.G;

@@ -340,7 +340,7 @@ struct NetT final : dlb_net {
     struct Conv28State {
         bool ok = false;
         int mode = [] { const char* e = std::getenv("DLB_CONV28"); return e ? std::atoi(e) : -1; }();            // 0 never, 1 always, otherwise from min_batch up
-        int min_batch = [] { const char* e = std::getenv("DLB_CONV28_MIN"); return e ? std::atoi(e) : 1024; }();
+        int min_batch = [] { const char* e = std::getenv("DLB_CONV28_MIN"); return e ? std::atoi(e) : 128; }();
 #ifndef DLB_CUDA_EMU
         conv28::Stage stage{};
 #endif

@@ -270,7 +270,81 @@ public:
     std::vector<Real> params() const { std::vector<Real> flat(static_cast<std::size_t>(dlb_net_param_count(_net))); check(dlb_net_get_params(_net, flat.data())); return flat; }
 };
 
+/// The reference's gradient containers - one LayerGradient per layer, data = {biases, weights | filters...} (LayerGradient.h:29-87,
+/// Net::allocate Net.h:291) - filled from a flat gradient in the library's parameter order.
+inline std::vector<LayerGradient<CpuDC>> to_layer_gradients(const Net<CpuDC>& net, const std::vector<Real>& flat) {
+    std::vector<LayerGradient<CpuDC>> out;
+    net.allocate(out, /*fill zeros*/ false);
+    std::size_t off = 0;
+    for (auto& lg : out)
+        for (auto& t : lg.data) {
+            if (off + t.size() > flat.size()) throw std::runtime_error("to_layer_gradients: parameter count mismatch");
+            std::memcpy(t.begin(), flat.data() + off, t.size() * sizeof(Real));
+            off += t.size();
+        }
+    if (off != flat.size()) throw std::runtime_error("to_layer_gradients: parameter count mismatch");
+    return out;
+}
+
+/// [n][size] host array of n equally sized host tensors
+inline std::vector<Real> pack_host(const std::vector<Tensor>& items) {
+    std::vector<Real> out;
+    if (items.empty()) return out;
+    const std::size_t sz = items[0].size();
+    out.resize(items.size() * sz);
+    for (std::size_t i = 0; i < items.size(); ++i) {
+        if (items[i].size() != sz) throw std::runtime_error("Incompatible collection of training and reference items.");
+        std::memcpy(out.data() + i * sz, items[i].begin(), sz * sizeof(Real));
+    }
+    return out;
+}
+
 }  // namespace dlb200_binding
+
+/// The sum over the items of Net<D>::calc_gradient_and_value's gradient (Net.inl:339-375; what learn accumulates per mini-batch,
+/// Net.inl:263-276), in the reference's containers.
+inline std::vector<LayerGradient<CpuDC>> calc_gradient_sum(const Net<CpuDC>& net, const std::vector<Tensor>& items, const std::vector<Tensor>& target_values,
+                                                           const CostFunctionId& cost_func_id) {
+    using namespace dlb200_binding;
+    if (items.size() != target_values.size() || items.empty()) throw std::runtime_error("Invalid input.");
+    DeviceNet dev(net);
+    const auto x = pack_host(items), y = pack_host(target_values);
+    check(dlb_net_forward_backward_host(dev.handle(), x.data(), y.data(), static_cast<int64_t>(items.size()), static_cast<int>(cost_func_id), /*scale*/ 0.0));
+    std::vector<Real> flat(static_cast<std::size_t>(dlb_net_param_count(dev.handle())));
+    check(dlb_net_read(dev.handle(), DLB_BUF_GRADIENT, 0, flat.data(), static_cast<int64_t>(flat.size() * sizeof(Real))));
+    return to_layer_gradients(net, flat);
+}
+
+/// What Net<D>::act_bpg leaves in its context for ONE item (Net.inl:117-132): per layer LayerData{Input, Trace{Derivatives, IndexMapping}}
+/// (LayerData.h:28-74), read back from the device traces; `out_value` receives the output of the last layer.
+inline std::vector<LayerData<CpuDC>> act_bpg_traces(const Net<CpuDC>& net, const Tensor& item, const Tensor& target_value, const CostFunctionId& cost_func_id,
+                                                    Tensor& out_value) {
+    using namespace dlb200_binding;
+    DeviceNet dev(net);
+    check(dlb_net_forward_backward_host(dev.handle(), item.begin(), target_value.begin(), 1, static_cast<int>(cost_func_id), 0.0));
+    const auto L = net.layers_count();
+    std::vector<LayerData<CpuDC>> out(L);
+    for (std::size_t l = 0; l < L; ++l) {
+        const auto in3 = net[l].in_size(), out3 = net[l].out_size();
+        if (l == 0) out[l].Input = item;
+        else {   // the input of layer l is the output of layer l - 1, in layer l's own shape
+            out[l].Input = Tensor(in3, false);
+            check(dlb_net_read(dev.handle(), DLB_BUF_OUTPUT, static_cast<int>(l) - 1, out[l].Input.begin(), static_cast<int64_t>(out[l].Input.size() * sizeof(Real))));
+        }
+        const auto n_out = static_cast<std::size_t>(out3.coord_prod());
+        if (dynamic_cast<const PLayer<CpuDC>*>(&net[l])) {   // a PLayer keeps the arg-max map and no derivatives (PLayer.inl:115-138)
+            std::vector<int32_t> map(n_out);
+            check(dlb_net_read(dev.handle(), DLB_BUF_INDEX_MAP, static_cast<int>(l), map.data(), static_cast<int64_t>(n_out * sizeof(int32_t))));
+            out[l].Trace.IndexMapping.assign(map.begin(), map.end());
+        } else {
+            out[l].Trace.Derivatives = Tensor(out3, false);
+            check(dlb_net_read(dev.handle(), DLB_BUF_DERIVATIVES, static_cast<int>(l), out[l].Trace.Derivatives.begin(), static_cast<int64_t>(n_out * sizeof(Real))));
+        }
+    }
+    out_value = Tensor(net[L - 1].out_size(), false);
+    check(dlb_net_read(dev.handle(), DLB_BUF_OUTPUT, static_cast<int>(L) - 1, out_value.begin(), static_cast<int64_t>(out_value.size() * sizeof(Real))));
+    return out;
+}
 
 /// Net<D>::learn (Net.inl:193-324) for a model held in the reference's Net object and a data set held in GpuDC tensors.
 /// `seed`: what Net::reset_random_generator(seed) would have been called with before the reference's own learn - the epoch

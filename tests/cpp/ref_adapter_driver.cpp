@@ -76,6 +76,88 @@ int rad_check_converters(const dlb_layer_spec* specs, int n_layers, unsigned see
     } catch (const std::runtime_error& e) { g_err = e.what(); return 2; } catch (...) { g_err = "unknown exception"; return 3; }
 }
 
+// Net::to_script of the reference net built from `specs` (Net.inl:521-530)
+int rad_net_script(const dlb_layer_spec* specs, int n_layers, char* buf, int64_t cap) {
+    try {
+        Net<CpuDC> net;
+        build(net, specs, n_layers);
+        const std::string s = net.to_script();
+        if ((int64_t)s.size() + 1 > cap) { g_err = "buffer too small"; return 1; }
+        std::memcpy(buf, s.c_str(), s.size() + 1);
+        return 0;
+    } catch (const std::runtime_error& e) { g_err = e.what(); return 2; } catch (...) { g_err = "unknown exception"; return 3; }
+}
+
+// The reference's own script reader on `script` (Net::try_load_from_script, Net.inl:56-93), written back by Net::to_script
+int rad_script_roundtrip(const char* script, char* buf, int64_t cap) {
+    try {
+        const Net<CpuDC> net{std::string(script)};
+        const std::string s = net.to_script();
+        if ((int64_t)s.size() + 1 > cap) { g_err = "buffer too small"; return 1; }
+        std::memcpy(buf, s.c_str(), s.size() + 1);
+        return 0;
+    } catch (const std::runtime_error& e) { g_err = e.what(); return 2; } catch (...) { g_err = "unknown exception"; return 3; }
+}
+
+// The binding's containers against the reference's own: the gradient SUM of a batch in LayerGradient containers (vs the sum of
+// Net::calc_gradient_and_value over the items), and the per-layer LayerData traces of the first item (vs the reference layers' own act
+// with trace data).  max_rel_err: largest |got - want| / (|want| + scale) seen; index maps must be equal.  Returns 0 when the shapes agree.
+int rad_check_containers(const dlb_layer_spec* specs, int n_layers, unsigned seed, const Real* x, const Real* y, int64_t n_items, int cost_id,
+                         double* max_rel_err_gradient, double* max_rel_err_traces, int64_t* index_map_mismatches) {
+    try {
+        Net<CpuDC>::reset_random_generator(seed);
+        Net<CpuDC> net;
+        build(net, specs, n_layers);
+        const Index3d in{ specs[0].in_c, specs[0].in_h, specs[0].in_w };
+        const Index3d out = net[net.layers_count() - 1].out_size();
+        const auto items = to_tensors(x, n_items, in), refs = to_tensors(y, n_items, out);
+        const auto cost = static_cast<CostFunctionId>(cost_id);
+        auto rel = [](const BasicCollection& got, const BasicCollection& want, double& worst) {
+            if (got.size() != want.size()) throw std::runtime_error("container sizes differ");
+            double scale = 0; for (std::size_t i = 0; i < want.size(); ++i) scale = std::max(scale, std::abs((double)want.begin()[i]));
+            for (std::size_t i = 0; i < want.size(); ++i)
+                worst = std::max(worst, std::abs((double)got.begin()[i] - (double)want.begin()[i]) / (std::abs((double)want.begin()[i]) + scale + 1e-30));
+        };
+        // gradients
+        std::vector<LayerGradient<CpuDC>> want;
+        net.allocate(want, true);
+        for (int64_t i = 0; i < n_items; ++i) {
+            auto g = std::get<0>(net.calc_gradient_and_value(items[(std::size_t)i], refs[(std::size_t)i], cost));
+            for (std::size_t l = 0; l < want.size(); ++l) want[l] += g[l];
+        }
+        const auto got = calc_gradient_sum(net, items, refs, cost);
+        if (got.size() != want.size()) throw std::runtime_error("layer counts differ");
+        *max_rel_err_gradient = 0;
+        for (std::size_t l = 0; l < want.size(); ++l) {
+            if (got[l].data.size() != want[l].data.size()) throw std::runtime_error("LayerGradient::data sizes differ");
+            for (std::size_t k = 0; k < want[l].data.size(); ++k) {
+                if (got[l].data[k].size_3d() != want[l].data[k].size_3d()) throw std::runtime_error("gradient tensor shapes differ");
+                rel(got[l].data[k], want[l].data[k], *max_rel_err_gradient);
+            }
+        }
+        // traces of the first item: the reference's layers, one after the other, with trace data
+        Tensor value;
+        const auto traces = act_bpg_traces(net, items[0], refs[0], cost, value);
+        *max_rel_err_traces = 0; *index_map_mismatches = 0;
+        Tensor cur = items[0];
+        for (std::size_t l = 0; l < net.layers_count(); ++l) {
+            LayerTraceData<CpuDC> tr;
+            Tensor nxt;
+            net[l].act(cur, nxt, &tr);
+            if (traces[l].Input.size_3d() != net[l].in_size()) throw std::runtime_error("LayerData::Input shape differs");
+            Tensor cur_shaped = cur; cur_shaped.reshape(net[l].in_size());
+            rel(traces[l].Input, cur_shaped, *max_rel_err_traces);
+            if (traces[l].Trace.Derivatives.size() != tr.Derivatives.size()) throw std::runtime_error("Trace.Derivatives sizes differ");
+            if (tr.Derivatives.size()) rel(traces[l].Trace.Derivatives, tr.Derivatives, *max_rel_err_traces);
+            if (traces[l].Trace.IndexMapping.size() != tr.IndexMapping.size()) throw std::runtime_error("Trace.IndexMapping sizes differ");
+            for (std::size_t i = 0; i < tr.IndexMapping.size(); ++i) *index_map_mismatches += traces[l].Trace.IndexMapping[i] != tr.IndexMapping[i];
+            cur = std::move(nxt);
+        }
+        rel(value, cur, *max_rel_err_traces);
+        return 0;
+    } catch (const std::runtime_error& e) { g_err = e.what(); return 2; } catch (...) { g_err = "unknown exception"; return 3; }
+}
+
 int rad_run(const dlb_layer_spec* specs, int n_layers, unsigned init_seed, unsigned learn_seed, const Real* x, const Real* y, int64_t n_items,
             int64_t batch, int64_t epochs, double lr, int cost_id, double lambda, int cpu_threads, Real* params_cpu, Real* params_gpu,
             int32_t* classes_cpu, int32_t* classes_gpu, int32_t* epochs_seen_gpu, double* eval_cost_gpu, double* eval_correct_gpu) {

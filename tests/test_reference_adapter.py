@@ -90,6 +90,41 @@ def test_reference_net_trained_through_the_gpu_binding(name, n_items, batch, epo
     assert seen.value == epochs, "the epoch callback must fire once per epoch"
     assert np.abs(p_cpu).max() > 0 and not np.array_equal(p_cpu, p_gpu * 0)
     H.assert_close("parameters: GpuDC binding vs the reference's own learn", p_gpu, p_cpu, real, rtol_mult=20)
-    assert np.array_equal(c_cpu, c_gpu), "the reference's inference on the two trained nets disagrees"
+    # the two nets' parameters agree within the bar, not bit for bit: an item whose two best outputs are within that bar of each other may
+    # flip (identical classes on IDENTICAL parameters are asserted in tests/test_net_gpu.py and tests/test_reference_gpu.py)
+    assert np.mean(c_cpu == c_gpu) >= 0.97, f"the reference's inference on the two trained nets disagrees on {int(np.sum(c_cpu != c_gpu))} of {n_items} items"
     assert 0.0 <= ev_correct.value <= 1.0 and np.isfinite(ev_cost.value)
     assert abs(ev_correct.value - float(np.mean(c_gpu == np.argmax(y, axis=1)))) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("real", ["f32", "f64"])
+@pytest.mark.parametrize("name,n_items", [("mini_lenet", 9), ("fixture", 5), ("avg", 6), ("lenet", 12)])
+def test_reference_containers_from_device_buffers(name, n_items, real):
+    """SURVEY.md section 8 a15: the binding hands back the reference's OWN container types - std::vector<LayerGradient<CpuDC>> (the
+    gradient sum of a mini-batch) and std::vector<LayerData<CpuDC>> (Input / Trace.Derivatives / Trace.IndexMapping of an item) - built
+    from the device buffers; compared, container by container, with what the reference's Net computes on the host; index maps exactly."""
+    lib = load(real)
+    vp = C.c_void_p
+    lib.rad_check_containers.argtypes = [C.POINTER(ob.LayerSpec), C.c_int, C.c_uint, vp, vp, C.c_int64, C.c_int, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    specs = NETS[name]
+    arr = (ob.LayerSpec * len(specs))(*specs)
+    dt = ob.dtype_of(real)
+    in_n = specs[0].in_c * specs[0].in_h * specs[0].in_w
+    out_shape = ob.out_shape(specs[-1])
+    out_n = out_shape[0] * out_shape[1] * out_shape[2]
+    rng = np.random.default_rng(9)
+    x = rng.uniform(0, 1, (n_items, in_n)).astype(dt)
+    cost = ob.SQUARED_ERROR if specs[-1].activation in (ob.LINEAR, ob.TANH) else ob.CROSS_ENTROPY
+    if cost == ob.CROSS_ENTROPY:
+        y = np.zeros((n_items, out_n), dt); y[np.arange(n_items), rng.integers(0, out_n, n_items)] = 1
+    else:
+        y = rng.uniform(0.05, 0.95, (n_items, out_n)).astype(dt)
+    eg, et, mism = C.c_double(-1), C.c_double(-1), C.c_int64(-1)
+    rc = lib.rad_check_containers(arr, len(specs), 7, x.ctypes.data, y.ctypes.data, n_items, cost, C.byref(eg), C.byref(et), C.byref(mism))
+    assert rc == 0, lib.rad_last_error().decode()
+    bar = 2e-5 if real == "f32" else 1e-11
+    assert 0 <= eg.value < bar, f"gradient containers: max relative error {eg.value:.3e}"
+    assert 0 <= et.value < bar, f"trace containers: max relative error {et.value:.3e}"
+    assert mism.value == 0, f"{mism.value} arg-max indices differ"
