@@ -518,7 +518,8 @@ def main():
                 e0.record(); it64 = net64.train_steps(256, 56, LR, cost_id, LAMBDA); e1.record()
                 ms64 = e0.elapsed_ms(e1)
                 line["f64"] = {"workload": "LeNet, Real = double, mini-batch 256", "value": it64 / (ms64 / 1e3), "unit": "samples/s", "ms_per_step": ms64 / 56,
-                               "contractions": "DFMA (tcgen05 has no fp64 kind)", "dfma_peak_tflops": pk.get("dfma_tflops")}
+                               "contractions": "DFMA (tcgen05 has no fp64 kind; the DMMA path mma.sync.m8n8k4.f64 measures the same peak)",
+                               "dfma_peak_tflops": pk.get("dfma_tflops"), "dmma_peak_tflops": pk.get("dmma_m8n8k4_tflops")}
                 net64.close()
             except Exception as exc:
                 line["f64"] = {"error": str(exc)[:200]}
@@ -589,7 +590,7 @@ def main():
         r1 = run_reference(args.real, 256, 8, 1, parallelism=1)
         line["cpu_baseline"]["one_thread"] = {"value": r1["value"], "unit": "samples/s", "cores": 1, "sample": r1["sample"]}
         if pk:
-            line["measured_peaks"] = {k: pk[k] for k in ("tf32_tcgen05_cta1_m128_n256_tflops", "tf32_3x_equivalent_fp32_tflops", "ffma2_tflops", "dfma_tflops") if k in pk}
+            line["measured_peaks"] = {k: pk[k] for k in ("tf32_tcgen05_cta1_m128_n256_tflops", "tf32_3x_equivalent_fp32_tflops", "ffma2_tflops", "dfma_tflops", "dmma_m8n8k4_tflops") if k in pk}
     if world > 1:
         same_after = ranks_identical()
         # per-kernel table of this rank at N > 1 (instrumented pass on every rank at once: the exchange kernel waits for its peers)

@@ -430,6 +430,9 @@ struct NetT final : dlb_net {
     bool p2p_on = false;
     R* publish_buf(int parity) { return reinterpret_cast<R*>(p2p_region + (size_t)parity * p2p_publish_bytes); }
     bool overlap_enabled = true;
+    // DLB_HEAD_FOLD=1: the head sums the split partials of the layer in front of it instead of a separate finalize kernel.  Measured SLOWER
+    // (70.1 vs 64.1 us per step at mini-batch 256: 30 dependent partial loads per element inside a one-warp-per-sample kernel), so it is off.
+    bool head_folds_finalize = [] { const char* e = std::getenv("DLB_HEAD_FOLD"); return e && e[0] == '1'; }();
     bool pdl_enabled = [] { const char* e = std::getenv("DLB_PDL"); return !(e && e[0] == '0'); }();   // programmatic dependent launches (DLB_PDL=0: off, for A/B runs)
     const void* ws_stamp = nullptr;   // the context scratch the captured graphs point into
     bool graphs_enabled = true;
@@ -890,6 +893,7 @@ struct NetT final : dlb_net {
             l = 2;
         }
         // hidden NLayers
+        const R* head_partials = nullptr; int head_partial_splits = 0;
         for (; l < Ln - 1; ++l) {
             const auto& Y = layers[(size_t)l];
             g_tag_layer = l;
@@ -901,8 +905,14 @@ struct NetT final : dlb_net {
                     const TcOperand A{l == 0 ? x : out[(size_t)l - 1], (long long)Y.in_n, 0, l == 0 ? gather_base : nullptr, l == 0 ? cursor : nullptr, -1};
                     const TcOperand Bo{bias + Y.bias_n, (long long)Y.in_n, 0, nullptr, nullptr, -1};
                     // behind the fused conv + pool kernel (which triggers early) the contraction is launched programmatically
+                    // the last hidden layer in front of a head with at most 128 inputs leaves a split reduction unfinalised: the head sums the
+                    // partials itself (fused.cuh, HeadInputPartials) - one dependent kernel less
+                    const bool defer = head_folds_finalize && l == Ln - 2 && Y.out_n <= 128;
+                    int splits = 1;
                     tc_gemm<kRedContig, kRedContig>(st, B, (int)Y.out_n, (int)Y.in_n, A, Bo, EpiFullForward<float>{out[(size_t)l], nullptr, bias, (int)Y.out_n, Y.s.activation}, lc.ws,
-                                                    /*pdl*/ plan.has_cp && l == 2 && pdl_enabled);
+                                                    /*pdl*/ plan.has_cp && l == 2 && pdl_enabled, defer ? &splits : nullptr);
+                    if (defer && splits > 1) { head_partials = static_cast<const R*>(lc.ws.ptr); head_partial_splits = splits; }
+                    else if (defer) head_partial_splits = 0;   // (one split: the contraction's own epilogue wrote the activations)
                     continue;
                 }
             }
@@ -926,20 +936,21 @@ struct NetT final : dlb_net {
             const R* bias = params + Y.param_off;
             const size_t smem = (size_t)Y.out_n * (size_t)Y.in_n * sizeof(R);
             const int grid = std::min((int)ceil_div(B, 8), 4 * kNumSMs);
+            const HeadInputPartials<R> hp{head_partial_splits > 1 ? head_partials : nullptr, head_partial_splits, params + Pv.param_off, Pv.s.activation, out[(size_t)h - 1]};
             {
                 TagScope tag_("head");
                 if (plan.head_nmax == 10)
                     DLB_LAUNCH_SMEM((full_head_kernel<R, 10>), dim3((unsigned)grid), dim3(256), smem, st, (const R*)out[(size_t)h - 1], bias,
                                     bias + Y.bias_n, refs, gather_base, cursor, out[(size_t)h], in_grad[(size_t)Ln], in_grad[(size_t)h], B,
-                                    (int)Y.in_n, (int)Y.out_n, Y.s.activation, cost, prev_act);
+                                    (int)Y.in_n, (int)Y.out_n, Y.s.activation, cost, prev_act, hp);
                 else if (plan.head_nmax == 16)
                     DLB_LAUNCH_SMEM((full_head_kernel<R, 16>), dim3((unsigned)grid), dim3(256), smem, st, (const R*)out[(size_t)h - 1], bias,
                                     bias + Y.bias_n, refs, gather_base, cursor, out[(size_t)h], in_grad[(size_t)Ln], in_grad[(size_t)h], B,
-                                    (int)Y.in_n, (int)Y.out_n, Y.s.activation, cost, prev_act);
+                                    (int)Y.in_n, (int)Y.out_n, Y.s.activation, cost, prev_act, hp);
                 else
                     DLB_LAUNCH_SMEM((full_head_kernel<R, 32>), dim3((unsigned)grid), dim3(256), smem, st, (const R*)out[(size_t)h - 1], bias,
                                     bias + Y.bias_n, refs, gather_base, cursor, out[(size_t)h], in_grad[(size_t)Ln], in_grad[(size_t)h], B,
-                                    (int)Y.in_n, (int)Y.out_n, Y.s.activation, cost, prev_act);
+                                    (int)Y.in_n, (int)Y.out_n, Y.s.activation, cost, prev_act, hp);
             }
             {
                 TagScope tag_("head_dW");

@@ -724,10 +724,17 @@ __global__ void __launch_bounds__(32 * FMAX, 1) conv_pool_backward_staged_kernel
 // activation gradient g = dC/dz, and the input gradient dx = W^T g (optionally times the previous layer's activation
 // derivative recomputed from x, which IS that layer's output).  One warp per sample; W lives in shared memory.
 // ---------------------------------------------------------------------------------------------------------------
+// Split-K partials of the previous NLayer's forward contraction, when that launch left them unfinalised (in_n <= 128): the head then
+// computes its own input x = f(sum of the partials + bias) - same association as gemm_finalize_kernel, i.e. the same bits - and stores it
+// for the weight gradients; one dependent kernel less on the critical path of a small mini-batch.
+template <class R>
+struct HeadInputPartials { const R* partials; int splits; const R* bias; int act; R* x_store; };
+
 template <class R, int NMAX>
 __global__ void full_head_kernel(const R* __restrict__ x, const R* __restrict__ bias, const R* __restrict__ W, const R* __restrict__ ref,
                                  const int* __restrict__ gather_base, const int* __restrict__ cursor, R* __restrict__ out,
-                                 R* __restrict__ g_out, R* __restrict__ dx, int B, int in_n, int n, int act, int cost_id, int prev_act) {
+                                 R* __restrict__ g_out, R* __restrict__ dx, int B, int in_n, int n, int act, int cost_id, int prev_act,
+                                 HeadInputPartials<R> hp) {
     DLB_DYNAMIC_SMEM(R, W_s);
     pdl_trigger();   // the input-gradient contraction that follows may set itself up while this grid runs
     const int* gather = resolve_gather(gather_base, cursor);
@@ -736,11 +743,27 @@ __global__ void full_head_kernel(const R* __restrict__ x, const R* __restrict__ 
     constexpr int XP = 4;
     const int b_first = blockIdx.x * wpb + threadIdx.x / 32;
     const bool pre = in_n <= 32 * XP;
+    auto load_x = [&](int b, int k) -> R {
+        if (!hp.partials) return x[(size_t)b * in_n + k];
+        R s8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s8[j] = R(0);
+        const size_t total = (size_t)B * in_n, e = (size_t)b * in_n + k;
+        for (int z = 0; z < hp.splits; z += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (z + j < hp.splits) s8[j] += hp.partials[(size_t)(z + j) * total + e];
+        }
+        R d;
+        const R v = apply_activation<R>(hp.act, (((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]))) + hp.bias[k], d);
+        hp.x_store[e] = v;
+        return v;
+    };
     R xpre[XP];
 #pragma unroll
     for (int j = 0; j < XP; ++j) {
         const int k = lane + 32 * j;
-        xpre[j] = (pre && b_first < B && k < in_n) ? x[(size_t)b_first * in_n + k] : R(0);
+        xpre[j] = (pre && b_first < B && k < in_n) ? load_x(b_first, k) : R(0);
     }
     size_t row_pre = (b_first < B && gather) ? (size_t)gather[b_first] : (size_t)b_first;
     for (int i = threadIdx.x; i < n * in_n; i += blockDim.x) W_s[i] = W[i];
@@ -753,12 +776,15 @@ __global__ void full_head_kernel(const R* __restrict__ x, const R* __restrict__ 
         R z[NMAX];
 #pragma unroll
         for (int nn = 0; nn < NMAX; ++nn) z[nn] = R(0);
+        R xcur[XP];
         if (pre) {
 #pragma unroll
             for (int j = 0; j < XP; ++j) {
                 const int k = lane + 32 * j;
+                xcur[j] = R(0);
                 if (k < in_n) {
-                    const R xv = b == b_first ? xpre[j] : xb[k];
+                    const R xv = b == b_first ? xpre[j] : load_x(b, k);
+                    xcur[j] = xv;
 #pragma unroll
                     for (int nn = 0; nn < NMAX; ++nn)
                         if (nn < n) z[nn] += W_s[nn * in_n + k] * xv;
@@ -814,13 +840,28 @@ __global__ void full_head_kernel(const R* __restrict__ x, const R* __restrict__ 
 #pragma unroll
         for (int nn = 0; nn < NMAX; ++nn) gg[nn] = nn < n ? __shfl_sync(0xffffffffu, ggl, nn) : R(0);
         if (dx) {
-            for (int k = lane; k < in_n; k += 32) {
-                R s = R(0);
+            if (pre) {   // (the inputs are still in registers)
 #pragma unroll
-                for (int nn = 0; nn < NMAX; ++nn)
-                    if (nn < n) s = W_s[nn * in_n + k] * gg[nn] + s;
-                if (prev_act) s = deriv_from_value<R>(prev_act, xb[k]) * s;
-                dx[(size_t)b * in_n + k] = s;
+                for (int j = 0; j < XP; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k < in_n) {
+                        R s = R(0);
+#pragma unroll
+                        for (int nn = 0; nn < NMAX; ++nn)
+                            if (nn < n) s = W_s[nn * in_n + k] * gg[nn] + s;
+                        if (prev_act) s = deriv_from_value<R>(prev_act, xcur[j]) * s;
+                        dx[(size_t)b * in_n + k] = s;
+                    }
+                }
+            } else {
+                for (int k = lane; k < in_n; k += 32) {
+                    R s = R(0);
+#pragma unroll
+                    for (int nn = 0; nn < NMAX; ++nn)
+                        if (nn < n) s = W_s[nn * in_n + k] * gg[nn] + s;
+                    if (prev_act) s = deriv_from_value<R>(prev_act, xb[k]) * s;
+                    dx[(size_t)b * in_n + k] = s;
+                }
             }
         }
     }

@@ -488,7 +488,9 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
 // Host launcher, instantiated per pair of operand kinds (the kernel carries only the producers it needs).  Falls back to
 // nothing: callers decide (by Real type and shape) whether to use this or gemm<R>.
 template <int KA, int KB, class EP>
-void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcOperand& b, EP ep, const GemmWorkspace& ws, bool pdl = false) {
+void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcOperand& b, EP ep, const GemmWorkspace& ws, bool pdl = false,
+             int* defer_finalize = nullptr) {   // non-null: a split reduction leaves its partials [splits][M][N] in ws for the consumer; receives `splits`
+    if (defer_finalize) *defer_finalize = 1;
     if (M <= 0 || N <= 0) return;
     if (a.kind != KA || b.kind != KB) throw std::logic_error("tc_gemm: operand kind does not match the instantiation");
     if (a.ld >= (1LL << 31) || b.ld >= (1LL << 31)) throw std::invalid_argument("tc_gemm: leading dimension exceeds the 32-bit range");
@@ -533,6 +535,7 @@ void tc_gemm(cudaStream_t st, int M, int N, int K, const TcOperand& a, const TcO
         DLB_LAUNCH_SMEM((tc::tc_gemm_kernel<EP, KA, KB>), grid, dim3(tc::kThreads), (size_t)tc::kSmemBytes, st, M, N, K, k_per_split, tiles_m, tiles_n,
                         n_tiles, splits, mma_n, a, b, ep, partials, use_tma, map_a, map_b);
     }
+    if (defer_finalize) { *defer_finalize = splits; return; }
     if (splits > 1) {
         const size_t total = (size_t)M * N;
         DLB_LAUNCH((gemm_finalize_kernel<float, EP>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), st,

@@ -94,7 +94,8 @@ def test_reference_net_trained_through_the_gpu_binding(name, n_items, batch, epo
     # flip (identical classes on IDENTICAL parameters are asserted in tests/test_net_gpu.py and tests/test_reference_gpu.py)
     assert np.mean(c_cpu == c_gpu) >= 0.97, f"the reference's inference on the two trained nets disagrees on {int(np.sum(c_cpu != c_gpu))} of {n_items} items"
     assert 0.0 <= ev_correct.value <= 1.0 and np.isfinite(ev_cost.value)
-    assert abs(ev_correct.value - float(np.mean(c_gpu == np.argmax(y, axis=1)))) < 1e-12
+    # (the device's own inference inside evaluate vs the reference's inference on the same parameters: a near-tie may flip one item)
+    assert abs(ev_correct.value - float(np.mean(c_gpu == np.argmax(y, axis=1)))) <= 2.0 / n_items + 1e-12
 
 
 @pytest.mark.gpu

@@ -108,6 +108,22 @@ __global__ void __launch_bounds__(512, 2) dfma_peak_kernel(int iters, double* si
     if (s == 123.456) sink[0] = s;
 }
 
+// fp64 tensor path available on sm_100a: mma.sync.m8n8k4.f64 (DMMA), 8 independent accumulator tiles per warp
+__global__ void __launch_bounds__(512, 2) dmma_peak_kernel(int iters, double* sink) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-9 + i; c[i][1] = 1.0 + i; }
+    const double a = 1.00000000001, b = 0.99999999999;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) sink[0] = s;
+}
+
 template <class F>
 static double time_ms(F&& launch) {
     cudaEvent_t e0, e1;
@@ -150,6 +166,8 @@ int main() {
         const double ms2 = time_ms([&] { ffma2_peak_kernel<<<blocks, 512>>>(iters, sink); });
         const double ms3 = time_ms([&] { dfma_peak_kernel<<<blocks, 512>>>(iters, dsink); });
         printf(", \"ffma_tflops\": %.1f, \"ffma2_tflops\": %.1f, \"dfma_tflops\": %.2f", total / (ms1 * 1e-3) / 1e12, 2.0 * total / (ms2 * 1e-3) / 1e12, total / (ms3 * 1e-3) / 1e12);
+        const double ms4 = time_ms([&] { dmma_peak_kernel<<<blocks, 512>>>(iters, dsink); });
+        printf(", \"dmma_m8n8k4_tflops\": %.2f", 2.0 * 8 * 8 * 4 * 8.0 * iters * 16.0 * blocks / (ms4 * 1e-3) / 1e12);
     }
     printf(", \"how\": \"tools/peaks.cu: best of 5 launches, CUDA events; tensor: one CTA per SM issuing tcgen05.mma kind::tf32 cta_group::1 back to back on shared-memory operands; CUDA cores: 2 x 512 threads per SM, 16 independent accumulators per thread\"}\n");
     return 0;
