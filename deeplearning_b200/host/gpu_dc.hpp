@@ -332,10 +332,12 @@ inline std::vector<LayerData<CpuDC>> act_bpg_traces(const Net<CpuDC>& net, const
             check(dlb_net_read(dev.handle(), DLB_BUF_OUTPUT, static_cast<int>(l) - 1, out[l].Input.begin(), static_cast<int64_t>(out[l].Input.size() * sizeof(Real))));
         }
         const auto n_out = static_cast<std::size_t>(out3.coord_prod());
-        if (dynamic_cast<const PLayer<CpuDC>*>(&net[l])) {   // a PLayer keeps the arg-max map and no derivatives (PLayer.inl:115-138)
-            std::vector<int32_t> map(n_out);
-            check(dlb_net_read(dev.handle(), DLB_BUF_INDEX_MAP, static_cast<int>(l), map.data(), static_cast<int64_t>(n_out * sizeof(int32_t))));
-            out[l].Trace.IndexMapping.assign(map.begin(), map.end());
+        if (dynamic_cast<const PLayer<CpuDC>*>(&net[l])) {   // a min / max PLayer keeps the arg-max map, an average one nothing (PLayer.inl:115-138)
+            if (to_spec(net[l]).pool_type != DLB_POOL_AVERAGE) {
+                std::vector<int32_t> map(n_out);
+                check(dlb_net_read(dev.handle(), DLB_BUF_INDEX_MAP, static_cast<int>(l), map.data(), static_cast<int64_t>(n_out * sizeof(int32_t))));
+                out[l].Trace.IndexMapping.assign(map.begin(), map.end());
+            }
         } else {
             out[l].Trace.Derivatives = Tensor(out3, false);
             check(dlb_net_read(dev.handle(), DLB_BUF_DERIVATIVES, static_cast<int>(l), out[l].Trace.Derivatives.begin(), static_cast<int64_t>(n_out * sizeof(Real))));

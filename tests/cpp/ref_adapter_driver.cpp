@@ -9,12 +9,27 @@
 #include <gpu_dc.hpp>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
+#include <csignal>
+#include <execinfo.h>
+#include <unistd.h>
 
 using namespace DeepLearning;
 
 namespace {
 thread_local std::string g_err;
+
+// RAD_DEBUG_SEGV=1: print a native backtrace when a crash happens inside the driver (development aid)
+void segv_backtrace(int sig) {
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+void maybe_install_segv_handler() {
+    if (std::getenv("RAD_DEBUG_SEGV")) { std::signal(SIGSEGV, segv_backtrace); std::signal(SIGABRT, segv_backtrace); }
+}
 
 void build(Net<CpuDC>& net, const dlb_layer_spec* specs, int n) {
     for (int i = 0; i < n; ++i) {
@@ -161,6 +176,7 @@ int rad_check_containers(const dlb_layer_spec* specs, int n_layers, unsigned see
 int rad_run(const dlb_layer_spec* specs, int n_layers, unsigned init_seed, unsigned learn_seed, const Real* x, const Real* y, int64_t n_items,
             int64_t batch, int64_t epochs, double lr, int cost_id, double lambda, int cpu_threads, Real* params_cpu, Real* params_gpu,
             int32_t* classes_cpu, int32_t* classes_gpu, int32_t* epochs_seen_gpu, double* eval_cost_gpu, double* eval_correct_gpu) {
+    maybe_install_segv_handler();
     try {
         const Index3d in{ specs[0].in_c, specs[0].in_h, specs[0].in_w };
         Net<CpuDC> net_cpu, net_gpu;

@@ -47,6 +47,43 @@ NETS = {"mini_lenet": gc.MINI_LENET, "fixture": gc.FIXTURE_NET, "avg": gc.AVG_NE
         "cifar": ob.cifar_specs()}
 
 
+# The GPU cases run in a FRESH process each: the float and the double build of the reference are two shared libraries with the same
+# C++ symbols, and a process that has trained through one of them corrupts its heap when it then trains through the other (seen on the
+# B200 as "munmap_chunk(): invalid pointer" inside std::regex of the second library, although both are built -fno-gnu-unique
+# -Wl,-Bsymbolic and loaded RTLD_LOCAL); either one alone is clean under MALLOC_CHECK_=3.
+def in_fresh_process(fn, *args):
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(1) as pool:
+        return pool.apply(fn, args)
+
+
+def _train_case(real, name, x, y, batch, epochs, lr, cost, lam, n_params):
+    lib = load(real)
+    specs = NETS[name]
+    arr = (ob.LayerSpec * len(specs))(*specs)
+    dt = ob.dtype_of(real)
+    n_items = x.shape[0]
+    p_cpu = np.zeros(n_params, dt); p_gpu = np.zeros(n_params, dt)
+    c_cpu = np.zeros(n_items, np.int32); c_gpu = np.zeros(n_items, np.int32)
+    seen = C.c_int32(0); ev_cost = C.c_double(0); ev_correct = C.c_double(0)
+    rc = lib.rad_run(arr, len(specs), 7, 11, x.ctypes.data, y.ctypes.data, n_items, batch, epochs, lr, cost, lam, 1,
+                     p_cpu.ctypes.data, p_gpu.ctypes.data, c_cpu.ctypes.data, c_gpu.ctypes.data, C.addressof(seen), C.addressof(ev_cost), C.addressof(ev_correct))
+    return dict(rc=rc, error=lib.rad_last_error().decode(), p_cpu=p_cpu, p_gpu=p_gpu, c_cpu=c_cpu, c_gpu=c_gpu, seen=seen.value,
+                ev_cost=ev_cost.value, ev_correct=ev_correct.value)
+
+
+def _container_case(real, name, x, y, cost):
+    lib = load(real)
+    vp = C.c_void_p
+    lib.rad_check_containers.argtypes = [C.POINTER(ob.LayerSpec), C.c_int, C.c_uint, vp, vp, C.c_int64, C.c_int, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    specs = NETS[name]
+    arr = (ob.LayerSpec * len(specs))(*specs)
+    eg, et, mism = C.c_double(-1), C.c_double(-1), C.c_int64(-1)
+    rc = lib.rad_check_containers(arr, len(specs), 7, x.ctypes.data, y.ctypes.data, x.shape[0], cost, C.byref(eg), C.byref(et), C.byref(mism))
+    return dict(rc=rc, error=lib.rad_last_error().decode(), eg=eg.value, et=et.value, mism=mism.value)
+
+
 @pytest.mark.parametrize("real", ["f32", "f64"])
 @pytest.mark.parametrize("name", list(NETS))
 def test_converters_round_trip(name, real):
@@ -81,12 +118,10 @@ def test_reference_net_trained_through_the_gpu_binding(name, n_items, batch, epo
         y = np.zeros((n_items, out_n), dt); y[np.arange(n_items), rng.integers(0, out_n, n_items)] = 1
     else:
         y = rng.uniform(0.05, 0.95, (n_items, out_n)).astype(dt)
-    p_cpu = np.zeros(n_params, dt); p_gpu = np.zeros(n_params, dt)
-    c_cpu = np.zeros(n_items, np.int32); c_gpu = np.zeros(n_items, np.int32)
-    seen = C.c_int32(0); ev_cost = C.c_double(0); ev_correct = C.c_double(0)
-    rc = lib.rad_run(arr, len(specs), 7, 11, x.ctypes.data, y.ctypes.data, n_items, batch, epochs, 0.05, cost, lam, 1,
-                     p_cpu.ctypes.data, p_gpu.ctypes.data, c_cpu.ctypes.data, c_gpu.ctypes.data, C.addressof(seen), C.addressof(ev_cost), C.addressof(ev_correct))
-    assert rc == 0, lib.rad_last_error().decode()
+    out = in_fresh_process(_train_case, real, name, x, y, batch, epochs, 0.05, cost, lam, int(n_params))
+    assert out["rc"] == 0, out["error"]
+    p_cpu, p_gpu, c_cpu, c_gpu = out["p_cpu"], out["p_gpu"], out["c_cpu"], out["c_gpu"]
+    seen, ev_cost, ev_correct = C.c_int32(out["seen"]), C.c_double(out["ev_cost"]), C.c_double(out["ev_correct"])
     assert seen.value == epochs, "the epoch callback must fire once per epoch"
     assert np.abs(p_cpu).max() > 0 and not np.array_equal(p_cpu, p_gpu * 0)
     H.assert_close("parameters: GpuDC binding vs the reference's own learn", p_gpu, p_cpu, real, rtol_mult=20)
@@ -105,12 +140,7 @@ def test_reference_containers_from_device_buffers(name, n_items, real):
     """SURVEY.md section 8 a15: the binding hands back the reference's OWN container types - std::vector<LayerGradient<CpuDC>> (the
     gradient sum of a mini-batch) and std::vector<LayerData<CpuDC>> (Input / Trace.Derivatives / Trace.IndexMapping of an item) - built
     from the device buffers; compared, container by container, with what the reference's Net computes on the host; index maps exactly."""
-    lib = load(real)
-    vp = C.c_void_p
-    lib.rad_check_containers.argtypes = [C.POINTER(ob.LayerSpec), C.c_int, C.c_uint, vp, vp, C.c_int64, C.c_int, C.POINTER(C.c_double),
-                                         C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     specs = NETS[name]
-    arr = (ob.LayerSpec * len(specs))(*specs)
     dt = ob.dtype_of(real)
     in_n = specs[0].in_c * specs[0].in_h * specs[0].in_w
     out_shape = ob.out_shape(specs[-1])
@@ -122,9 +152,9 @@ def test_reference_containers_from_device_buffers(name, n_items, real):
         y = np.zeros((n_items, out_n), dt); y[np.arange(n_items), rng.integers(0, out_n, n_items)] = 1
     else:
         y = rng.uniform(0.05, 0.95, (n_items, out_n)).astype(dt)
-    eg, et, mism = C.c_double(-1), C.c_double(-1), C.c_int64(-1)
-    rc = lib.rad_check_containers(arr, len(specs), 7, x.ctypes.data, y.ctypes.data, n_items, cost, C.byref(eg), C.byref(et), C.byref(mism))
-    assert rc == 0, lib.rad_last_error().decode()
+    out = in_fresh_process(_container_case, real, name, x, y, cost)
+    assert out["rc"] == 0, out["error"]
+    eg, et, mism = C.c_double(out["eg"]), C.c_double(out["et"]), C.c_int64(out["mism"])
     bar = 2e-5 if real == "f32" else 1e-11
     assert 0 <= eg.value < bar, f"gradient containers: max relative error {eg.value:.3e}"
     assert 0 <= et.value < bar, f"trace containers: max relative error {et.value:.3e}"

@@ -54,7 +54,7 @@ def launches(src, dst):
     print(open(dst).read())
 
 
-TAGS = (("conv_pool_forward", "conv_pool_fwd"), ("conv_pool_backward", "conv_pool_bwd"), ("full_head_kernel", "head"),
+TAGS = (("conv28_forward", "conv_pool_fwd"), ("conv28_backward", "conv_pool_bwd"), ("conv_pool_forward", "conv_pool_fwd"), ("conv_pool_backward", "conv_pool_bwd"), ("full_head_kernel", "head"),
         ("p2p_reduce_update_kernel", "reduce_update"), ("reduce_update_kernel", "reduce_update"), ("batch_outer_partial_kernel", "head_dW"),
         ("tc_gemm_kernel<EpiFullForward", "full_fwd"), ("tc_gemm_kernel<EpiWeightAndBias", "full_dW"),
         ("tc_gemm_kernel<EpiStoreTimesDeriv", "full_dX"))
