@@ -303,7 +303,47 @@ struct NetT final : dlb_net {
     R* stage_y = nullptr;           // [cap][out_n(L-1)]
     int* gather_dev = nullptr;      // [cap]
     R* data_x = nullptr; R* data_y = nullptr; int64_t n_items = 0; bool own_data = false;
-    int* perm_dev = nullptr; int64_t perm_cap = 0;
+    // The epoch permutation: two device buffers and two pinned host buffers used alternately, so that the next epoch's permutation is
+    // uploaded behind the kernels of the current one WITHOUT draining the stream (two synchronisations per epoch used to leave a bubble of
+    // tens of microseconds - at 4 steps per epoch and, data parallel, a different one on every rank, i.e. a wait at the exchange barrier).
+    int* perm_dev = nullptr; int64_t perm_cap = 0;   // the buffer of the current epoch
+    int* perm_bufs[2] = {nullptr, nullptr}; int* perm_host[2] = {nullptr, nullptr}; int perm_sel = 0;
+#ifndef DLB_CUDA_EMU
+    cudaEvent_t perm_ev[2] = {nullptr, nullptr}; bool perm_ev_pending[2] = {false, false};
+#endif
+    void ensure_perm(int64_t n) {
+        if (perm_cap >= n) return;
+        DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+        drop_graphs();
+        for (int i = 0; i < 2; ++i) {
+            dev_free(perm_bufs[i]); perm_bufs[i] = dev_alloc<int>((size_t)n);
+#ifndef DLB_CUDA_EMU
+            if (perm_host[i]) cudaFreeHost(perm_host[i]);
+            DLB_CUDA(cudaMallocHost((void**)&perm_host[i], (size_t)n * sizeof(int)));
+            if (!perm_ev[i]) DLB_CUDA(cudaEventCreateWithFlags(&perm_ev[i], cudaEventDisableTiming));
+            perm_ev_pending[i] = false;
+#else
+            std::free(perm_host[i]); perm_host[i] = static_cast<int*>(std::malloc((size_t)n * sizeof(int)));
+#endif
+        }
+        perm_dev = perm_bufs[0]; perm_sel = 0; perm_cap = n;
+    }
+    // Uploads the permutation of the next epoch into the other buffer (stream-ordered behind everything that reads the current one) and
+    // resets the device-side batch cursor.
+    void upload_permutation(const std::vector<std::size_t>& index_map) {
+        perm_sel ^= 1;
+        int* h = perm_host[perm_sel];
+#ifndef DLB_CUDA_EMU
+        if (perm_ev_pending[perm_sel]) DLB_CUDA(cudaEventSynchronize(perm_ev[perm_sel]));   // the upload that last read this pinned buffer (two epochs ago) has run
+#endif
+        for (int64_t i = 0; i < n_items; ++i) h[i] = (int)index_map[(size_t)i];
+        perm_dev = perm_bufs[perm_sel];
+        DLB_CUDA(cudaMemcpyAsync(perm_dev, h, (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        DLB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(int), ctx->stream));
+#ifndef DLB_CUDA_EMU
+        DLB_CUDA(cudaEventRecord(perm_ev[perm_sel], ctx->stream)); perm_ev_pending[perm_sel] = true;
+#endif
+    }
     double* cost_dev = nullptr;
     int last_B = 0;
     UpdateSegments segs{};
@@ -356,9 +396,9 @@ struct NetT final : dlb_net {
     // CUDA graphs of the whole step, one per distinct (share, batch, hyper-parameters): the per-step launch sequence is
     // identical for every batch of an epoch because the batch position lives in d_cursor on the device.
     struct StepKey {
-        int64_t mine, global; double lr, reg; int cost; const void* x; int flags;
+        int64_t mine, global; double lr, reg; int cost; const void* x; int flags; const void* gather;   // (gather: which of the two permutation buffers)
         bool operator==(const StepKey& o) const {
-            return mine == o.mine && global == o.global && lr == o.lr && reg == o.reg && cost == o.cost && x == o.x && flags == o.flags;
+            return mine == o.mine && global == o.global && lr == o.lr && reg == o.reg && cost == o.cost && x == o.x && flags == o.flags && gather == o.gather;
         }
     };
     struct StepGraph {
@@ -428,7 +468,12 @@ struct NetT final : dlb_net {
     unsigned long long p2p_step = 0;          // host mirror of *d_p2p_step (both advance once per step)
     unsigned long long* d_p2p_step = nullptr;
     bool p2p_on = false;
-    R* publish_buf(int parity) { return reinterpret_cast<R*>(p2p_region + (size_t)parity * p2p_publish_bytes); }
+    // this rank's slot of the given parity inside its own region: [parity][kMaxPeers slots][publish bytes] | flags
+    R* publish_buf(int parity) { return reinterpret_cast<R*>(p2p_region + ((size_t)parity * kMaxPeers + (size_t)rank) * p2p_publish_bytes); }
+    unsigned long long* p2p_prof = nullptr;   // DLB_P2P_PROF=1 (development): device counters of the exchange kernel, printed when the net is destroyed
+    // DLB_P2P_PUSH=1: push the slot to the peers instead of letting them pull it.  Measured equal (8 GPUs: 158.3 vs 154.0 us per step): the
+    // exchange kernel's time is the wait for the slowest rank at its barrier (20-30 us at 2 GPUs, DLB_P2P_PROF=1), not the 1.2 MB per peer.
+    bool p2p_push = [] { const char* e = std::getenv("DLB_P2P_PUSH"); return e && e[0] == '1'; }();
     bool overlap_enabled = true;
     // DLB_HEAD_FOLD=1: the head sums the split partials of the layer in front of it instead of a separate finalize kernel.  Measured SLOWER
     // (70.1 vs 64.1 us per step at mini-batch 256: 30 dependent partial loads per element inside a one-warp-per-sample kernel), so it is off.
@@ -560,7 +605,16 @@ struct NetT final : dlb_net {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         free_workspace();
-        dev_free(params); dev_free(grads); dev_free(cost_dev); dev_free(perm_dev);
+        dev_free(params); dev_free(grads); dev_free(cost_dev);
+        for (int i = 0; i < 2; ++i) {
+            dev_free(perm_bufs[i]);
+#ifndef DLB_CUDA_EMU
+            if (perm_host[i]) cudaFreeHost(perm_host[i]);
+            if (perm_ev[i]) cudaEventDestroy(perm_ev[i]);
+#else
+            std::free(perm_host[i]);
+#endif
+        }
         drop_graphs();
 #ifndef DLB_CUDA_EMU
         if (side_head) { cudaStreamSynchronize(side_head); cudaStreamDestroy(side_head); }
@@ -582,6 +636,13 @@ struct NetT final : dlb_net {
         for (size_t r = 0; r < p2p_peer_regions.size(); ++r)
             if (p2p_peer_regions[r] && p2p_peer_regions[r] != p2p_region) cudaIpcCloseMemHandle(p2p_peer_regions[r]);
 #endif
+        if (p2p_prof) {
+            unsigned long long h[4] = {0, 0, 0, 0};
+            cudaMemcpy(h, p2p_prof, sizeof h, cudaMemcpyDeviceToHost);
+            if (h[0]) std::fprintf(stderr, "[dlb p2p rank %d] %llu exchange kernels: block 0 passed the barrier after %.2f us, finished its data after %.2f us (averages)\n", rank,
+                                   h[0], 1e-3 * (double)h[1] / (double)h[0], 1e-3 * (double)h[2] / (double)h[0]);
+            cudaFree(p2p_prof);
+        }
         if (p2p_region) cudaFree(p2p_region);
         dev_free(d_p2p_step);
         dev_free(cp_partial); dev_free(head_partial); dev_free(d_cursor); dev_free(mask_dev);
@@ -1094,7 +1155,7 @@ struct NetT final : dlb_net {
             if (rs.partial[i]) n_partial += rs.end[i] - (i == 0 ? 0 : rs.end[i - 1]);
         const int partial_blocks = (int)ceil_div<long long>(n_partial, 16);
         DLB_LAUNCH((reduce_update_kernel<R>), dim3((unsigned)(partial_blocks + ceil_div<size_t>((size_t)n_params, 256))), dim3(256), ctx->stream,
-                   params, grads, publish ? publish_buf(0) : (R*)nullptr, p2p_publish_bytes / sizeof(R), (const unsigned long long*)d_p2p_step,
+                   params, grads, publish ? publish_buf(0) : (R*)nullptr, (size_t)kMaxPeers * p2p_publish_bytes / sizeof(R), (const unsigned long long*)d_p2p_step,
                    (size_t)n_params, rs, partial_blocks, n_partial, do_update ? 1 : 0, static_cast<R>(1) + reg * l_rate,
                    l_rate * grad_norm, reg > static_cast<R>(0) ? 1 : 0, advance ? d_cursor : (int*)nullptr, advance);
     }
@@ -1118,7 +1179,7 @@ struct NetT final : dlb_net {
             TagScope tag_("p2p_reduce_update");
             DLB_LAUNCH((p2p_reduce_update_kernel<R>), dim3(2 * kNumSMs), dim3(256), ctx->stream, params, grads, (size_t)n_params, pt, world, rank,
                        d_p2p_step, reinterpret_cast<unsigned int*>(d_p2p_step + 1), segs, static_cast<R>(1) + reg * l_rate, l_rate * grad_norm,
-                       reg > static_cast<R>(0) ? 1 : 0, advance ? d_cursor : (int*)nullptr, advance);
+                       reg > static_cast<R>(0) ? 1 : 0, advance ? d_cursor : (int*)nullptr, advance, p2p_push ? 1 : 0, p2p_prof);
             return;
         }
 #endif
@@ -1170,7 +1231,7 @@ struct NetT final : dlb_net {
                 else distributed_finish(true, lr, reg_factor, global, advance);
             };
             // Only paths whose buffers are fixed replay a graph: the resident-data path (cursor-relative gather).
-            if (cursor && x == data_x) { run_graphed(StepKey{mine, global, lr, reg_factor, cost, x, p2p_on ? -1 : 0}, body); return; }
+            if (cursor && x == data_x) { run_graphed(StepKey{mine, global, lr, reg_factor, cost, x, p2p_on ? -1 : 0, gather_base}, body); return; }
             body();
             return;
         }
@@ -1206,14 +1267,10 @@ struct NetT final : dlb_net {
         const R reg_factor = static_cast<R>(lambda) / static_cast<R>(n_items);   // Net.inl:203
         std::vector<std::size_t> index_map((size_t)n_items);
         std::iota(index_map.begin(), index_map.end(), 0);                         // Net.inl:164-171
-        std::vector<int> perm32((size_t)n_items);
-        if (perm_cap < n_items) { dev_free(perm_dev); perm_dev = dev_alloc<int>((size_t)n_items); perm_cap = n_items; }
+        ensure_perm(n_items);
         for (int64_t e = 0; e < epochs; ++e) {
             std::ranges::shuffle(index_map, rng);                                 // Net.inl:158-161, 223
-            for (int64_t i = 0; i < n_items; ++i) perm32[(size_t)i] = (int)index_map[(size_t)i];
-            DLB_CUDA(cudaStreamSynchronize(ctx->stream));   // previous epoch's kernels may still read perm_dev
-            DLB_CUDA(cudaMemcpyAsync(perm_dev, perm32.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            DLB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(int), ctx->stream));
+            upload_permutation(index_map);
             int64_t start = 0;
             while (start < n_items) {
                 // Net.inl:235-236: fewer than 1.5 * batch_size remaining items are taken as one batch
@@ -1243,18 +1300,13 @@ struct NetT final : dlb_net {
         DLB_REQUIRE(batch > 0 && n_steps >= 0, "Invalid batch size / step count");
         use_device(ctx);
         const R reg_factor = static_cast<R>(lambda) / static_cast<R>(n_items);
-        if (perm_cap < n_items) { dev_free(perm_dev); perm_dev = dev_alloc<int>((size_t)n_items); perm_cap = n_items; ts_cursor = -1; }
+        if (perm_cap < n_items) { ensure_perm(n_items); ts_cursor = -1; }
         if ((int64_t)ts_index_map.size() != n_items) { ts_index_map.resize((size_t)n_items); std::iota(ts_index_map.begin(), ts_index_map.end(), 0); ts_cursor = -1; }
         int64_t consumed = 0;
         for (int64_t s = 0; s < n_steps; ++s) {
             if (ts_cursor < 0 || ts_cursor >= n_items) {
                 std::ranges::shuffle(ts_index_map, rng);
-                std::vector<int> perm32((size_t)n_items);
-                for (int64_t i = 0; i < n_items; ++i) perm32[(size_t)i] = (int)ts_index_map[(size_t)i];
-                DLB_CUDA(cudaStreamSynchronize(ctx->stream));
-                DLB_CUDA(cudaMemcpyAsync(perm_dev, perm32.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-                DLB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(int), ctx->stream));
-                DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+                upload_permutation(ts_index_map);
                 ts_cursor = 0;
             }
             const int64_t start = ts_cursor;
@@ -1467,7 +1519,7 @@ struct NetT final : dlb_net {
     void enable_tensor_cores(int mode) override { tc_mode = mode; drop_graphs(); }
     void enable_step_kernel(int mode) override { mg.enabled = mode != 0; }
 
-    // Allocates the shared region [publish 0 | publish 1 | flags] and returns its CUDA IPC handle (64 bytes).
+    // Allocates the shared region [parity 0: kMaxPeers slots | parity 1: kMaxPeers slots | flags] and returns its CUDA IPC handle (64 bytes).
     void p2p_export(void* handle64) override {
 #ifdef DLB_CUDA_EMU
         (void)handle64; throw std::runtime_error("peer memory is not available");
@@ -1475,7 +1527,7 @@ struct NetT final : dlb_net {
         use_device(ctx);
         if (!p2p_region) {
             p2p_publish_bytes = (((size_t)n_params * sizeof(R)) + 255) / 256 * 256;
-            const size_t total = 2 * p2p_publish_bytes + kMaxPeers * sizeof(unsigned long long);
+            const size_t total = 2 * (size_t)kMaxPeers * p2p_publish_bytes + kMaxPeers * sizeof(unsigned long long);
             DLB_CUDA(cudaMalloc((void**)&p2p_region, total));
             DLB_CUDA(cudaMemset(p2p_region, 0, total));
             d_p2p_step = dev_alloc<unsigned long long>(2);   // [step counter | blocks-done counter of the peer kernel]
@@ -1506,8 +1558,9 @@ struct NetT final : dlb_net {
             DLB_CUDA(cudaIpcOpenMemHandle(&p2p_peer_regions[(size_t)r], h, cudaIpcMemLazyEnablePeerAccess));
         }
         rank = rank_; world = world_; p2p_on = world_ > 1; p2p_step = 0;
+        if (std::getenv("DLB_P2P_PROF") && !p2p_prof) { p2p_prof = dev_alloc<unsigned long long>(4); DLB_CUDA(cudaMemset(p2p_prof, 0, 4 * sizeof(unsigned long long))); }
         DLB_CUDA(cudaMemset(d_p2p_step, 0, 2 * sizeof(unsigned long long)));
-        DLB_CUDA(cudaMemset(p2p_region + 2 * p2p_publish_bytes, 0, kMaxPeers * sizeof(unsigned long long)));
+        DLB_CUDA(cudaMemset(p2p_region + 2 * (size_t)kMaxPeers * p2p_publish_bytes, 0, kMaxPeers * sizeof(unsigned long long)));
 #endif
     }
 

@@ -1006,41 +1006,83 @@ __global__ void reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads, R
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
 struct PeerTable {
-    const unsigned char* region[kMaxPeers];   // peer r's shared region: [publish 0 | publish 1 | flags[world]]
-    size_t publish_bytes;
+    const unsigned char* region[kMaxPeers];   // peer r's shared region: [parity 0: kMaxPeers slots | parity 1: kMaxPeers slots | flags[kMaxPeers]]
+    size_t publish_bytes;                     // bytes of one slot (the flat gradient, rounded up to 256)
 };
 
-// The step counter lives on the device so that a captured CUDA graph of the step stays valid from step to step: the
-// publish kernel and the peer kernel read it (parity = which half is published, value + 1 = the barrier ticket); the LAST
-// block of the peer kernel to finish advances it (a block-completion counter), so no extra one-thread launch is needed.
+// Data-parallel finish over NVLink peer memory, ONE kernel per rank and step.  Rank r's gradient sum of its share of the mini-batch sits
+// in slot r of its own region (written by the reduction kernel in front of this one).
+//   pull (default)  the ranks barrier through flags in peer memory, then every rank READS slot r of peer r's region.
+//   push            every rank first WRITES its slot into slot r of every peer's region (posted stores), then the barrier, then each rank
+//                   sums the `world` slots of its OWN region (local reads).  DLB_P2P_PUSH=1.
+// Measured equal (8 GPUs: 154.0 us per step pull, 158.3 push; 2 GPUs: 309 / 312): the kernel's time is the wait for the slowest rank at the
+// barrier (block 0 passes it 15-33 us after the kernel starts, DLB_P2P_PROF=1), not the transfer of 1.2 MB per peer.
+// Either way the slots are summed in rank order (bit-identical total on every rank) and the update is applied in the same pass.
+// The step counter lives on the device so that a captured CUDA graph of the step stays valid from step to step: the reduction kernel and
+// this kernel read it (parity = which half is in use, value + 1 = the barrier ticket); the LAST block to finish advances it.
+// All CTAs of the grid are co-resident (2 x 148 x 256 threads), which the in-kernel waits rely on.
 template <class R> struct alignas(16) Vec16 { R v[16 / sizeof(R)]; };
 
 template <class R>
 __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads_total, size_t n, PeerTable peers, int world, int rank,
                                          unsigned long long* __restrict__ counter, unsigned int* __restrict__ blocks_done, UpdateSegments segs,
-                                         R param_scale, R grad_scale, int nontrivial_reg, int* __restrict__ cursor, int advance) {
+                                         R param_scale, R grad_scale, int nontrivial_reg, int* __restrict__ cursor, int advance, int push,
+                                         unsigned long long* __restrict__ prof) {   // prof (development, nullable): [launches, ns to barrier passed, ns to data done] of block 0
     constexpr int V = 16 / (int)sizeof(R);
+    unsigned long long t_in = 0;
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_in));
     const unsigned long long t = *counter;
     const unsigned long long step = t + 1;
-    const size_t half = (size_t)(t & 1) * peers.publish_bytes;
-    // (1) cross-GPU barrier.  The local gradient was written by the previous kernel in this stream, so it is complete.
-    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+    const size_t half = (size_t)(t & 1) * kMaxPeers * peers.publish_bytes;
+    const size_t flags_off = 2 * (size_t)kMaxPeers * peers.publish_bytes;
+    const size_t nv = n / V;
+    unsigned int* push_done = blocks_done + 1;
+    __shared__ int last_pusher;
+    auto post_flags = [&]() {   // threads < world of ONE block: tell every peer that this rank's slot is complete
+        if ((int)threadIdx.x < world) {
+            __threadfence_system();
+            volatile unsigned long long* remote =
+                reinterpret_cast<unsigned long long*>(const_cast<unsigned char*>(peers.region[threadIdx.x]) + flags_off) + rank;
+            *remote = step;
+        }
+    };
+    if (push) {
+        // (0) this rank's slot -> slot `rank` of every peer (16-byte posted stores; the tail elements as scalars)
+        const unsigned char* own = peers.region[rank] + half + (size_t)rank * peers.publish_bytes;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+            const Vec16<R> v = reinterpret_cast<const Vec16<R>*>(own)[i];
+            for (int r = 0; r < world; ++r)
+                if (r != rank) reinterpret_cast<Vec16<R>*>(const_cast<unsigned char*>(peers.region[r]) + half + (size_t)rank * peers.publish_bytes)[i] = v;
+        }
+        for (size_t e = nv * V + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+            const R v = reinterpret_cast<const R*>(own)[e];
+            for (int r = 0; r < world; ++r)
+                if (r != rank) reinterpret_cast<R*>(const_cast<unsigned char*>(peers.region[r]) + half + (size_t)rank * peers.publish_bytes)[e] = v;
+        }
         __threadfence_system();
-        volatile unsigned long long* remote =
-            reinterpret_cast<unsigned long long*>(const_cast<unsigned char*>(peers.region[threadIdx.x]) + 2 * peers.publish_bytes) + rank;
-        *remote = step;
+        __syncthreads();
+        if (threadIdx.x == 0) last_pusher = atomicAdd(push_done, 1u) == gridDim.x - 1 ? 1 : 0;
+        __syncthreads();
+        if (last_pusher) {   // every block's stores are out: raise the flags
+            if (threadIdx.x == 0) *push_done = 0u;
+            post_flags();
+        }
+    } else if (blockIdx.x == 0) {
+        post_flags();   // the local slot was written by the previous kernel in this stream, so it is complete
     }
+    // (1) cross-GPU barrier: wait until every rank's flag carries this step's ticket
     if ((int)threadIdx.x < world) {
         volatile unsigned long long* mine =
-            reinterpret_cast<unsigned long long*>(const_cast<unsigned char*>(peers.region[rank]) + 2 * peers.publish_bytes) + threadIdx.x;
+            reinterpret_cast<unsigned long long*>(const_cast<unsigned char*>(peers.region[rank]) + flags_off) + threadIdx.x;
         long long spin = 0;
         while (*mine < step) { if (++spin > (1LL << 31)) __trap(); }   // bounded: a lost peer becomes a launch failure, not a hang
         __threadfence_system();
     }
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0 && cursor) *cursor += advance;
-    // (2) + (3): 16 bytes per thread and rank, the loads of ALL ranks in flight together (one NVLink round trip, not `world` of them),
-    // then the sum in rank order (identical on every rank) and the update
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long tb; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tb)); atomicAdd(prof, 1ULL); atomicAdd(prof + 1, tb - t_in); }
+    // (2) + (3): 16 bytes per thread and rank, the loads of ALL ranks in flight together, the sum in rank order (identical on every rank), the update
+    auto slot = [&](int r) -> const unsigned char* { return peers.region[push ? rank : r] + half + (size_t)r * peers.publish_bytes; };
     auto update_one = [&](size_t e, R gsum) {
         grads_total[e] = gsum;
         int s = 0;
@@ -1049,7 +1091,6 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(R* __restrict__ 
         const R xv = p[e];
         p[e] = reg ? xv * param_scale + gsum * grad_scale : xv + gsum * grad_scale;
     };
-    const size_t nv = n / V;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
         Vec16<R> acc;
 #pragma unroll
@@ -1057,7 +1098,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(R* __restrict__ 
         for (int r0 = 0; r0 < world; r0 += 8) {
             Vec16<R> v[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) v[r] = reinterpret_cast<const Vec16<R>*>(peers.region[min(r0 + r, world - 1)] + half)[i];
+            for (int r = 0; r < 8; ++r) v[r] = reinterpret_cast<const Vec16<R>*>(slot(min(r0 + r, world - 1)))[i];
 #pragma unroll
             for (int r = 0; r < 8; ++r)
                 if (r0 + r < world) {
@@ -1070,11 +1111,12 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(R* __restrict__ 
     }
     for (size_t e = nv * V + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
         R gsum = R(0);
-        for (int r = 0; r < world; ++r) gsum += reinterpret_cast<const R*>(peers.region[r] + half)[e];
+        for (int r = 0; r < world; ++r) gsum += reinterpret_cast<const R*>(slot(r))[e];
         update_one(e, gsum);
     }
     // (4) the last block out advances the step counter (every block read it at the top)
     __syncthreads();
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long te; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(te)); atomicAdd(prof + 2, te - t_in); }
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(blocks_done, 1u) == gridDim.x - 1) { *blocks_done = 0u; *counter = step; }

@@ -42,7 +42,7 @@ namespace mega {
 
 constexpr int kThreads = 384;
 constexpr int kWarps = kThreads / 32;
-constexpr int IH = 28, IW = 28, OHW = 24, PHW = 12, NPOS = 144, NPIX = 576, IMG = 784, KK = 25;
+constexpr int IW = 28, OHW = 24, PHW = 12, NPOS = 144, NPIX = 576, IMG = 784, KK = 25;
 constexpr int kBiasBlk = 33;                  // float2 slots per 4 x 8 output block in the staged untied bias (32 + 1: bank spread)
 constexpr int kTasks = 18;                    // 6 x 3 blocks of 4 x 8 convolution outputs per sample
 constexpr int kSubMax = kThreads / kTasks;    // samples per pass of the convolution phases (21)

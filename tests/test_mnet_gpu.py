@@ -47,7 +47,8 @@ def test_reference_fixtures(real):
 
 @pytest.mark.parametrize("real", ["f32", "f64"])
 @pytest.mark.parametrize("depth,dims,acts,n", [(1, [3, 5], (ob.TANH,), 4), (6, [5, 9, 7, 4], (ob.SIGMOID, ob.TANH, ob.SIGMOID), 11),
-                                                (13, [17, 70, 33], (ob.RELU, ob.LINEAR), 37), (5, [40, 130], (ob.TANH,), 150)])
+                                                (13, [17, 70, 33], (ob.RELU, ob.LINEAR), 37), (5, [40, 130], (ob.TANH,), 150),
+                                                (4, [20, 256, 8], (ob.TANH, ob.SIGMOID), 300)])   # (the last one: single-launch recurrence contractions)
 def test_against_the_oracle(real, depth, dims, acts, n):
     """Ragged sizes (tiles of the contractions partly filled, split reductions), depth 1 (no recurrence), every element-wise activation."""
     dt = np.float32 if real == "f32" else np.float64
