@@ -636,6 +636,7 @@ struct NetT final : dlb_net {
         for (size_t r = 0; r < p2p_peer_regions.size(); ++r)
             if (p2p_peer_regions[r] && p2p_peer_regions[r] != p2p_region) cudaIpcCloseMemHandle(p2p_peer_regions[r]);
 #endif
+#ifndef DLB_CUDA_EMU
         if (p2p_prof) {
             unsigned long long h[4] = {0, 0, 0, 0};
             cudaMemcpy(h, p2p_prof, sizeof h, cudaMemcpyDeviceToHost);
@@ -643,6 +644,7 @@ struct NetT final : dlb_net {
                                    h[0], 1e-3 * (double)h[1] / (double)h[0], 1e-3 * (double)h[2] / (double)h[0]);
             cudaFree(p2p_prof);
         }
+#endif
         if (p2p_region) cudaFree(p2p_region);
         dev_free(d_p2p_step);
         dev_free(cp_partial); dev_free(head_partial); dev_free(d_cursor); dev_free(mask_dev);
@@ -1527,7 +1529,7 @@ struct NetT final : dlb_net {
         use_device(ctx);
         if (!p2p_region) {
             p2p_publish_bytes = (((size_t)n_params * sizeof(R)) + 255) / 256 * 256;
-            const size_t total = 2 * (size_t)kMaxPeers * p2p_publish_bytes + kMaxPeers * sizeof(unsigned long long);
+            const size_t total = 2 * (size_t)kMaxPeers * p2p_publish_bytes + (kMaxPeers + 1) * sizeof(unsigned long long);
             DLB_CUDA(cudaMalloc((void**)&p2p_region, total));
             DLB_CUDA(cudaMemset(p2p_region, 0, total));
             d_p2p_step = dev_alloc<unsigned long long>(2);   // [step counter | blocks-done counter of the peer kernel]
@@ -1560,7 +1562,7 @@ struct NetT final : dlb_net {
         rank = rank_; world = world_; p2p_on = world_ > 1; p2p_step = 0;
         if (std::getenv("DLB_P2P_PROF") && !p2p_prof) { p2p_prof = dev_alloc<unsigned long long>(4); DLB_CUDA(cudaMemset(p2p_prof, 0, 4 * sizeof(unsigned long long))); }
         DLB_CUDA(cudaMemset(d_p2p_step, 0, 2 * sizeof(unsigned long long)));
-        DLB_CUDA(cudaMemset(p2p_region + 2 * (size_t)kMaxPeers * p2p_publish_bytes, 0, kMaxPeers * sizeof(unsigned long long)));
+        DLB_CUDA(cudaMemset(p2p_region + 2 * (size_t)kMaxPeers * p2p_publish_bytes, 0, (kMaxPeers + 1) * sizeof(unsigned long long)));
 #endif
     }
 

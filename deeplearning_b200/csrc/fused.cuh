@@ -1006,7 +1006,7 @@ __global__ void reduce_update_kernel(R* __restrict__ p, R* __restrict__ grads, R
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
 struct PeerTable {
-    const unsigned char* region[kMaxPeers];   // peer r's shared region: [parity 0: kMaxPeers slots | parity 1: kMaxPeers slots | flags[kMaxPeers]]
+    const unsigned char* region[kMaxPeers];   // peer r's shared region: [parity 0: kMaxPeers slots | parity 1: kMaxPeers slots | flags[kMaxPeers] | local release word]
     size_t publish_bytes;                     // bytes of one slot (the flat gradient, rounded up to 256)
 };
 
@@ -1070,15 +1070,28 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(R* __restrict__ 
     } else if (blockIdx.x == 0) {
         post_flags();   // the local slot was written by the previous kernel in this stream, so it is complete
     }
-    // (1) cross-GPU barrier: wait until every rank's flag carries this step's ticket
-    if ((int)threadIdx.x < world) {
-        volatile unsigned long long* mine =
-            reinterpret_cast<unsigned long long*>(const_cast<unsigned char*>(peers.region[rank]) + flags_off) + threadIdx.x;
-        long long spin = 0;
-        while (*mine < step) { if (++spin > (1LL << 31)) __trap(); }   // bounded: a lost peer becomes a launch failure, not a hang
-        __threadfence_system();
+    // (1) cross-GPU barrier: wait until every rank's flag carries this step's ticket.  Only block 0 polls the flags the peers write
+    // (tools/flag_probe.cu: a flag hop takes 3.8 us with one polling block and 8.8 us when all 296 blocks poll the same line); it then
+    // releases the other blocks through a local word.
+    volatile unsigned long long* go = reinterpret_cast<unsigned long long*>(const_cast<unsigned char*>(peers.region[rank]) + flags_off) + kMaxPeers;
+    if (blockIdx.x == 0) {
+        if ((int)threadIdx.x < world) {
+            volatile unsigned long long* mine =
+                reinterpret_cast<unsigned long long*>(const_cast<unsigned char*>(peers.region[rank]) + flags_off) + threadIdx.x;
+            long long spin = 0;
+            while (*mine < step) { if (++spin > (1LL << 31)) __trap(); }   // bounded: a lost peer becomes a launch failure, not a hang
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { *go = step; __threadfence(); }
+    } else {
+        if (threadIdx.x == 0) {
+            long long spin = 0;
+            while (*go < step) { __nanosleep(64); if (++spin > (1LL << 28)) __trap(); }
+            __threadfence_system();
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0 && cursor) *cursor += advance;
     if (prof && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long tb; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tb)); atomicAdd(prof, 1ULL); atomicAdd(prof + 1, tb - t_in); }
     // (2) + (3): 16 bytes per thread and rank, the loads of ALL ranks in flight together, the sum in rank order (identical on every rank), the update
