@@ -388,6 +388,7 @@ struct NetT final : dlb_net {
     bool conv28_for(int64_t B) const { return c28.ok && c28.mode != 0 && (c28.mode == 1 || B >= c28.min_batch); }
     R* cp_partial = nullptr; int cp_grid = 0;          // [cp_grid][cp.n_par] per-CTA partial gradients of the conv stage
     int cp_rows = 0;                                    // rows of cp_partial the last backward wrote (the reduction sums these)
+    bool imap1_holds_selectors = false;                 // the last fused forward left one-byte window selectors in imap[1] (conv28.cu)
     R* head_partial = nullptr; int head_chunks = 0;     // [head_chunks][n * (in_n + 1)]
     int head_chunk_cap = 0;
     int* d_cursor = nullptr;                            // device-side offset of the current batch in the epoch permutation
@@ -837,6 +838,7 @@ struct NetT final : dlb_net {
     // ---- forward / backward over one batch --------------------------------------------------------------------
     // x: [rows][in0] device; gather (nullable): batch slot -> row of x.
     void forward(int B, const R* x, const int* gather, bool traces) {
+        imap1_holds_selectors = false;
         LaunchCtx lc = ctx->lc();
         lc.tc = std::is_same_v<R, float> && tc_for(B);
         lc.gather_rows = x == data_x ? n_items : (long long)cap;
@@ -944,6 +946,7 @@ struct NetT final : dlb_net {
                 if (conv28_for(B)) {   // (the index-map buffer holds the one-byte window selectors here)
                     conv28::forward(st, c28.stage, x, gather_base, cursor, params + Y.param_off, params + Y.param_off + Y.bias_n, out[1],
                                     reinterpret_cast<unsigned char*>(imap[1]), B);
+                    imap1_holds_selectors = true;
                     done = true;
                 }
             }
@@ -952,6 +955,7 @@ struct NetT final : dlb_net {
                 const int grid = std::min((int)ceil_div(B, plan.cp.spc), kNumSMs);
                 conv_pool_forward<R>(st, plan.cp, grid, x, gather_base, cursor, params + Y.param_off, params + Y.param_off + Y.bias_n,
                                      out[1], imap[1], B);
+                imap1_holds_selectors = false;
             }
             l = 2;
         }
@@ -1457,6 +1461,23 @@ struct NetT final : dlb_net {
         }
         DLB_REQUIRE(what == DLB_BUF_GRADIENT || last_B > 0, "No forward/backward pass has run yet");
         DLB_REQUIRE((size_t)bytes >= need, "Destination buffer too small");
+        if (what == DLB_BUF_INDEX_MAP && layer == 1 && imap1_holds_selectors) {
+            // the large-batch first stage keeps one byte per window (position 0..3 inside the 2 x 2 window, 255 = none): expand it to the
+            // reference's Trace.IndexMapping - the flat index of the extremum inside the PLayer's input (PLayer.inl:115-138)
+            const auto& P = layers[1].s;
+            const int OW = P.in_w, POW = P.in_w / 2, NPOS = (P.in_h / 2) * POW, F = P.in_c;
+            const size_t n = b * (size_t)layers[1].out_n;
+            std::vector<unsigned char> sel(n);
+            DLB_CUDA(cudaMemcpyAsync(sel.data(), src, n, cudaMemcpyDeviceToHost, ctx->stream));
+            DLB_CUDA(cudaStreamSynchronize(ctx->stream));
+            int* out_map = static_cast<int*>(dst);
+            for (size_t i = 0; i < n; ++i) {
+                const int w = (int)(i % (size_t)NPOS), f = (int)((i / (size_t)NPOS) % (size_t)F);
+                const int py = w / POW, px = w - py * POW, q = sel[i];
+                out_map[i] = q > 3 ? -1 : (f * P.in_h + 2 * py + (q >> 1)) * OW + 2 * px + (q & 1);
+            }
+            return;
+        }
         DLB_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
         DLB_CUDA(cudaStreamSynchronize(ctx->stream));
     }

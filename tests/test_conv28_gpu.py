@@ -1,6 +1,6 @@
 """GPU parity of the large-batch kernels of the first LeNet stage (csrc/conv28.cu: dense FFMA2 convolution + untied bias +
 activation + 2x2 max|min pooling forward, routed-gradient correlation backward, one-byte window selectors).  They take over
-from mini-batch 1024 up (DLB_CONV28_MIN); DLB_CONV28=1 forces them at every size so that ragged passes and sample groups are
+from mini-batch 128 up (DLB_CONV28_MIN); DLB_CONV28=1 forces them at every size so that ragged passes and sample groups are
 covered at sizes the oracle finishes in seconds.  Checked against the CPU oracle (CLayer.inl:108-197, PLayer.inl:115-170),
 against the small-batch kernels of fused.cuh (forward bit for bit), and for run-to-run bit-identity."""
 import numpy as np
@@ -52,8 +52,8 @@ def test_learn_matches_oracle(name, batch, n_items, monkeypatch):
 
 
 def test_default_threshold_large_batch_vs_oracle(monkeypatch):
-    """No environment override: mini-batch 1100 crosses the threshold (53 passes of 21 samples over the CTA columns, 8 sample groups
-    of 137-138 in the backward); three steps of LeNet against the oracle."""
+    """No environment override: mini-batch 1100 is above the threshold and uses the 512-thread forward (40 passes of 28 samples over
+    the CTA columns; 14 sample groups of 78-79 in the backward); three steps of LeNet against the oracle."""
     specs, cost = VARIANTS["lenet"]
     orc, gpu = make(specs, 5, None, monkeypatch)
     n, batch = 3300, 1100
@@ -70,7 +70,7 @@ def test_forward_is_bit_identical_to_the_small_batch_kernel(batch, monkeypatch):
     """Same tap order, same fused multiply-adds, bias added last: the pooled values of both forward kernels are the same bits; the
     parameters after the step agree within the bar (the backward sums in a different order)."""
     specs, cost = VARIANTS["lenet"]
-    pooled, params = [], []
+    pooled, params, maps = [], [], []
     x = y = None
     for mode in ("1", "0"):
         orc, gpu = make(specs, 7, mode, monkeypatch)
@@ -78,8 +78,10 @@ def test_forward_is_bit_identical_to_the_small_batch_kernel(batch, monkeypatch):
         gpu.set_dataset(x, y)
         gpu.step_indices(np.arange(batch, dtype=np.int64), 0.05, dl.CostFunctionId(cost), reg_factor=0.001)
         gpu._last_batch = batch
-        pooled.append(gpu.read(dl.BUF_OUTPUT, 1)); params.append(gpu.get_params())
+        pooled.append(gpu.read(dl.BUF_OUTPUT, 1)); params.append(gpu.get_params()); maps.append(gpu.read(dl.BUF_INDEX_MAP, 1))
     assert np.array_equal(pooled[0], pooled[1]), "pooled values differ between the two forward kernels"
+    # the one-byte window selectors read back as the reference's Trace.IndexMapping (dlb_net_read expands them)
+    assert maps[0].dtype == maps[1].dtype and np.array_equal(maps[0], maps[1]), "arg-max index maps differ"
     H.assert_close("one step, conv28 vs fused.cuh kernels", params[0], params[1], "f32", rtol_mult=20)
 
 
