@@ -451,7 +451,9 @@ def main():
                             "share_of_step": top["share"], "us_per_launch": top["us_per_launch"]}
         line["kernels"] = kernels[:12]
         bps = step_bytes_per_sample(net, batch, sz)
-        line["step_roofline"] = {"bytes_per_sample": bps, "roofline_samples_per_s": peak * 1e9 / bps, "frac": value / (peak * 1e9 / bps)}
+        line["step_roofline"] = {"bytes_per_sample": bps, "roofline_samples_per_s": peak * 1e9 / bps, "frac": value / (peak * 1e9 / bps),
+                                 "note": "bytes = SURVEY 8(d)'s per-kernel (UNFUSED) accounting summed over the step: a fused step moves fewer bytes, "
+                                         "so this fraction contains fusion credit and is not an achieved-bandwidth figure (see traffic / kernels)"}
 
         # the data-parallel workload's per-GPU share on one GPU, for reading the scaling series; with its own kernel table
         net.train_steps(8192, 3, LR, cost_id, LAMBDA)
@@ -471,6 +473,7 @@ def main():
                                    "frac_of_hbm_peak": (ab / (us * 1e-6) / 1e9 / peak) if ab else None})
         bps8 = step_bytes_per_sample(net, 8192, sz)
         big["step_roofline_frac"] = big["value"] / (peak * 1e9 / bps8)
+        big["step_roofline_note"] = "against the UNFUSED per-kernel byte accounting of SURVEY 8(d): fusion credit, not achieved DRAM bandwidth (per-kernel frac_of_hbm_peak above is)"
         line["config5_on_1_gpu"] = big
 
         pk = measured_peaks()

@@ -254,11 +254,13 @@ __global__ void __launch_bounds__(kBT, 1) conv28_backward_kernel(const BwdArgs a
         // out of the barrier the FMA pipe of a scheduler then serves one warp while the other two are in their latency-bound parts.
         auto bias_sums = [&] {
             if (tid < 2 * NPOS) {
-                for (int ss = 0; ss < ns; ++ss) {
-                    const unsigned q = sb[ss * 2 * NPOS + tid];
+#pragma unroll
+                for (int ss = 0; ss < kBS; ++ss) {   // fully unrolled (no loop bookkeeping); samples beyond ns read as "no position"; one predicated add per position
+                    const unsigned q = ss < ns ? (unsigned)sb[ss * 2 * NPOS + tid] : 255u;
                     const float gz = deriv_from_value<float>(a.act, pv[ss * 2 * NPOS + tid]) * gv[ss * 2 * NPOS + tid];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) db[k] += q == (unsigned)k ? gz : 0.f;
+                    for (int k = 0; k < 4; ++k)
+                        asm("{ .reg .pred p; setp.eq.u32 p, %2, %3; @p add.f32 %0, %0, %1; }" : "+f"(db[k]) : "f"(gz), "r"(q), "r"((unsigned)k));
                 }
             }
         };
@@ -292,15 +294,17 @@ __global__ void __launch_bounds__(kBT, 1) conv28_backward_kernel(const BwdArgs a
                 const float4 v0 = q[0], v1 = q[1], v2 = q[2];
                 xr[0] = v0.x; xr[1] = v0.y; xr[2] = v0.z; xr[3] = v0.w; xr[4] = v1.x; xr[5] = v1.y; xr[6] = v1.z; xr[7] = v1.w;
                 xr[8] = v2.x; xr[9] = v2.y; xr[10] = v2.z; xr[11] = v2.w;
+                // column outermost: the up to 20 multiply-adds of one column (4 gradient rows x 5 taps) go to 20 DIFFERENT accumulators, so
+                // consecutive FFMA2 are independent (tap-outermost order chained 8 of them through one accumulator)
 #pragma unroll
-                for (int dy = 0; dy < 4; ++dy) {
-                    const int ky = r - dy;
-                    if (ky < 0 || ky > 4) continue;
+                for (int c = 0; c < 8; ++c)
 #pragma unroll
-                    for (int kx = 0; kx < 5; ++kx)
+                    for (int dy = 0; dy < 4; ++dy) {
+                        const int ky = r - dy;
+                        if (ky < 0 || ky > 4) continue;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) dk[ky * 5 + kx] = ffma2_bcast(Gd[dy][c], xr[c + kx], dk[ky * 5 + kx]);
-                }
+                        for (int kx = 0; kx < 5; ++kx) dk[ky * 5 + kx] = ffma2_bcast(Gd[dy][c], xr[c + kx], dk[ky * 5 + kx]);
+                    }
             }
         }
         if (!bias_first) bias_sums();
