@@ -249,6 +249,106 @@ inline DeviceBuffer<Real> pack(const std::vector<GpuDC::tensor_t>& items) {
     return out;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Per-sample layer API on GpuDC containers: what ALayer<GpuDC>::act / backpropagate / update do for ONE item
+// (ALayer.h:205-257; GPU originals: CudaTensor::convolve / convolution_gradient / min_max_pool / average_pool ..., CudaMatrix::mul_add /
+// transpose_mul, CudaTensor.cu:395-761, CudaMatrix.cu:227-498).  Every call is one launch of the library's batched operator with
+// batch = 1; the trace / gradient arguments are the reference's own LayerTraceData<GpuDC> / LayerData<GpuDC> / LayerGradient<GpuDC>.
+// The batched trainer (learn above) is the fast path; this is the compatibility surface for code written against single items.
+// ---------------------------------------------------------------------------------------------------------------------------------
+namespace ops {   // Real -> the _f32 / _f64 entry points
+inline int conv_forward(dlb_context* c, const dlb_layer_spec* s, const float* x, const float* b, const float* w, float* y, float* d) { return dlb_conv_forward_f32(c, s, 1, x, nullptr, b, w, y, d); }
+inline int conv_forward(dlb_context* c, const dlb_layer_spec* s, const double* x, const double* b, const double* w, double* y, double* d) { return dlb_conv_forward_f64(c, s, 1, x, nullptr, b, w, y, d); }
+inline int conv_backward(dlb_context* c, const dlb_layer_spec* s, const float* x, const float* dl, const float* dv, const float* w, float* g, float* db, float* dw, float* dx, double sc) { return dlb_conv_backward_f32(c, s, 1, x, nullptr, dl, dv, w, g, db, dw, dx, sc); }
+inline int conv_backward(dlb_context* c, const dlb_layer_spec* s, const double* x, const double* dl, const double* dv, const double* w, double* g, double* db, double* dw, double* dx, double sc) { return dlb_conv_backward_f64(c, s, 1, x, nullptr, dl, dv, w, g, db, dw, dx, sc); }
+inline int pool_forward(dlb_context* c, const dlb_layer_spec* s, const float* x, float* y, int32_t* m) { return dlb_pool_forward_f32(c, s, 1, x, y, m); }
+inline int pool_forward(dlb_context* c, const dlb_layer_spec* s, const double* x, double* y, int32_t* m) { return dlb_pool_forward_f64(c, s, 1, x, y, m); }
+inline int pool_backward(dlb_context* c, const dlb_layer_spec* s, const float* dl, const int32_t* m, float* dx) { return dlb_pool_backward_f32(c, s, 1, dl, m, dx); }
+inline int pool_backward(dlb_context* c, const dlb_layer_spec* s, const double* dl, const int32_t* m, double* dx) { return dlb_pool_backward_f64(c, s, 1, dl, m, dx); }
+inline int full_forward(dlb_context* c, const dlb_layer_spec* s, const float* x, const float* b, const float* w, float* y, float* d) { return dlb_full_forward_f32(c, s, 1, x, nullptr, b, w, y, d); }
+inline int full_forward(dlb_context* c, const dlb_layer_spec* s, const double* x, const double* b, const double* w, double* y, double* d) { return dlb_full_forward_f64(c, s, 1, x, nullptr, b, w, y, d); }
+inline int full_backward(dlb_context* c, const dlb_layer_spec* s, const float* x, const float* dl, const float* dv, const float* w, float* g, float* db, float* dw, float* dx, double sc) { return dlb_full_backward_f32(c, s, 1, x, nullptr, dl, dv, w, g, db, dw, dx, sc); }
+inline int full_backward(dlb_context* c, const dlb_layer_spec* s, const double* x, const double* dl, const double* dv, const double* w, double* g, double* db, double* dw, double* dx, double sc) { return dlb_full_backward_f64(c, s, 1, x, nullptr, dl, dv, w, g, db, dw, dx, sc); }
+inline int sgd_update(dlb_context* c, float* p, const float* g, int64_t n, int reg, double lr, double rf, double gs) { return dlb_sgd_update_f32(c, p, g, n, reg, lr, rf, gs); }
+inline int sgd_update(dlb_context* c, double* p, const double* g, int64_t n, int reg, double lr, double rf, double gs) { return dlb_sgd_update_f64(c, p, g, n, reg, lr, rf, gs); }
+inline int cost_gradient(dlb_context* c, int id, int n, const float* o, const float* r, float* g) { return dlb_cost_gradient_f32(c, id, 1, n, o, r, nullptr, g); }
+inline int cost_gradient(dlb_context* c, int id, int n, const double* o, const double* r, double* g) { return dlb_cost_gradient_f64(c, id, 1, n, o, r, nullptr, g); }
+}  // namespace ops
+
+/// One reference layer mirrored on the device: its descriptor and its parameters [biases | weights or filters] in one buffer.
+class GpuLayer {
+    dlb_layer_spec _spec{};
+    DeviceBuffer<Real> _params;
+    std::size_t _bias_n = 0, _weight_n = 0;
+    mutable DeviceBuffer<Real> _g;   // dC/dz scratch of backpropagate
+    static std::vector<const BasicCollection*> containers(const ALayer<CpuDC>& layer) {
+        std::vector<const BasicCollection*> out;
+        if (auto n = dynamic_cast<const NLayer<CpuDC>*>(&layer)) { out.push_back(&n->biases()); out.push_back(&n->weights()); }
+        else if (auto c = dynamic_cast<const CLayer<CpuDC>*>(&layer)) { out.push_back(&c->biases()); for (const auto& f : c->filters()) out.push_back(&f); }
+        return out;
+    }
+public:
+    explicit GpuLayer(const ALayer<CpuDC>& layer) : _spec(to_spec(layer)) {
+        std::vector<Real> flat;
+        const auto cs = containers(layer);
+        for (std::size_t i = 0; i < cs.size(); ++i) { if (i == 0) _bias_n = cs[i]->size(); else _weight_n += cs[i]->size(); flat.insert(flat.end(), cs[i]->begin(), cs[i]->end()); }
+        if (!flat.empty()) _params.upload(flat.data(), flat.size());
+    }
+    const dlb_layer_spec& spec() const { return _spec; }
+    Index3d in_size() const { return { _spec.in_c, _spec.in_h, _spec.in_w }; }
+    Index3d out_size(const ALayer<CpuDC>& like) const { return like.out_size(); }
+    const Real* biases() const { return _params.begin(); }
+    const Real* weights() const { return _params.begin() + _bias_n; }
+
+    /// ALayer<D>::act for one item (CLayer.inl:108-137, PLayer.inl:115-138, NLayer.inl:131-142); `output` must have the layer's output size
+    void act(const GpuTensor& input, GpuTensor& output, LayerTraceData<GpuDC>* const trace) const {
+        Real* deriv = nullptr; int32_t* map = nullptr;
+        if (trace && _spec.type != DLB_LAYER_PULL) { trace->Derivatives.resize(output.size_3d()); deriv = trace->Derivatives.begin(); }
+        if (trace && _spec.type == DLB_LAYER_PULL && _spec.pool_type != DLB_POOL_AVERAGE) { trace->IndexMapping.resize(output.size()); map = trace->IndexMapping.begin(); }
+        switch (_spec.type) {
+        case DLB_LAYER_CONVOLUTION: check(ops::conv_forward(context(), &_spec, input.begin(), biases(), weights(), output.begin(), deriv)); break;
+        case DLB_LAYER_PULL: check(ops::pool_forward(context(), &_spec, input.begin(), output.begin(), map)); break;
+        default: check(ops::full_forward(context(), &_spec, input.begin(), biases(), weights(), output.begin(), deriv)); break;
+        }
+    }
+    /// ALayer<D>::backpropagate for one item (CLayer.inl:139-197, PLayer.inl:140-168, NLayer.inl:144-171): layer_grad.data = {biases, weights}
+    /// as ONE device tensor each (filters concatenated), scaled accumulation as in the reference (gradient_scale_factor)
+    void backpropagate(const GpuTensor& deltas, const LayerData<GpuDC>& processing_data, GpuTensor& input_grad, LayerGradient<GpuDC>& layer_grad,
+                       const bool evaluate_input_gradient = true, const Real gradient_scale_factor = static_cast<Real>(0)) const {
+        Real* dx = nullptr;
+        if (evaluate_input_gradient) { input_grad.resize(in_size()); dx = input_grad.begin(); }
+        if (_spec.type == DLB_LAYER_PULL) {
+            if (dx) check(ops::pool_backward(context(), &_spec, deltas.begin(), processing_data.Trace.IndexMapping.begin(), dx));
+            return;
+        }
+        if (layer_grad.data.size() != 2) {
+            layer_grad.data.resize(2);
+            layer_grad.data[0] = GpuTensor(Index3d{ 1, 1, static_cast<long long>(_bias_n) }, true);
+            layer_grad.data[1] = GpuTensor(Index3d{ 1, 1, static_cast<long long>(_weight_n) }, true);
+        }
+        _g.resize(deltas.size());
+        if (_spec.type == DLB_LAYER_CONVOLUTION)
+            check(ops::conv_backward(context(), &_spec, processing_data.Input.begin(), deltas.begin(), processing_data.Trace.Derivatives.begin(), weights(), _g.begin(),
+                                     layer_grad.data[0].begin(), layer_grad.data[1].begin(), dx, gradient_scale_factor));
+        else
+            check(ops::full_backward(context(), &_spec, processing_data.Input.begin(), deltas.begin(), processing_data.Trace.Derivatives.begin(), weights(), _g.begin(),
+                                     layer_grad.data[0].begin(), layer_grad.data[1].begin(), dx, gradient_scale_factor));
+    }
+    /// ALayer<D>::update (ALayer.inl:97-122): biases unregularised, weights with the regularisation factor; l_rate is signed as in the reference
+    void update(const LayerGradient<GpuDC>& gradient, const Real& l_rate, const Real& reg_factor, const Real& grad_scale_factor = static_cast<Real>(1)) {
+        if (_spec.type == DLB_LAYER_PULL) return;
+        check(ops::sgd_update(context(), _params.begin(), gradient.data[0].begin(), static_cast<int64_t>(_bias_n), 0, l_rate, reg_factor, grad_scale_factor));
+        check(ops::sgd_update(context(), _params.begin() + _bias_n, gradient.data[1].begin(), static_cast<int64_t>(_weight_n), 1, l_rate, reg_factor, grad_scale_factor));
+    }
+    /// the parameters as one host vector [biases | weights] (the layer's containers in the reference's order)
+    std::vector<Real> params_to_host() const { return _params.to_stdvector(); }
+};
+
+/// CostFunction<T>::deriv_in_place for one item on the device (CostFunction.inl:47-51)
+inline void cost_deriv_in_place(GpuTensor& in_out, const GpuTensor& reference, const CostFunctionId& id) {
+    check(ops::cost_gradient(context(), static_cast<int>(id), static_cast<int>(in_out.size()), in_out.begin(), reference.begin(), in_out.begin()));
+}
+
 /// A libdlb200 net mirroring a reference net (layers, parameters, keep rates).
 class DeviceNet {
     dlb_net* _net = nullptr;

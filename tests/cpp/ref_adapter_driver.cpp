@@ -173,6 +173,88 @@ int rad_check_containers(const dlb_layer_spec* specs, int n_layers, unsigned see
     } catch (const std::runtime_error& e) { g_err = e.what(); return 2; } catch (...) { g_err = "unknown exception"; return 3; }
 }
 
+// SURVEY.md section 8 f4 - the per-sample layer API of the binding (GpuLayer::act / backpropagate / update on GpuDC containers, one batched
+// operator launch with batch = 1 each) against the reference's own layers on the host, layer by layer, the way the reference's GPU tests
+// compare the two data contexts (DeepLearningCudaTest/NetLayersCudaTest.cpp:77-172): outputs, Trace.Derivatives, Trace.IndexMapping, input
+// gradients, layer gradients (with the scaled accumulation: two items, the second with gradient_scale_factor = 0.5), parameters after
+// ALayer::update.  max_rel_err: largest |got - want| / (|want| + scale); index maps must be equal.
+int rad_check_per_sample(const dlb_layer_spec* specs, int n_layers, unsigned seed, const Real* x, const Real* y, int cost_id, double* max_rel_err,
+                         int64_t* index_map_mismatches) {
+    try {
+        Net<CpuDC>::reset_random_generator(seed);
+        Net<CpuDC> net;
+        build(net, specs, n_layers);
+        const auto L = net.layers_count();
+        const Index3d in{ specs[0].in_c, specs[0].in_h, specs[0].in_w };
+        const Index3d out = net[L - 1].out_size();
+        const auto items = to_tensors(x, 2, in), refs = to_tensors(y, 2, out);
+        const CostFunction<Tensor> cost_cpu(static_cast<CostFunctionId>(cost_id));
+        *max_rel_err = 0; *index_map_mismatches = 0;
+        auto rel = [&](const Real* got, const Real* want, std::size_t n) {
+            double scale = 0; for (std::size_t i = 0; i < n; ++i) scale = std::max(scale, std::abs((double)want[i]));
+            for (std::size_t i = 0; i < n; ++i) *max_rel_err = std::max(*max_rel_err, std::abs((double)got[i] - (double)want[i]) / (std::abs((double)want[i]) + scale + 1e-30));
+        };
+        auto rel_t = [&](const GpuDC::tensor_t& got, const BasicCollection& want) {
+            if (got.size() != want.size()) throw std::runtime_error("per-sample API: tensor sizes differ");
+            const Tensor h = got.to_host(); rel(h.begin(), want.begin(), want.size());
+        };
+        std::vector<dlb200_binding::GpuLayer> dev;
+        for (std::size_t l = 0; l < L; ++l) dev.emplace_back(net[l]);
+        std::vector<LayerGradient<CpuDC>> g_cpu(L);
+        std::vector<LayerGradient<GpuDC>> g_gpu(L);
+        for (std::size_t l = 0; l < L; ++l) net[l].allocate(g_cpu[l], true);
+        for (int item = 0; item < 2; ++item) {
+            const Real scale = item == 0 ? Real(0) : Real(0.5);
+            // forward with traces, both sides
+            std::vector<LayerData<CpuDC>> d_cpu(L); std::vector<LayerData<GpuDC>> d_gpu(L);
+            Tensor cur = items[(std::size_t)item]; GpuDC::tensor_t cur_g = GpuDC::from_host(cur);
+            for (std::size_t l = 0; l < L; ++l) {
+                cur.reshape(net[l].in_size());
+                d_cpu[l].Input = cur;
+                d_gpu[l].Input = cur_g;
+                Tensor nxt; net[l].act(cur, nxt, &d_cpu[l].Trace);
+                GpuDC::tensor_t nxt_g(net[l].out_size(), false);
+                dev[l].act(cur_g, nxt_g, &d_gpu[l].Trace);
+                rel_t(nxt_g, nxt);
+                if (d_cpu[l].Trace.Derivatives.size()) rel_t(d_gpu[l].Trace.Derivatives, d_cpu[l].Trace.Derivatives);
+                if (d_cpu[l].Trace.IndexMapping.size() != d_gpu[l].Trace.IndexMapping.size()) throw std::runtime_error("per-sample API: index map sizes differ");
+                const auto map_g = d_gpu[l].Trace.IndexMapping.to_stdvector();
+                for (std::size_t i = 0; i < map_g.size(); ++i) *index_map_mismatches += map_g[i] != d_cpu[l].Trace.IndexMapping[i];
+                cur = std::move(nxt); cur_g = std::move(nxt_g);
+            }
+            // cost derivative, then backward through every layer
+            cost_cpu.deriv_in_place(cur, refs[(std::size_t)item]);
+            const GpuDC::tensor_t ref_g = GpuDC::from_host(refs[(std::size_t)item]);
+            dlb200_binding::cost_deriv_in_place(cur_g, ref_g, static_cast<CostFunctionId>(cost_id));
+            rel_t(cur_g, cur);
+            for (long long l = (long long)L - 1; l >= 0; --l) {
+                Tensor in_grad; GpuDC::tensor_t in_grad_g;
+                cur.reshape(net[(std::size_t)l].out_size());   // (an NLayer hands its input gradient back flat)
+                net[(std::size_t)l].backpropagate(cur, d_cpu[(std::size_t)l], in_grad, g_cpu[(std::size_t)l], l != 0, scale);
+                dev[(std::size_t)l].backpropagate(cur_g, d_gpu[(std::size_t)l], in_grad_g, g_gpu[(std::size_t)l], l != 0, scale);
+                if (l != 0) { rel_t(in_grad_g, in_grad); cur = std::move(in_grad); cur_g = std::move(in_grad_g); }
+            }
+        }
+        // gradients (after the scaled accumulation of the second item) and the update
+        for (std::size_t l = 0; l < L; ++l) {
+            std::vector<Real> flat;
+            for (const auto& t : g_cpu[l].data) flat.insert(flat.end(), t.begin(), t.end());
+            if (flat.empty()) continue;
+            if (g_gpu[l].data.size() != 2 || g_gpu[l].data[0].size() + g_gpu[l].data[1].size() != flat.size()) throw std::runtime_error("per-sample API: gradient sizes differ");
+            const Tensor gb = g_gpu[l].data[0].to_host(), gw = g_gpu[l].data[1].to_host();
+            rel(gb.begin(), flat.data(), gb.size()); rel(gw.begin(), flat.data() + gb.size(), gw.size());
+            net[l].update(g_cpu[l], Real(-0.05), Real(0.01));
+            dev[l].update(g_gpu[l], Real(-0.05), Real(0.01));
+        }
+        const auto want = dlb200_binding::flatten_params(net);
+        std::vector<Real> got;
+        for (std::size_t l = 0; l < L; ++l) { const auto p = dev[l].params_to_host(); got.insert(got.end(), p.begin(), p.end()); }
+        if (got.size() != want.size()) throw std::runtime_error("per-sample API: parameter counts differ");
+        rel(got.data(), want.data(), want.size());
+        return 0;
+    } catch (const std::runtime_error& e) { g_err = e.what(); return 2; } catch (...) { g_err = "unknown exception"; return 3; }
+}
+
 int rad_run(const dlb_layer_spec* specs, int n_layers, unsigned init_seed, unsigned learn_seed, const Real* x, const Real* y, int64_t n_items,
             int64_t batch, int64_t epochs, double lr, int cost_id, double lambda, int cpu_threads, Real* params_cpu, Real* params_gpu,
             int32_t* classes_cpu, int32_t* classes_gpu, int32_t* epochs_seen_gpu, double* eval_cost_gpu, double* eval_correct_gpu) {

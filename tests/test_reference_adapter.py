@@ -159,3 +159,41 @@ def test_reference_containers_from_device_buffers(name, n_items, real):
     assert 0 <= eg.value < bar, f"gradient containers: max relative error {eg.value:.3e}"
     assert 0 <= et.value < bar, f"trace containers: max relative error {et.value:.3e}"
     assert mism.value == 0, f"{mism.value} arg-max indices differ"
+
+
+def _per_sample_case(real, name, x, y, cost):
+    lib = load(real)
+    vp = C.c_void_p
+    lib.rad_check_per_sample.argtypes = [C.POINTER(ob.LayerSpec), C.c_int, C.c_uint, vp, vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    specs = NETS[name]
+    arr = (ob.LayerSpec * len(specs))(*specs)
+    err, mism = C.c_double(-1), C.c_int64(-1)
+    rc = lib.rad_check_per_sample(arr, len(specs), 7, x.ctypes.data, y.ctypes.data, cost, C.byref(err), C.byref(mism))
+    return dict(rc=rc, error=lib.rad_last_error().decode(), err=err.value, mism=mism.value)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("real", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["mini_lenet", "fixture", "avg", "mini_mlp"])
+def test_per_sample_layer_api(name, real):
+    """SURVEY.md section 8 f4: GpuLayer::act / backpropagate / update on GpuDC containers (one item per call, the library's batched operators
+    with batch = 1) against the reference's own layers on the host, layer by layer - outputs, Trace.Derivatives, Trace.IndexMapping (exactly),
+    input gradients, layer gradients with the scaled accumulation, parameters after update - as the reference's own GPU tests do
+    (DeepLearningCudaTest/NetLayersCudaTest.cpp:77-172)."""
+    specs = NETS[name]
+    dt = ob.dtype_of(real)
+    in_n = specs[0].in_c * specs[0].in_h * specs[0].in_w
+    out_shape = ob.out_shape(specs[-1])
+    out_n = out_shape[0] * out_shape[1] * out_shape[2]
+    rng = np.random.default_rng(13)
+    x = rng.uniform(0, 1, (2, in_n)).astype(dt)
+    cost = ob.SQUARED_ERROR if specs[-1].activation in (ob.LINEAR, ob.TANH) else ob.CROSS_ENTROPY
+    if cost == ob.CROSS_ENTROPY:
+        y = np.zeros((2, out_n), dt); y[np.arange(2), rng.integers(0, out_n, 2)] = 1
+    else:
+        y = rng.uniform(0.05, 0.95, (2, out_n)).astype(dt)
+    out = in_fresh_process(_per_sample_case, real, name, x, y, cost)
+    assert out["rc"] == 0, out["error"]
+    bar = 2e-5 if real == "f32" else 1e-11
+    assert 0 <= out["err"] < bar, f"per-sample layer API: max relative error {out['err']:.3e}"
+    assert out["mism"] == 0, f"{out['mism']} arg-max indices differ"
