@@ -54,7 +54,7 @@ SYMBOLS = [
     "dlb_net_write_gradient", "dlb_net_eval_host", "dlb_nccl_get_unique_id", "dlb_net_set_distributed",
     "dlb_shuffle_sequence", "dlb_net_train_steps", "dlb_rank_slice", "dlb_event_create", "dlb_event_destroy",
     "dlb_event_record", "dlb_event_elapsed_ms", "dlb_timing_enable", "dlb_timing_report", "dlb_net_describe_plan",
-    "dlb_net_enable_graphs", "dlb_net_enable_tensor_cores", "dlb_net_enable_step_kernel", "dlb_matmul_f32", "dlb_net_step_host_async",
+    "dlb_net_enable_graphs", "dlb_net_enable_tensor_cores", "dlb_net_enable_step_kernel", "dlb_matmul_f32", "dlb_matmul_f64", "dlb_net_step_host_async",
     "dlb_net_p2p_export", "dlb_net_set_distributed_p2p", "dlb_net_evaluate_host",
     "dlb_net_set_keep_rate", "dlb_net_mask_size", "dlb_net_set_dropout_masks", "dlb_dropout_masks", "dlb_context_device",
     "dlb_mnet_last_error", "dlb_mnet_create", "dlb_mnet_destroy", "dlb_mnet_param_count", "dlb_mnet_layer_param_offset", "dlb_mnet_set_params",
@@ -134,6 +134,7 @@ def load() -> C.CDLL:
     lib.dlb_net_set_dropout_masks.argtypes = [vp, vp]
     lib.dlb_dropout_masks.argtypes = [C.c_uint, vp, vp, i32, i64, i32, vp]
     lib.dlb_matmul_f32.argtypes = [vp, i32, i32, i32, vp, i64, i32, vp, i64, i32, vp, i32]
+    lib.dlb_matmul_f64.argtypes = [vp, i32, i32, i32, vp, i64, i32, vp, i64, i32, vp]
     lib.dlb_context_device.argtypes = [vp]
     lib.dlb_mnet_last_error.restype = C.c_char_p
     lib.dlb_mnet_create.argtypes = [vp, i32, C.POINTER(RMLayerSpec), i32, i32, C.POINTER(vp)]

@@ -1871,6 +1871,22 @@ int dlb_matmul_f32(dlb_context* ctx, int M, int N, int K, const float* A, int64_
     });
 }
 
+// The same contraction for Real = double: the DFMA micro-kernels of gemm.cuh (tcgen05 has no fp64 kind, and mma.sync.m8n8k4.f64
+// measures the same peak as the DFMA pipe on this part: tools/peaks.cu).
+int dlb_matmul_f64(dlb_context* ctx, int M, int N, int K, const double* A, int64_t lda, int a_transposed, const double* B, int64_t ldb,
+                   int b_transposed, double* C) {
+    return guarded([&] {
+        DLB_REQUIRE(ctx && A && B && C && M > 0 && N > 0 && K > 0, "Incompatible matrix-vector dimensionality");
+        use_device(ctx); ensure_op_ws(ctx);
+        TagScope tag_("matmul");
+        auto run = [&](auto al, auto bl) { gemm<double>(ctx->stream, M, N, K, al, bl, EpiStore<double>{C, (size_t)N}, ctx->ws); };
+        if (!a_transposed && !b_transposed) run(DenseRowLoader<double>{A, (size_t)lda, nullptr}, DenseRowLoader<double>{B, (size_t)ldb, nullptr});
+        else if (!a_transposed && b_transposed) run(DenseRowLoader<double>{A, (size_t)lda, nullptr}, DenseColLoader<double>{B, (size_t)ldb, nullptr});
+        else if (a_transposed && !b_transposed) run(DenseColLoader<double>{A, (size_t)lda, nullptr}, DenseRowLoader<double>{B, (size_t)ldb, nullptr});
+        else run(DenseColLoader<double>{A, (size_t)lda, nullptr}, DenseColLoader<double>{B, (size_t)ldb, nullptr});
+    });
+}
+
 #ifdef DLB_TC_PROFILE
 // Development builds only (-DDLB_TC_PROFILE): reads and clears the phase clocks of tc_gemm_kernel (not part of the ABI).
 extern "C" __attribute__((visibility("default"))) int dlb_debug_tc_profile(unsigned long long* out16) {

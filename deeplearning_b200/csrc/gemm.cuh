@@ -195,6 +195,107 @@ gemm64_kernel(int M, int N, int K, int k_per_split, AL a, BL b, EP ep, R* __rest
     }
 }
 
+// Real = double: 128 x 64 output tile, 256 threads, 8 x 4 outputs per thread, 8 reduction steps per stage.  The 64-wide micro-kernel
+// above is bound by shared-memory wavefronts in double precision (4 LDS.128 per 16 DFMA, the column operand at a 32-byte lane stride =
+// half-used wavefronts: ~47 % of the DFMA peak in steady state, profiles/r2_bench_f64.json); here a thread owns 8 rows (one broadcast
+// 64-byte run) and two column PAIRS 32 columns apart, so that the 16 lanes of a row read 256 contiguous bytes per load: 6 LDS.128 per
+// 32 DFMA and at most 12 wavefronts per 64 pipe cycles - the DFMA pipe (36.3 TFLOP/s measured, the same as DMMA) is the bound.
+template <class AL, class BL, class EP>
+__global__ void __launch_bounds__(256, 2)
+gemm_f64_kernel(int M, int N, int K, int k_per_split, AL a, BL b, EP ep, double* __restrict__ partials) {
+    constexpr int BM = 128, BN = 64, BK = 8, NT = 256, PAD = 4;
+    constexpr int EA = BM * BK / NT, EB = BN * BK / NT;     // operand elements per thread and stage (4 / 2)
+    __shared__ __align__(16) double As[2][BK][BM + PAD];
+    __shared__ __align__(16) double Bs[2][BK][BN + PAD];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int kb = blockIdx.z * k_per_split;
+    const int ke = min(K, kb + k_per_split);
+
+    double ra[EA], rb[EB];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < EA; ++q) {
+            const int e = tid + q * NT;
+            int oo, rr;
+            if (AL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BM; rr = e / BM; }
+            ra[q] = (i0 + oo < M && k0 + rr < ke) ? a(i0 + oo, k0 + rr) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < EB; ++q) {
+            const int e = tid + q * NT;
+            int oo, rr;
+            if (BL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BN; rr = e / BN; }
+            rb[q] = (j0 + oo < N && k0 + rr < ke) ? b(j0 + oo, k0 + rr) : 0.0;
+        }
+    };
+    auto store = [&](int s) {
+#pragma unroll
+        for (int q = 0; q < EA; ++q) {
+            const int e = tid + q * NT;
+            int oo, rr;
+            if (AL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BM; rr = e / BM; }
+            As[s][rr][oo] = ra[q];
+        }
+#pragma unroll
+        for (int q = 0; q < EB; ++q) {
+            const int e = tid + q * NT;
+            int oo, rr;
+            if (BL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BN; rr = e / BN; }
+            Bs[s][rr][oo] = rb[q];
+        }
+    };
+
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    fetch(kb);
+    store(0);
+    __syncthreads();
+    int s = 0;
+    for (int k0 = kb; k0 < ke; k0 += BK, s ^= 1) {
+        const bool more = k0 + BK < ke;
+        if (more) fetch(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            double ar[8], br[4];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&As[s][kk][ty * 8 + i]);
+                ar[i] = v.x; ar[i + 1] = v.y;
+            }
+            const double2 b0 = *reinterpret_cast<const double2*>(&Bs[s][kk][tx * 2]);
+            const double2 b1 = *reinterpret_cast<const double2*>(&Bs[s][kk][32 + tx * 2]);
+            br[0] = b0.x; br[1] = b0.y; br[2] = b1.x; br[3] = b1.y;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += ar[i] * br[j];
+        }
+        if (more) store(s ^ 1);
+        __syncthreads();
+    }
+
+    const bool split = gridDim.z > 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gi = i0 + ty * 8 + i;
+        if (gi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gj = j0 + (j >> 1) * 32 + tx * 2 + (j & 1);
+            if (gj >= N) continue;
+            if (split) partials[((size_t)blockIdx.z * M + gi) * N + gj] = acc[i][j];
+            else ep(gi, gj, acc[i][j]);
+        }
+    }
+}
+
 // Adds the split partials in split order and runs the epilogue once per output element.
 template <class R, class EP>
 __global__ void gemm_finalize_kernel(const R* __restrict__ partials, int splits, int M, int N, EP ep) {
@@ -226,6 +327,41 @@ template <class R, class AL, class BL, class EP>
 void gemm(cudaStream_t st, int M, int N, int K, AL a, BL b, EP ep, const GemmWorkspace& ws) {
     if (M <= 0 || N <= 0) return;
     const bool small = M <= 32 || N <= 32;
+    if constexpr (sizeof(R) == 8) {
+        if (!small) {
+            // 128 x 64 tiles, two CTAs per SM.  The reduction is split so that the grid fills whole waves of 2 x 148 CTAs: the smallest
+            // number of splits (at least two k-tiles each) whose last wave is at least 85 % full, else the fullest one.
+            constexpr int BM = 128, BN = 64, BK = 8;
+            const long tiles = (long)ceil_div(M, BM) * ceil_div(N, BN);
+            const long cap = 2L * kNumSMs;
+            const int ktiles = ceil_div(K > 0 ? K : 1, BK);
+            const size_t per_split = (size_t)M * N * sizeof(R);
+            long max_s = std::min<long>(ktiles / 2 > 0 ? ktiles / 2 : 1, per_split ? (long)(ws.bytes / per_split) : 1);
+            if (max_s > 64) max_s = 64;
+            if (max_s < 1) max_s = 1;
+            int splits = 1;
+            if (tiles < 4 * cap) {
+                double best = -1.0;
+                for (long sp = 1; sp <= max_s; ++sp) {
+                    const long ctas = tiles * sp;
+                    const double eff = (double)ctas / (double)(ceil_div<long>(ctas, cap) * cap);
+                    if (eff > best + 1e-9) { best = eff; splits = (int)sp; }
+                    if (eff >= 0.85) { splits = (int)sp; break; }
+                }
+            }
+            int k_per_split = ceil_div(ceil_div(K > 0 ? K : 1, splits), BK) * BK;
+            splits = ceil_div(K > 0 ? K : 1, k_per_split);
+            const dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
+            R* partials = static_cast<R*>(ws.ptr);
+            DLB_LAUNCH((gemm_f64_kernel<AL, BL, EP>), grid, dim3(256), st, M, N, K, k_per_split, a, b, ep, partials);
+            if (splits > 1) {
+                const size_t total = (size_t)M * N;
+                DLB_LAUNCH((gemm_finalize_kernel<R, EP>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), st,
+                           (const R*)partials, splits, M, N, ep);
+            }
+            return;
+        }
+    }
     const int BM = small ? 32 : 64, BN = BM;
     const int BK = small ? 16 : Gemm64<R>::BK;
     const long tiles = (long)ceil_div(M, BM) * ceil_div(N, BN);

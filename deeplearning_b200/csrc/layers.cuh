@@ -243,14 +243,14 @@ __global__ void act_grad_bias_partial_kernel(const R* __restrict__ delta, const 
 // (Tensor.cpp:721-734, thrust::scatter on the GPU, CudaTensor.cu:751-761); here every INPUT element looks up the
 // one window that covers it, so the pass is a single coalesced write with no memset and no scatter.
 // ---------------------------------------------------------------------------------------------------------------
-template <class R>
-__global__ void pool_forward_kernel(const R* __restrict__ x, R* __restrict__ y, int* __restrict__ map, size_t total,
+template <class R, class IDX>   // IDX = unsigned whenever the element count allows it: 64-bit divisions by run-time values cost ~100 instructions each
+__global__ void pool_forward_kernel(const R* __restrict__ x, R* __restrict__ y, int* __restrict__ map, IDX total,
                                     int C, int H, int W, int wh, int ww, int OH, int OW, int type) {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
-    const int ox = (int)(e % OW); size_t t = e / OW;
-    const int oy = (int)(t % OH); t /= OH;
-    const int c = (int)(t % C); const size_t b = t / C;
+    const int ox = (int)(e % (IDX)OW); IDX t = e / (IDX)OW;
+    const int oy = (int)(t % (IDX)OH); t /= (IDX)OH;
+    const int c = (int)(t % (IDX)C); const size_t b = t / (IDX)C;
     const R* xs = x + b * (size_t)C * H * W;
     if (type == DLB_POOL_AVERAGE) {
         R acc = R(0);
@@ -272,14 +272,14 @@ __global__ void pool_forward_kernel(const R* __restrict__ x, R* __restrict__ y, 
     if (map) map[e] = best_id;
 }
 
-template <class R>
-__global__ void pool_backward_kernel(const R* __restrict__ delta, const int* __restrict__ map, R* __restrict__ dx, size_t total,
+template <class R, class IDX>
+__global__ void pool_backward_kernel(const R* __restrict__ delta, const int* __restrict__ map, R* __restrict__ dx, IDX total,
                                      int C, int H, int W, int wh, int ww, int OH, int OW, int type) {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
-    const int x = (int)(e % W); size_t t = e / W;
-    const int y = (int)(t % H); t /= H;
-    const int c = (int)(t % C); const size_t b = t / C;
+    const int x = (int)(e % (IDX)W); IDX t = e / (IDX)W;
+    const int y = (int)(t % (IDX)H); t /= (IDX)H;
+    const int c = (int)(t % (IDX)C); const size_t b = t / (IDX)C;
     const int oy = y / wh, ox = x / ww;
     R v = R(0);
     if (oy < OH && ox < OW) {
@@ -288,6 +288,73 @@ __global__ void pool_backward_kernel(const R* __restrict__ delta, const int* __r
         else if (map[o] == (c * H + y) * W + x) v = delta[o];
     }
     dx[e] = v;
+}
+
+// The bandwidth kernels for the shape every net of BASELINE.json pools with: 2 x 2 max / min windows on maps with an even height and a
+// width that is a multiple of 4.  Rows of consecutive channels and samples are contiguous, so with H even the whole batch is ONE
+// [rows][W] matrix whose row pairs (2p, 2p + 1) pool into row p of a [rows / 2][W / 2] matrix: no (sample, channel, y) decomposition
+// except one modulo for the map's sample-relative index.  One thread = two neighbouring windows: two 16-byte (float) or four 16-byte
+// (double) loads, one 8- / 16-byte store of the outputs and one 8-byte store of the map entries; backward is the mirror image
+// (every input element written exactly once, no zero fill, no scatter).  Window scan order (ky, kx) and the strict comparison of
+// Tensor::min_max_pool (Tensor.cpp:673-716) are kept, so the index map is the reference's bit for bit.
+template <class R> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+__device__ __forceinline__ void load4_stream(const float* p, float (&v)[4]) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4_stream(const double* p, double (&v)[4]) {
+    const double2 a = __ldcs(reinterpret_cast<const double2*>(p)), b = __ldcs(reinterpret_cast<const double2*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void store4(double* p, const double (&v)[4]) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]); reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
+
+template <class R, bool IS_MAX>
+__global__ void __launch_bounds__(256) pool2x2_forward_kernel(const R* __restrict__ x, R* __restrict__ y, int* __restrict__ map, unsigned pairs,
+                                                              unsigned W, unsigned pairs_per_row, unsigned rows_per_sample) {
+    const unsigned e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= pairs) return;
+    const unsigned prow = e / pairs_per_row, px = e - prow * pairs_per_row;
+    const R* r0 = x + (size_t)prow * 2 * W + px * 4;
+    R a[4], b[4];
+    load4_stream(r0, a); load4_stream(r0 + W, b);
+    const int id0 = (int)((prow % rows_per_sample) * 2 * W + px * 4);   // index of a[0] inside its sample
+    R out[2]; int ids[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        R best = IS_MAX ? -real_limits<R>::max() : real_limits<R>::max();
+        int best_id = -1;
+        const R cur[4] = {a[2 * j], a[2 * j + 1], b[2 * j], b[2 * j + 1]};
+        const int id[4] = {id0 + 2 * j, id0 + 2 * j + 1, id0 + (int)W + 2 * j, id0 + (int)W + 2 * j + 1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (IS_MAX ? (best < cur[k]) : (best > cur[k])) { best = cur[k]; best_id = id[k]; }
+        out[j] = best; ids[j] = best_id;
+    }
+    const size_t o = (size_t)prow * (2 * pairs_per_row) + px * 2;
+    typename Vec2<R>::type yo; yo.x = out[0]; yo.y = out[1];
+    *reinterpret_cast<typename Vec2<R>::type*>(y + o) = yo;
+    if (map) *reinterpret_cast<int2*>(map + o) = make_int2(ids[0], ids[1]);
+}
+
+template <class R>
+__global__ void __launch_bounds__(256) pool2x2_backward_kernel(const R* __restrict__ delta, const int* __restrict__ map, R* __restrict__ dx, unsigned pairs,
+                                                               unsigned W, unsigned pairs_per_row, unsigned rows_per_sample) {
+    const unsigned e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= pairs) return;
+    const unsigned prow = e / pairs_per_row, px = e - prow * pairs_per_row;
+    const size_t o = (size_t)prow * (2 * pairs_per_row) + px * 2;
+    const typename Vec2<R>::type d = __ldcs(reinterpret_cast<const typename Vec2<R>::type*>(delta + o));
+    const int2 m = __ldcs(reinterpret_cast<const int2*>(map + o));
+    const int id0 = (int)((prow % rows_per_sample) * 2 * W + px * 4);
+    const int id1 = id0 + (int)W;
+    const R a[4] = {m.x == id0 ? d.x : R(0), m.x == id0 + 1 ? d.x : R(0), m.y == id0 + 2 ? d.y : R(0), m.y == id0 + 3 ? d.y : R(0)};
+    const R b[4] = {m.x == id1 ? d.x : R(0), m.x == id1 + 1 ? d.x : R(0), m.y == id1 + 2 ? d.y : R(0), m.y == id1 + 3 ? d.y : R(0)};
+    R* r0 = dx + (size_t)prow * 2 * W + px * 4;
+    store4(r0, a); store4(r0 + W, b);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -682,14 +749,36 @@ void conv_backward(const LaunchCtx& lc, int B, const ConvGeom& cg, int act, cons
     }
 }
 
+// 2 x 2 max / min pooling of an even-height, multiple-of-4-width map through 16-byte aligned pointers: the vectorised kernels apply
+template <class R>
+inline bool pool2x2_applies(int B, const dlb_layer_spec& s, const void* big, const void* small_a, const void* small_b) {
+    if (s.win_h != 2 || s.win_w != 2 || (s.in_h & 1) || (s.in_w & 3) || s.pool_type == DLB_POOL_AVERAGE) return false;
+    if ((size_t)s.in_c * s.in_h * s.in_w >= (1u << 31) || (size_t)B * s.in_c * s.in_h * s.in_w / 8 >= (1ull << 32)) return false;
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(big) | reinterpret_cast<uintptr_t>(small_a) | reinterpret_cast<uintptr_t>(small_b);
+    return (bits & 15) == 0;
+}
+
 template <class R>
 void pool_forward(const LaunchCtx& lc, int B, const dlb_layer_spec& s, const R* x, R* y, int* map) {
     TagScope tag_("pool_fwd");
     const int OH = conv_out_size(s.in_h, s.win_h, 0, s.win_h), OW = conv_out_size(s.in_w, s.win_w, 0, s.win_w);
     const size_t total = (size_t)B * s.in_c * OH * OW;
     if (!total) return;
-    DLB_LAUNCH((pool_forward_kernel<R>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, x, y, map, total,
-               s.in_c, s.in_h, s.in_w, s.win_h, s.win_w, OH, OW, s.pool_type);
+    if (pool2x2_applies<R>(B, s, x, y, map)) {
+        const unsigned pairs = (unsigned)(total / 2);
+        const dim3 grid((unsigned)ceil_div<size_t>(pairs, 256));
+        if (s.pool_type == DLB_POOL_MAX)
+            DLB_LAUNCH((pool2x2_forward_kernel<R, true>), grid, dim3(256), lc.stream, x, y, map, pairs, (unsigned)s.in_w, (unsigned)(s.in_w / 4), (unsigned)(s.in_c * OH));
+        else
+            DLB_LAUNCH((pool2x2_forward_kernel<R, false>), grid, dim3(256), lc.stream, x, y, map, pairs, (unsigned)s.in_w, (unsigned)(s.in_w / 4), (unsigned)(s.in_c * OH));
+        return;
+    }
+    if (total < (1ull << 31))
+        DLB_LAUNCH((pool_forward_kernel<R, unsigned>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, x, y, map, (unsigned)total,
+                   s.in_c, s.in_h, s.in_w, s.win_h, s.win_w, OH, OW, s.pool_type);
+    else
+        DLB_LAUNCH((pool_forward_kernel<R, size_t>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, x, y, map, total,
+                   s.in_c, s.in_h, s.in_w, s.win_h, s.win_w, OH, OW, s.pool_type);
 }
 
 template <class R>
@@ -698,8 +787,18 @@ void pool_backward(const LaunchCtx& lc, int B, const dlb_layer_spec& s, const R*
     const int OH = conv_out_size(s.in_h, s.win_h, 0, s.win_h), OW = conv_out_size(s.in_w, s.win_w, 0, s.win_w);
     const size_t total = (size_t)B * s.in_c * s.in_h * s.in_w;
     if (!total) return;
-    DLB_LAUNCH((pool_backward_kernel<R>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, delta, map, dx, total,
-               s.in_c, s.in_h, s.in_w, s.win_h, s.win_w, OH, OW, s.pool_type);
+    if (pool2x2_applies<R>(B, s, dx, delta, map)) {
+        const unsigned pairs = (unsigned)(total / 8);
+        DLB_LAUNCH((pool2x2_backward_kernel<R>), dim3((unsigned)ceil_div<size_t>(pairs, 256)), dim3(256), lc.stream, delta, map, dx, pairs,
+                   (unsigned)s.in_w, (unsigned)(s.in_w / 4), (unsigned)(s.in_c * OH));
+        return;
+    }
+    if (total < (1ull << 31))
+        DLB_LAUNCH((pool_backward_kernel<R, unsigned>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, delta, map, dx, (unsigned)total,
+                   s.in_c, s.in_h, s.in_w, s.win_h, s.win_w, OH, OW, s.pool_type);
+    else
+        DLB_LAUNCH((pool_backward_kernel<R, size_t>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), lc.stream, delta, map, dx, total,
+                   s.in_c, s.in_h, s.in_w, s.win_h, s.win_w, OH, OW, s.pool_type);
 }
 
 template <class R>

@@ -177,6 +177,9 @@ DLB_API int dlb_net_enable_step_kernel(dlb_net* net, int mode);
  * the operand is stored [K][M] / [K][N] with leading dimension lda / ldb.  use_tensor_cores selects tcgen05 (3xTF32). */
 DLB_API int dlb_matmul_f32(dlb_context* ctx, int M, int N, int K, const float* A, int64_t lda, int a_transposed, const float* B,
                            int64_t ldb, int b_transposed, float* C, int use_tensor_cores);
+/* The same for Real = double (DFMA micro-kernels; tcgen05 has no fp64 kind). */
+DLB_API int dlb_matmul_f64(dlb_context* ctx, int M, int N, int K, const double* A, int64_t lda, int a_transposed, const double* B,
+                           int64_t ldb, int b_transposed, double* C);
 
 /* One mini-batch step on explicit item indices of the resident data set (host int64 indices, n of them). */
 DLB_API int dlb_net_step_indices(dlb_net* net, const int64_t* indices, int64_t n, double learning_rate, int cost_id, double reg_factor);

@@ -41,3 +41,28 @@ def test_matmul_layouts(M, N, K, a_t, b_t, use_tc):
     err = np.abs(got - want)
     worst = float(np.max(err / bound))
     assert worst <= 1.0, f"max err/bound {worst:.3f} (max abs err {err.max():.3e})"
+
+
+@pytest.mark.parametrize("a_t,b_t", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", SHAPES + [(8192, 100, 331), (100, 700, 4099)])
+def test_matmul_f64_layouts(M, N, K, a_t, b_t):
+    """Real = double: the 128 x 64 DFMA micro-kernel (and the 32 x 32 one for skinny outputs) with its wave-filling reduction splits,
+    every operand layout; bound 4e-15 * (|A| |B|^T) element-wise (double rounding level: the products are exact in fp64 up to 2^-53
+    each, the sums are ordered differently from numpy's)."""
+    rng = np.random.default_rng(M * 5 + N * 11 + K)
+    A = rng.normal(size=(M, K))
+    B = rng.normal(size=(N, K))
+    dev = Dev()
+    try:
+        dA = dev.up(np.ascontiguousarray(A.T) if a_t else A)
+        dB = dev.up(np.ascontiguousarray(B.T) if b_t else B)
+        dC = dev.empty((M, N), np.float64)
+        _capi.check(dev.lib.dlb_matmul_f64(dev.ctx.h, M, N, K, dA, M if a_t else K, a_t, dB, N if b_t else K, b_t, dC))
+        got = dev.down(dC, (M, N), np.float64)
+    finally:
+        dev.close()
+    want = A @ B.T
+    bound = 4e-15 * (np.abs(A) @ np.abs(B).T) * max(1.0, np.sqrt(K) / 8) + 1e-300
+    err = np.abs(got - want)
+    worst = float(np.max(err / bound))
+    assert worst <= 1.0, f"max err/bound {worst:.3f} (max abs err {err.max():.3e})"

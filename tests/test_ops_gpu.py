@@ -119,19 +119,26 @@ def test_parametric_layer_forward_backward(name, real, use_gather):
 
 @pytest.mark.parametrize("real", ["f32", "f64"])
 @pytest.mark.parametrize("pool_type", [ob.POOL_MAX, ob.POOL_MIN, ob.POOL_AVERAGE])
-def test_player_forward_backward(pool_type, real):
-    """PLayer {5,10,7} window 3x4 (trailing row/columns dropped); ties resolved to the first element in scan order."""
-    spec = ob.pool((5, 10, 7), (3, 4), pool_type)
+@pytest.mark.parametrize("in_size,window", [((5, 10, 7), (3, 4)),     # generic kernel: trailing row / columns dropped
+                                            ((3, 8, 12), (2, 2)),     # vectorised 2 x 2 kernels (even height, width a multiple of 4)
+                                            ((6, 4, 4), (2, 2)),      # ... one thread per output row
+                                            ((2, 6, 6), (2, 2)),      # width not a multiple of 4: generic kernel
+                                            ((3, 5, 8), (2, 2))])     # odd height: generic kernel, last row uncovered
+def test_player_forward_backward(in_size, window, pool_type, real):
+    """PLayer forward / backward, every kernel variant (layers.cuh); small integer inputs give many exact ties inside the windows, which
+    must resolve to the first element in (ky, kx) scan order: outputs, index maps and input gradients exactly equal to the oracle's."""
+    spec = ob.pool(in_size, window, pool_type)
+    Cn, n_in = in_size[0], in_size[0] * in_size[1] * in_size[2]
     # a conv front-end only to give the oracle net a first layer whose input gradient is evaluated for the pool
-    net_specs = [ob.conv((5, 10, 7), (1, 1), 5, ob.LINEAR), spec]
+    net_specs = [ob.conv(in_size, (1, 1), Cn, ob.LINEAR), spec]
     orc = ob.OracleNet(net_specs, real)
     dt = orc.dtype
     p = np.zeros(orc.param_count, dt)
-    p[350:] = np.eye(5, dtype=dt).ravel()            # identity 1x1 convolution, zero bias: the pool sees the input itself
+    p[n_in:] = np.eye(Cn, dtype=dt).ravel()            # identity 1x1 convolution, zero bias: the pool sees the input itself
     orc.set_params(p)
     rng = np.random.default_rng(4)
-    B = 4
-    x = rng.integers(-3, 4, (B, 350)).astype(dt)      # small integers: many exact ties inside the windows
+    B = 5
+    x = rng.integers(-3, 4, (B, n_in)).astype(dt)      # small integers: many exact ties inside the windows
     out_n = orc.out_sizes[1]
     dev = Dev()
     try:
@@ -139,15 +146,15 @@ def test_player_forward_backward(pool_type, real):
         d_x, d_y, d_map = dev.up(x), dev.empty((B, out_n), dt), dev.empty((B, out_n), np.int32)
         _capi.check(fn(dev, "pool_forward", real)(dev.ctx.h, C.byref(dspec), B, d_x, d_y, d_map))
         traces = [orc.trace(x[i], np.zeros(out_n, dt), ob.COST_LINEAR) for i in range(B)]
-        want_y = np.stack([t["acts"][350:] for t in traces])
+        want_y = np.stack([t["acts"][n_in:] for t in traces])
         assert np.array_equal(dev.down(d_y, (B, out_n), dt), want_y), "pool output must be exactly equal"
         if pool_type != ob.POOL_AVERAGE:
-            want_map = np.stack([t["index_map"][350:] for t in traces])
+            want_map = np.stack([t["index_map"][n_in:] for t in traces])
             assert np.array_equal(dev.down(d_map, (B, out_n), np.int32), want_map), "index map must be exactly equal"
-        d_delta, d_dx = dev.up(np.ones((B, out_n), dt)), dev.empty((B, 350), dt)
+        d_delta, d_dx = dev.up(np.ones((B, out_n), dt)), dev.empty((B, n_in), dt)
         _capi.check(fn(dev, "pool_backward", real)(dev.ctx.h, C.byref(dspec), B, d_delta, d_map, d_dx))
-        want_dx = np.stack([t["in_grads"][350:] for t in traces])
-        assert np.array_equal(dev.down(d_dx, (B, 350), dt), want_dx), "pool input gradient must be exactly equal"
+        want_dx = np.stack([t["in_grads"][n_in:] for t in traces])
+        assert np.array_equal(dev.down(d_dx, (B, n_in), dt), want_dx), "pool input gradient must be exactly equal"
     finally:
         dev.close()
 

@@ -224,13 +224,16 @@ using std::isnan;
 using std::max;
 using std::min;
 template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) double2 { double x, y; };
 struct alignas(8) float2 { float x, y; };
 struct alignas(8) int2 { int x, y; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline int2 make_int2(int x, int y) { return int2{x, y}; }
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline void __threadfence_system() {}
 inline void __threadfence() {}
+inline void __nanosleep(unsigned) {}
 inline void __trap() { std::abort(); }
