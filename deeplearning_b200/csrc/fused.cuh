@@ -893,6 +893,12 @@ struct DenseColOnesLoader {  // value = j < ld ? base[row(red) * ld + j] : 1
         const size_t row = gather ? (size_t)gather[r] : (size_t)r;
         return base[row * ld + o];
     }
+    // strided protocol (gemm.cuh): outer indices from outer_limit() on read as 1 (the bias column)
+    __host__ __device__ bool strided() const { return gather_base == nullptr; }
+    __device__ __forceinline__ const R* origin() const { return base; }
+    __device__ __forceinline__ size_t outer_step() const { return 1; }
+    __device__ __forceinline__ size_t red_step() const { return ld; }
+    __device__ __forceinline__ int outer_limit() const { return (int)ld; }
 };
 
 template <class R>

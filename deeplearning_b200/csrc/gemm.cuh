@@ -10,6 +10,8 @@
 // epilogue, which is where the gradient scale / SGD update is fused.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dlb {
@@ -195,18 +197,83 @@ gemm64_kernel(int M, int N, int K, int k_per_split, AL a, BL b, EP ep, R* __rest
     }
 }
 
+// Optional "strided" protocol of an operand loader: strided() (host-evaluable) promises that for outer < outer_limit() the value is
+// origin()[outer * outer_step() + red * red_step()] and 1 from outer_limit() on (the bias column of ones).  The double kernel below then
+// keeps ONE running pointer per operand and two bits of state per element instead of evaluating the functor per element and k-tile:
+// the functor path spends ~30 integer instructions per fetched element (64-bit index products, the gather test and its branch), a
+// third of everything the 128 x 64 kernel issued (ncu source page, profiles/r2_full_gemm_f64_B8192.txt).
+template <class L, class = void> struct IsStrided { static constexpr bool value = false; };
+template <class L> struct IsStrided<L, std::void_t<decltype(&L::red_step)>> { static constexpr bool value = true; };
+
+// 8-byte asynchronous global -> shared copy (LDGSTS), zero fill when !valid (src-size 0: nothing is read)
+__device__ __forceinline__ void gemm_cp_async_f64(double* dst_smem, const double* src, bool valid) {
+#ifdef DLB_CUDA_EMU
+    *dst_smem = valid ? *src : 0.0;
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int n = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+#endif
+}
+__device__ __forceinline__ void gemm_cp_async_commit() {
+#ifndef DLB_CUDA_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N> __device__ __forceinline__ void gemm_cp_async_wait() {
+#ifndef DLB_CUDA_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+template <class L, int EXT, int PAD, int BK, int NT>
+struct StridedFetch {
+    static constexpr int E = EXT * BK / NT;          // elements per thread and k-tile
+    const double* p; const double* safe; size_t qstep, kstep; unsigned state; int r0, rq, soff, sstep;
+    __device__ __forceinline__ void init(const L& l, int tid, int o_base, int extent, int kb) {
+        int oo, rr, dq_o, dq_r;
+        if (L::kRedFast) { rr = tid % BK; oo = tid / BK; dq_o = NT / BK; dq_r = 0; }
+        else { oo = tid % EXT; rr = tid / EXT; dq_o = 0; dq_r = NT / EXT; }
+        safe = l.origin();
+        p = safe + (size_t)(o_base + oo) * l.outer_step() + (size_t)(kb + rr) * l.red_step();
+        qstep = (size_t)dq_o * l.outer_step() + (size_t)dq_r * l.red_step();
+        kstep = (size_t)BK * l.red_step();
+        r0 = rr; rq = dq_r; state = 0;
+        soff = rr * (EXT + PAD) + oo; sstep = dq_r * (EXT + PAD) + dq_o;   // element q lands at stage[soff + q * sstep]
+        const int limit = l.outer_limit();
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int o = o_base + oo + q * dq_o;
+            state |= (o >= extent ? 0u : (o >= limit ? 2u : 1u)) << (2 * q);   // 0: outside the matrix, 1: load, 2: the column of ones
+        }
+    }
+    // k-tiles are issued in order, so the pointer just advances; `stage` = first element of the [BK][EXT + PAD] stage
+    __device__ __forceinline__ void issue(double* stage, int k0, int ke) {
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const unsigned st = (state >> (2 * q)) & 3u;
+            const bool in_k = k0 + r0 + q * rq < ke;
+            double* dst = stage + soff + q * sstep;
+            if (st == 2u) *dst = in_k ? 1.0 : 0.0;
+            else { const bool ok = st == 1u && in_k; gemm_cp_async_f64(dst, ok ? p + q * qstep : safe, ok); }
+        }
+        p += kstep;
+    }
+};
+
 // Real = double: 128 x 64 output tile, 256 threads, 8 x 4 outputs per thread, 8 reduction steps per stage.  The 64-wide micro-kernel
 // above is bound by shared-memory wavefronts in double precision (4 LDS.128 per 16 DFMA, the column operand at a 32-byte lane stride =
 // half-used wavefronts: ~47 % of the DFMA peak in steady state, profiles/r2_bench_f64.json); here a thread owns 8 rows (one broadcast
 // 64-byte run) and two column PAIRS 32 columns apart, so that the 16 lanes of a row read 256 contiguous bytes per load: 6 LDS.128 per
 // 32 DFMA and at most 12 wavefronts per 64 pipe cycles - the DFMA pipe (36.3 TFLOP/s measured, the same as DMMA) is the bound.
-template <class AL, class BL, class EP>
+template <bool FAST, class AL, class BL, class EP>
 __global__ void __launch_bounds__(256, 2)
 gemm_f64_kernel(int M, int N, int K, int k_per_split, AL a, BL b, EP ep, double* __restrict__ partials) {
     constexpr int BM = 128, BN = 64, BK = 8, NT = 256, PAD = 4;
     constexpr int EA = BM * BK / NT, EB = BN * BK / NT;     // operand elements per thread and stage (4 / 2)
-    __shared__ __align__(16) double As[2][BK][BM + PAD];
-    __shared__ __align__(16) double Bs[2][BK][BN + PAD];
+    constexpr int NS = FAST ? 3 : 2;                          // stages: cp.async two k-tiles ahead / register-staged double buffer
+    __shared__ __align__(16) double As[NS][BK][BM + PAD];
+    __shared__ __align__(16) double Bs[NS][BK][BN + PAD];
 
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
@@ -216,19 +283,21 @@ gemm_f64_kernel(int M, int N, int K, int k_per_split, AL a, BL b, EP ep, double*
 
     double ra[EA], rb[EB];
     auto fetch = [&](int k0) {
+        {
 #pragma unroll
-        for (int q = 0; q < EA; ++q) {
-            const int e = tid + q * NT;
-            int oo, rr;
-            if (AL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BM; rr = e / BM; }
-            ra[q] = (i0 + oo < M && k0 + rr < ke) ? a(i0 + oo, k0 + rr) : 0.0;
-        }
+            for (int q = 0; q < EA; ++q) {
+                const int e = tid + q * NT;
+                int oo, rr;
+                if (AL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BM; rr = e / BM; }
+                ra[q] = (i0 + oo < M && k0 + rr < ke) ? a(i0 + oo, k0 + rr) : 0.0;
+            }
 #pragma unroll
-        for (int q = 0; q < EB; ++q) {
-            const int e = tid + q * NT;
-            int oo, rr;
-            if (BL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BN; rr = e / BN; }
-            rb[q] = (j0 + oo < N && k0 + rr < ke) ? b(j0 + oo, k0 + rr) : 0.0;
+            for (int q = 0; q < EB; ++q) {
+                const int e = tid + q * NT;
+                int oo, rr;
+                if (BL::kRedFast) { rr = e % BK; oo = e / BK; } else { oo = e % BN; rr = e / BN; }
+                rb[q] = (j0 + oo < N && k0 + rr < ke) ? b(j0 + oo, k0 + rr) : 0.0;
+            }
         }
     };
     auto store = [&](int s) {
@@ -254,13 +323,7 @@ gemm_f64_kernel(int M, int N, int K, int k_per_split, AL a, BL b, EP ep, double*
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
-    fetch(kb);
-    store(0);
-    __syncthreads();
-    int s = 0;
-    for (int k0 = kb; k0 < ke; k0 += BK, s ^= 1) {
-        const bool more = k0 + BK < ke;
-        if (more) fetch(k0 + BK);
+    auto multiply = [&](int s) {
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             double ar[8], br[4];
@@ -277,8 +340,39 @@ gemm_f64_kernel(int M, int N, int K, int k_per_split, AL a, BL b, EP ep, double*
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] += ar[i] * br[j];
         }
-        if (more) store(s ^ 1);
+    };
+    if constexpr (FAST) {
+        // three stages, asynchronous copies two k-tiles ahead, ONE barrier per k-tile: the stage refilled in iteration `it` was
+        // multiplied in iteration it - 1, which every thread has left when it passes this iteration's barrier
+        StridedFetch<AL, BM, PAD, BK, NT> fa; StridedFetch<BL, BN, PAD, BK, NT> fb;
+        fa.init(a, tid, i0, M, kb); fb.init(b, tid, j0, N, kb);
+        int k_next = kb, s_next = 0;
+        auto issue = [&]() {
+            if (k_next < ke) { fa.issue(&As[s_next][0][0], k_next, ke); fb.issue(&Bs[s_next][0][0], k_next, ke); }
+            gemm_cp_async_commit();                       // (an empty group at the tail keeps the wait count uniform)
+            k_next += BK; s_next = s_next == 2 ? 0 : s_next + 1;
+        };
+        issue(); issue();
+        int s = 0;
+        for (int k0 = kb; k0 < ke; k0 += BK, s = s == 2 ? 0 : s + 1) {
+            gemm_cp_async_wait<1>();
+            __syncthreads();
+            issue();
+            multiply(s);
+        }
+        gemm_cp_async_wait<0>();
+    } else {
+        fetch(kb);
+        store(0);
         __syncthreads();
+        int s = 0;
+        for (int k0 = kb; k0 < ke; k0 += BK, s ^= 1) {
+            const bool more = k0 + BK < ke;
+            if (more) fetch(k0 + BK);
+            multiply(s);
+            if (more) store(s ^ 1);
+            __syncthreads();
+        }
     }
 
     const bool split = gridDim.z > 1;
@@ -353,7 +447,12 @@ void gemm(cudaStream_t st, int M, int N, int K, AL a, BL b, EP ep, const GemmWor
             splits = ceil_div(K > 0 ? K : 1, k_per_split);
             const dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
             R* partials = static_cast<R*>(ws.ptr);
-            DLB_LAUNCH((gemm_f64_kernel<AL, BL, EP>), grid, dim3(256), st, M, N, K, k_per_split, a, b, ep, partials);
+            bool fast = false;
+            if constexpr (IsStrided<AL>::value && IsStrided<BL>::value) fast = a.strided() && b.strided();
+            if constexpr (IsStrided<AL>::value && IsStrided<BL>::value) {
+                if (fast) DLB_LAUNCH((gemm_f64_kernel<true, AL, BL, EP>), grid, dim3(256), st, M, N, K, k_per_split, a, b, ep, partials);
+            }
+            if (!fast) DLB_LAUNCH((gemm_f64_kernel<false, AL, BL, EP>), grid, dim3(256), st, M, N, K, k_per_split, a, b, ep, partials);
             if (splits > 1) {
                 const size_t total = (size_t)M * N;
                 DLB_LAUNCH((gemm_finalize_kernel<R, EP>), dim3((unsigned)ceil_div<size_t>(total, 256)), dim3(256), st,

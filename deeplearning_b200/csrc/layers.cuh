@@ -44,6 +44,12 @@ struct DenseRowLoader {  // value = base[row(outer) * ld + red]; `gather` (optio
         const size_t row = gather ? (size_t)gather[o] : (size_t)o;
         return base[row * ld + r];
     }
+    // strided protocol (gemm.cuh): without a gather the value is origin()[o * outer_step() + r * red_step()]
+    __host__ __device__ bool strided() const { return gather == nullptr; }
+    __device__ __forceinline__ const R* origin() const { return base; }
+    __device__ __forceinline__ size_t outer_step() const { return ld; }
+    __device__ __forceinline__ size_t red_step() const { return 1; }
+    __device__ __forceinline__ int outer_limit() const { return 0x7fffffff; }
 };
 
 template <class R>
@@ -54,6 +60,11 @@ struct DenseColLoader {  // value = base[row(red) * ld + outer]; `gather` (optio
         const size_t row = gather ? (size_t)gather[r] : (size_t)r;
         return base[row * ld + o];
     }
+    __host__ __device__ bool strided() const { return gather == nullptr; }
+    __device__ __forceinline__ const R* origin() const { return base; }
+    __device__ __forceinline__ size_t outer_step() const { return 1; }
+    __device__ __forceinline__ size_t red_step() const { return ld; }
+    __device__ __forceinline__ int outer_limit() const { return 0x7fffffff; }
 };
 
 // Element (pixel = (b, oy, ox), k = (c, ky, kx)) of the receptive-field matrix of a mini-batch, with zero padding

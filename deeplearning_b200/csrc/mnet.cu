@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -173,6 +174,7 @@ struct MNetT final : dlb_mnet {
         cudaFree(params); cudaFree(grads); cudaFree(norms); cudaFree(ws.ptr);
     }
     void free_batch() {
+        drop_graph();                                 // (the captured step holds these buffers' addresses)
         for (R* p : {x_bm, y_bm, x_tm, y_tm, out_bm}) cudaFree(p);
         for (auto* v : {&H, &D, &A, &G}) { for (R* p : *v) cudaFree(p); v->clear(); }
         x_bm = y_bm = x_tm = y_tm = out_bm = nullptr; cap = 0;
@@ -320,10 +322,37 @@ struct MNetT final : dlb_mnet {
         MN_CUDA(cudaSetDevice(device));
         ensure(n); upload(x, y, (int)n); resident_B = (int)n;
     }
+    // A step on the resident mini-batch is ~400 dependent launches of 2-10 us (the recurrence), with no host decision in between: the
+    // second step of a (batch, cost, rate, regularisation) combination is captured into a CUDA graph and every later one replays it
+    // (same kernels, same order: bit-identical to the eager step).  DLB_MNET_GRAPH=0 keeps the eager launches (A/B measurements).
+    struct StepGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int B = 0, cost = -1; double lr = 0, reg = 0; long long launches = 0; } sg;
+    void drop_graph() {
+        if (sg.exec) cudaGraphExecDestroy(sg.exec);
+        if (sg.graph) cudaGraphDestroy(sg.graph);
+        sg = StepGraph{};
+    }
     void learn_resident(int cost_id, double lr, double reg, int64_t steps) override {
         MN_CUDA(cudaSetDevice(device));
         if (resident_B <= 0) throw std::invalid_argument("no resident mini-batch (dlb_mnet_set_batch)");
-        for (int64_t s = 0; s < steps; ++s) { forward(resident_B); backward(resident_B, cost_id); update(resident_B, lr, reg); }
+        auto eager = [&] { forward(resident_B); backward(resident_B, cost_id); update(resident_B, lr, reg); };
+        int64_t s = 0;
+        static const bool graphs_on = [] { const char* e = std::getenv("DLB_MNET_GRAPH"); return !(e && e[0] == '0'); }();
+        if (graphs_on && !g_timing_on && steps >= 2) {
+            if (!sg.exec || sg.B != resident_B || sg.cost != cost_id || sg.lr != lr || sg.reg != reg) {
+                drop_graph();
+                eager(); ++s;                                      // first step eager (one-time kernel attributes are set outside a capture)
+                const long long before = g_launch_count.load();
+                MN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                try { eager(); } catch (...) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(st, &junk); if (junk) cudaGraphDestroy(junk); throw; }
+                MN_CUDA(cudaStreamEndCapture(st, &sg.graph));
+                sg.launches = g_launch_count.load() - before;
+                g_launch_count.store(before);
+                MN_CUDA(cudaGraphInstantiate(&sg.exec, sg.graph, 0));
+                sg.B = resident_B; sg.cost = cost_id; sg.lr = lr; sg.reg = reg;
+            }
+            for (; s < steps; ++s) { MN_CUDA(cudaGraphLaunch(sg.exec, st)); g_launch_count.fetch_add(sg.launches, std::memory_order_relaxed); }
+        }
+        for (; s < steps; ++s) eager();
     }
 };
 

@@ -46,6 +46,7 @@ class Dev:
 
 
 def timed(dev, calls, reps):
+    reps = int(os.environ.get("BENCH_OPS_REPS", reps))   # 1 under ncu
     """calls: list of zero-argument launches (one per buffer set); returns microseconds per launch"""
     for f in calls:
         f()
