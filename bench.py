@@ -197,6 +197,34 @@ def measured_peaks():
         return {}
 
 
+def compute_fraction(net, key: str, batch: int, us: float, real: str, pk: dict) -> dict:
+    """Arithmetic side of a contraction / convolution kernel: algorithmic flops per launch (2 per multiply-add, the reference's own
+    operation count - NOT the 3x of the 3xTF32 scheme) against the measured peak of the pipe the kernel runs on (profiles/peaks_r2.json:
+    3xTF32-equivalent tcgen05, packed FFMA2, DFMA).  Empty for the bandwidth kernels."""
+    layer_s, tag, kernel = key.split(":", 2)
+    l = int(layer_s)
+    if l < 0 or l >= net.layers_count() or kernel == "gemm_finalize_kernel":
+        return {}
+    in_n, out_n = net.layer_in_size(l), net.layer_out_size(l)
+    spec = net._specs[l]
+    if tag in ("conv_pool_fwd", "conv_pool_bwd", "conv_fwd", "conv_dK", "conv_dX"):
+        flops = 2.0 * batch * out_n * spec.in_c * spec.win_h * spec.win_w
+    elif tag in ("full_fwd", "full_dW", "full_dX", "head_dW"):
+        flops = 2.0 * batch * in_n * out_n
+    elif tag == "head":
+        flops = 4.0 * batch * in_n * out_n
+    else:
+        return {}
+    if real == "f64":
+        pipe, peak = "dfma", pk.get("dfma_tflops")
+    elif "tc_gemm" in kernel:
+        pipe, peak = "tcgen05 3xTF32 (fp32-equivalent)", pk.get("tf32_3x_equivalent_fp32_tflops")
+    else:
+        pipe, peak = "ffma2", pk.get("ffma2_tflops")
+    tf = flops / (us * 1e-6) / 1e12
+    return {"tflops": tf, "compute_pipe": pipe, "compute_peak_tflops": peak, "frac_of_compute_peak": (tf / peak) if peak else None}
+
+
 CIFAR_FLOP_PER_SAMPLE = 119_946_240      # SURVEY.md section 8(d), config 3
 CIFAR_BYTES_PER_SAMPLE_F32 = 1_826_370
 
@@ -442,7 +470,8 @@ def main():
             ab = algorithmic_bytes(net, k, batch, sz)
             per_launch_us = 1e3 * t / n
             kernels.append({"kernel": k, "launches_per_step": n / t_steps, "us_per_launch": per_launch_us, "share": t / total_ms,
-                            "algorithmic_bytes": ab, "gbs": (ab / (per_launch_us * 1e-6) / 1e9) if ab else None})
+                            "algorithmic_bytes": ab, "gbs": (ab / (per_launch_us * 1e-6) / 1e9) if ab else None,
+                            **compute_fraction(net, k, batch, per_launch_us, args.real, measured_peaks())})
         peak, peak_src = hbm_peak()
         top = kernels[0] if kernels else {"kernel": None, "gbs": None, "share": None, "us_per_launch": None}
         line["roofline"] = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
@@ -470,7 +499,8 @@ def main():
             ab = algorithmic_bytes(net, k, 8192, sz)
             us = 1e3 * t / n
             big["kernels"].append({"kernel": k, "us_per_launch": us, "share": t / tot, "gbs": (ab / (us * 1e-6) / 1e9) if ab else None,
-                                   "frac_of_hbm_peak": (ab / (us * 1e-6) / 1e9 / peak) if ab else None})
+                                   "frac_of_hbm_peak": (ab / (us * 1e-6) / 1e9 / peak) if ab else None,
+                                   **compute_fraction(net, k, 8192, us, args.real, measured_peaks())})
         bps8 = step_bytes_per_sample(net, 8192, sz)
         big["step_roofline_frac"] = big["value"] / (peak * 1e9 / bps8)
         big["step_roofline_note"] = "against the UNFUSED per-kernel byte accounting of SURVEY 8(d): fusion credit, not achieved DRAM bandwidth (per-kernel frac_of_hbm_peak above is)"
@@ -614,7 +644,8 @@ def main():
                 ab = algorithmic_bytes(net, k, mine, sz)
                 us = 1e3 * t / n
                 kernels.append({"kernel": k, "launches_per_step": n / t_steps, "us_per_launch": us, "share": t / total_ms,
-                                "gbs": (ab / (us * 1e-6) / 1e9) if ab else None, "frac_of_hbm_peak": (ab / (us * 1e-6) / 1e9 / peak) if ab else None})
+                                "gbs": (ab / (us * 1e-6) / 1e9) if ab else None, "frac_of_hbm_peak": (ab / (us * 1e-6) / 1e9 / peak) if ab else None,
+                                **compute_fraction(net, k, mine, us, args.real, measured_peaks())})
             line["kernels"] = kernels
             line["serial_kernel_us_per_step"] = 1e3 * total_ms / t_steps
             if kernels:

@@ -12,8 +12,9 @@ if "roofline" in d:
                                                                    None if k["gbs"] is None else round(k["gbs"])))
     c5 = d.get("config5_on_1_gpu", {})
     for k in c5.get("kernels", []):
-        print("  [B=8192] %-44s %9.2f us share %.3f GB/s %s frac %s" % (k["kernel"], k["us_per_launch"], k["share"],
-              None if k["gbs"] is None else round(k["gbs"]), None if k["frac_of_hbm_peak"] is None else round(k["frac_of_hbm_peak"], 3)))
+        print("  [B=8192] %-44s %9.2f us share %.3f GB/s %s frac %s | %s" % (k["kernel"], k["us_per_launch"], k["share"],
+              None if k["gbs"] is None else round(k["gbs"]), None if k["frac_of_hbm_peak"] is None else round(k["frac_of_hbm_peak"], 3),
+              "" if not k.get("frac_of_compute_peak") else "%.1f TFLOP/s = %.2f of %s" % (k["tflops"], k["frac_of_compute_peak"], k["compute_pipe"])))
     c5 = {k: v for k, v in c5.items() if k != "kernels"}
     print(" cfg5@1gpu", c5, " cpu", d.get("cpu_baseline", {}).get("value"), d.get("cpu_baseline", {}).get("cores"))
 print(" clocks", d.get("clocks"))
