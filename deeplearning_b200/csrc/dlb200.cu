@@ -390,6 +390,17 @@ struct NetT final : dlb_net {
     int cp_rows = 0;                                    // rows of cp_partial the last backward wrote (the reduction sums these)
     bool imap1_holds_selectors = false;                 // the last fused forward left one-byte window selectors in imap[1] (conv28.cu)
     R* head_partial = nullptr; int head_chunks = 0;     // [head_chunks][n * (in_n + 1)]
+    // Transposed copy W^T [in_n][out_n] of each hidden NLayer's weights (float, tensor-core steps): the input-gradient contraction
+    // dx[b][k] = sum_n g[b][n] W[n][k] reads W along its strided index; from W^T both of its operands are reduction-contiguous, i.e. the
+    // K-major plan of tc_gemm (TMA tiles, only the lo parts computed) instead of the transposing one.  Rebuilt at the start of every step
+    // on the head's side stream, beside the forward pass (1.15 MB at LeNet: ~3 us, off the critical path).  DLB_DX_WT=0 disables it,
+    // DLB_DX_WT_MIN sets the smallest mini-batch it is used for.
+    std::vector<R*> wT;
+    cudaEvent_t wt_fork_ev = nullptr, wt_done_ev = nullptr;
+    bool wt_enabled = [] { const char* e = std::getenv("DLB_DX_WT"); return !(e && e[0] == '0'); }();
+    // Measured (B200, LeNet): 78.5 -> 72.0 us for the contraction at mini-batch 8 192 (step 16.55 -> 16.94 M samples/s), but at mini-batch
+    // 256 the extra kernel costs more than the contraction gains (63.6 -> 64.4 us per step): used from 1 024 samples per GPU up.
+    int wt_min_batch = [] { const char* e = std::getenv("DLB_DX_WT_MIN"); return e ? std::atoi(e) : 1024; }();
     int head_chunk_cap = 0;
     int* d_cursor = nullptr;                            // device-side offset of the current batch in the epoch permutation
     static constexpr int kHeadChunk = 32;
@@ -528,6 +539,13 @@ struct NetT final : dlb_net {
             for (auto& e : fork_events) DLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ws_side.bytes = 64u << 20;
             DLB_CUDA(cudaMalloc(&ws_side.ptr, ws_side.bytes));
+            DLB_CUDA(cudaEventCreateWithFlags(&wt_fork_ev, cudaEventDisableTiming));
+            DLB_CUDA(cudaEventCreateWithFlags(&wt_done_ev, cudaEventDisableTiming));
+            wT.assign((size_t)L(), nullptr);
+            if constexpr (std::is_same_v<R, float>) {
+                for (int l = std::max(plan.first_fc, 1); l < L() - 1; ++l)
+                    if (layers[(size_t)l].s.type == DLB_LAYER_FULL) wT[(size_t)l] = dev_alloc<R>((size_t)layers[(size_t)l].in_n * layers[(size_t)l].out_n);
+            }
         }
         DLB_CUDA(cudaStreamCreateWithFlags(&side_copy, cudaStreamNonBlocking));
         DLB_CUDA(cudaStreamCreateWithFlags(&side_d2h, cudaStreamNonBlocking));
@@ -622,6 +640,8 @@ struct NetT final : dlb_net {
         if (side_dw) { cudaStreamSynchronize(side_dw); cudaStreamDestroy(side_dw); }
         for (auto& e : fork_events) cudaEventDestroy(e);
         if (ws_side.ptr) cudaFree(ws_side.ptr);
+        if (wt_fork_ev) cudaEventDestroy(wt_fork_ev);
+        if (wt_done_ev) cudaEventDestroy(wt_done_ev);
         if (side_copy) { cudaStreamSynchronize(side_copy); cudaStreamDestroy(side_copy); }
         if (side_d2h) {
             cudaStreamSynchronize(side_d2h);
@@ -937,6 +957,29 @@ struct NetT final : dlb_net {
 #endif
         bool forked_dw = false;
         int l = 0;
+        bool wt_ready = false, wt_forked = false;
+#ifndef DLB_CUDA_EMU
+        if constexpr (std::is_same_v<R, float>) {
+            if (wt_enabled && tc_for(B) && B >= wt_min_batch && !wT.empty()) {
+                cudaStream_t ts = st;
+                if (fork) {
+                    DLB_CUDA(cudaEventRecord(wt_fork_ev, st));
+                    DLB_CUDA(cudaStreamWaitEvent(side_head, wt_fork_ev, 0));
+                    ts = side_head; wt_forked = true;
+                }
+                for (int t = std::max(plan.first_fc, 1); t < Ln - 1; ++t) {
+                    if (!wT[(size_t)t]) continue;
+                    const auto& T = layers[(size_t)t];
+                    g_tag_layer = t;
+                    TagScope tag_("wT");
+                    DLB_LAUNCH((transpose_kernel<R>), dim3((unsigned)ceil_div<size_t>(T.in_n, 32), (unsigned)ceil_div<size_t>(T.out_n, 32)), dim3(256), ts,
+                               (const R*)(params + T.param_off + T.bias_n), wT[(size_t)t], (int)T.out_n, (int)T.in_n);
+                    wt_ready = true;
+                }
+                if (wt_forked && wt_ready) DLB_CUDA(cudaEventRecord(wt_done_ev, side_head));
+            }
+        }
+#endif
         if (plan.has_cp) {
             g_tag_layer = 0;
             const auto& Y = layers[0];
@@ -1004,6 +1047,11 @@ struct NetT final : dlb_net {
             const size_t smem = (size_t)Y.out_n * (size_t)Y.in_n * sizeof(R);
             const int grid = std::min((int)ceil_div(B, 8), 4 * kNumSMs);
             const HeadInputPartials<R> hp{head_partial_splits > 1 ? head_partials : nullptr, head_partial_splits, params + Pv.param_off, Pv.s.activation, out[(size_t)h - 1]};
+#ifndef DLB_CUDA_EMU
+            // the transposed weights of the hidden NLayers (side stream, since the start of the step) are joined here, in front of the head:
+            // the input-gradient contraction that needs them is launched programmatically right behind the head kernel
+            if (wt_forked && wt_ready) DLB_CUDA(cudaStreamWaitEvent(st, wt_done_ev, 0));
+#endif
             {
                 TagScope tag_("head");
                 if (plan.head_nmax == 10)
@@ -1070,10 +1118,15 @@ struct NetT final : dlb_net {
                         const auto& Pv = layers[(size_t)l - 1];
                         const int prev_act = Pv.s.type == DLB_LAYER_FULL ? Pv.s.activation : 0;
                         const TcOperand A{gl, (long long)Y.out_n, 0, nullptr, nullptr, -1};
-                        const TcOperand Bo{params + Y.param_off + Y.bias_n, (long long)Y.in_n, 1, nullptr, nullptr, -1};
-                        tc_gemm<kRedContig, kOuterContig>(st, B, (int)Y.in_n, (int)Y.out_n, A, Bo,
-                                EpiStoreTimesDeriv<float>{in_grad[(size_t)l], (size_t)Y.in_n, out[(size_t)l - 1], prev_act}, lc.ws,
-                                /*pdl: the head kernel is the previous kernel on this stream and triggers early*/ l == Ln - 2 && pdl_enabled);
+                        const EpiStoreTimesDeriv<float> epi{in_grad[(size_t)l], (size_t)Y.in_n, out[(size_t)l - 1], prev_act};
+                        const bool pdl = /*the head kernel is the previous kernel on this stream and triggers early*/ l == Ln - 2 && pdl_enabled;
+                        if (wt_ready && wT[(size_t)l]) {   // W^T [in_n][out_n]: both operands reduction-contiguous (K-major plan, TMA where the rows are 16-byte multiples)
+                            const TcOperand Bo{wT[(size_t)l], (long long)Y.out_n, 0, nullptr, nullptr, -1};
+                            tc_gemm<kRedContig, kRedContig>(st, B, (int)Y.in_n, (int)Y.out_n, A, Bo, epi, lc.ws, pdl);
+                        } else {
+                            const TcOperand Bo{params + Y.param_off + Y.bias_n, (long long)Y.in_n, 1, nullptr, nullptr, -1};
+                            tc_gemm<kRedContig, kOuterContig>(st, B, (int)Y.in_n, (int)Y.out_n, A, Bo, epi, lc.ws, pdl);
+                        }
                     }
                     done_tc = true;
                 }

@@ -760,6 +760,20 @@ void conv_backward(const LaunchCtx& lc, int B, const ConvGeom& cg, int act, cons
     }
 }
 
+// out[c][r] = in[r][c] for a row-major [rows][cols] matrix (32 x 32 tiles through padded shared memory, both sides coalesced).
+// Used once per step for the transposed copy of a hidden NLayer's weights that feeds the input-gradient contraction K-major (dlb200.cu).
+template <class R>
+__global__ void __launch_bounds__(256) transpose_kernel(const R* __restrict__ in, R* __restrict__ out, int rows, int cols) {
+    __shared__ R tile[32][33];
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = ty; j < 32; j += 8)
+        if (r0 + j < rows && c0 + tx < cols) tile[j][tx] = in[(size_t)(r0 + j) * cols + c0 + tx];
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8)
+        if (c0 + j < cols && r0 + tx < rows) out[(size_t)(c0 + j) * rows + r0 + tx] = tile[tx][j];
+}
+
 // 2 x 2 max / min pooling of an even-height, multiple-of-4-width map through 16-byte aligned pointers: the vectorised kernels apply
 template <class R>
 inline bool pool2x2_applies(int B, const dlb_layer_spec& s, const void* big, const void* small_a, const void* small_b) {

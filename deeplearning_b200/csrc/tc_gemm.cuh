@@ -439,12 +439,19 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
                         const int gr = c.i0 + quad * 32 + lane;
                         if (gr < M) {
                             const int n_cols = min(32, N - (c.j0 + c0));
+                            // (a full block runs without a trip-count test: the shared-memory loads of eight columns are in flight together -
+                            // with ONE warp per scheduler draining the accumulator, the epilogue is bound by its own dependent-issue latency)
+                            if (n_cols == 32 && !split) {
+#pragma unroll 8
+                                for (int q = 0; q < 32; ++q) ep(gr, c.j0 + c0 + q, tile[q * 33 + lane]);
+                            } else {
 #pragma unroll 4
-                            for (int q = 0; q < n_cols; ++q) {
-                                const float accv = tile[q * 33 + lane];
-                                const int gj = c.j0 + c0 + q;
-                                if (split) partials[((size_t)c.z * M + gr) * N + gj] = accv;
-                                else ep(gr, gj, accv);
+                                for (int q = 0; q < n_cols; ++q) {
+                                    const float accv = tile[q * 33 + lane];
+                                    const int gj = c.j0 + c0 + q;
+                                    if (split) partials[((size_t)c.z * M + gr) * N + gj] = accv;
+                                    else ep(gr, gj, accv);
+                                }
                             }
                         }
                         __syncwarp();
@@ -456,13 +463,25 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
                         __syncwarp();
                         const int gj = c.j0 + c0 + lane;
                         if (gj < N) {
+                            const int gr0 = c.i0 + quad * 32;
+                            if (gr0 + 32 <= M) {   // a full block: no row test, eight rows in flight (see above)
+                                if (split) {
+                                    float* pp = partials + ((size_t)c.z * M + gr0) * N + gj;
+#pragma unroll 8
+                                    for (int r = 0; r < 32; ++r) pp[(size_t)r * N] = tile[r * 33 + lane];
+                                } else {
+#pragma unroll 8
+                                    for (int r = 0; r < 32; ++r) ep(gr0 + r, gj, tile[r * 33 + lane]);
+                                }
+                            } else {
 #pragma unroll 4
-                            for (int r = 0; r < 32; ++r) {
-                                const int gr = c.i0 + quad * 32 + r;
-                                if (gr >= M) break;
-                                const float accv = tile[r * 33 + lane];
-                                if (split) partials[((size_t)c.z * M + gr) * N + gj] = accv;
-                                else ep(gr, gj, accv);
+                                for (int r = 0; r < 32; ++r) {
+                                    const int gr = gr0 + r;
+                                    if (gr >= M) break;
+                                    const float accv = tile[r * 33 + lane];
+                                    if (split) partials[((size_t)c.z * M + gr) * N + gj] = accv;
+                                    else ep(gr, gj, accv);
+                                }
                             }
                         }
                         __syncwarp();

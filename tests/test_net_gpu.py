@@ -94,6 +94,37 @@ def test_learn_matches_oracle(name, batch, n_items, lam, real):
     assert np.array_equal(gpu.predict(x), orc.eval(x)), "predicted classes differ"
 
 
+WT_NETS = {
+    "mini_lenet": MINI_LENET,
+    # a 23-wide hidden layer: rows of W^T that are no multiple of 16 bytes, i.e. the cp.async producers instead of TMA
+    "lenet_23": [ob.conv((1, 12, 12), (3, 3), 4, ob.RELU), ob.pool((4, 10, 10), (2, 2), ob.POOL_MAX),
+                 ob.full((4, 5, 5), 23, ob.TANH), ob.full((1, 1, 23), 10, ob.SOFTMAX)],
+    # two hidden NLayers behind the first: both take their input gradient from transposed weights
+    "mlp_4": [ob.full((1, 1, 20), 15, ob.SIGMOID), ob.full((1, 1, 15), 13, ob.TANH), ob.full((1, 1, 13), 12, ob.SIGMOID),
+              ob.full((1, 1, 12), 10, ob.SOFTMAX)],
+}
+
+
+@pytest.mark.parametrize("name,batch,n_items", [("mini_lenet", 8, 50), ("lenet_23", 6, 30), ("mlp_4", 10, 64)])
+def test_input_gradient_from_transposed_weights(name, batch, n_items, monkeypatch):
+    """The hidden NLayers' input-gradient contraction fed from the per-step transposed copy of the weights (K-major plan of tc_gemm.cuh;
+    the library uses it from 1 024 samples per GPU up, DLB_DX_WT_MIN lowers the bar for this test): same weights after Net::learn as the
+    oracle, and the transposing plan likewise."""
+    specs, cost = WT_NETS[name], ob.CROSS_ENTROPY
+    lam = 0.1
+    results = {}
+    for wt_min in ("1", "1000000"):
+        monkeypatch.setenv("DLB_DX_WT_MIN", wt_min)   # read when the net is created
+        orc, gpu = H.make_pair(specs, "f32", seed=21)
+        x, y = H.synthetic_batch(orc, n_items, "f32", seed=22, lo=0.0, hi=1.0, one_hot=cost == ob.CROSS_ENTROPY)
+        gpu.reset_random_generator(4)
+        gpu.learn(x, y, batch, 2, 0.05, dl.CostFunctionId(cost), lam)
+        results[wt_min] = gpu.get_params()
+    orc.learn(x, y, batch, 2, 0.05, cost, lam, threads=1, perms=dl.shuffle_sequence(4, n_items, 2))
+    H.assert_close("parameters (transposed-weights plan)", results["1"], orc.get_params(), "f32", rtol_mult=20)
+    H.assert_close("parameters (transposing plan)", results["1000000"], orc.get_params(), "f32", rtol_mult=20)
+
+
 @pytest.mark.parametrize("real,tc_mode", [("f32", 2), ("f32", 1), ("f32", 0), ("f64", 1)])
 def test_lenet_step_full_size(real, tc_mode):
     """BASELINE configs[1] at its real size: one mini-batch of 256 through LeNet; gradient = sum over the batch of the
