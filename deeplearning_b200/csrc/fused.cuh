@@ -917,6 +917,18 @@ struct EpiStoreTimesDeriv {  // input gradient times the previous layer's activa
         const size_t o = (size_t)i * ld + j;
         out[o] = prev_act ? deriv_from_value<R>(prev_act, prev_y[o]) * acc : acc;
     }
+    __device__ __forceinline__ bool row4_ok() const {
+        return (ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) | (prev_act ? reinterpret_cast<uintptr_t>(prev_y) : 0)) & 15) == 0;
+    }
+    __device__ __forceinline__ void row4(int i, int j, float4 a) const {
+        const size_t o = (size_t)i * ld + j;
+        if (prev_act) {
+            const float4 p = *reinterpret_cast<const float4*>(prev_y + o);
+            a.x = deriv_from_value<R>(prev_act, p.x) * a.x; a.y = deriv_from_value<R>(prev_act, p.y) * a.y;
+            a.z = deriv_from_value<R>(prev_act, p.z) * a.z; a.w = deriv_from_value<R>(prev_act, p.w) * a.w;
+        }
+        *reinterpret_cast<float4*>(out + o) = a;
+    }
 };
 
 template <class R>

@@ -136,6 +136,18 @@ struct EpiFullForward {  // y[b][n] = act(acc + bias[n]);  deriv optional  (NLay
         y[o] = v;
         if (deriv) deriv[o] = d;
     }
+    __device__ __forceinline__ bool row4_ok() const {
+        return (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(deriv) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+    }
+    __device__ __forceinline__ void row4(int b, int n, float4 a) const {
+        const float4 bv = *reinterpret_cast<const float4*>(bias + n);
+        float4 v, d;
+        v.x = apply_activation<R>(act, a.x + bv.x, d.x); v.y = apply_activation<R>(act, a.y + bv.y, d.y);
+        v.z = apply_activation<R>(act, a.z + bv.z, d.z); v.w = apply_activation<R>(act, a.w + bv.w, d.w);
+        const size_t o = (size_t)b * N + n;
+        *reinterpret_cast<float4*>(y + o) = v;
+        if (deriv) *reinterpret_cast<float4*>(deriv + o) = d;
+    }
 };
 
 template <class R>
@@ -163,6 +175,9 @@ template <class R>
 struct EpiStore {
     R* out; size_t ld;
     __device__ __forceinline__ void operator()(int i, int j, R acc) const { out[(size_t)i * ld + j] = acc; }
+    // optional row-segment protocol of the tensor-core epilogue (tc_gemm.cuh): four consecutive columns j .. j + 3 of row i at once
+    __device__ __forceinline__ bool row4_ok() const { return (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0; }
+    __device__ __forceinline__ void row4(int i, int j, float4 a) const { *reinterpret_cast<float4*>(out + (size_t)i * ld + j) = a; }
 };
 
 template <class R>

@@ -63,6 +63,10 @@ static_assert(kProducerWarps % 4 == 0, "epilogue warp -> TMEM lane quadrant mapp
 
 // Epilogues that set `static constexpr bool kLaneIsRow = true` are called with consecutive lanes on consecutive ROWS of
 // the output tile (the convolution layouts [b][f][pixel]: rows are pixels); the default is consecutive columns.
+// Epilogues with the optional row-segment protocol (row4_ok / row4): the accumulator registers of a lane ARE 32 consecutive columns of
+// its row, so they are stored straight from registers as eight 16-byte segments - no shared-memory transposition, no warp barriers.
+template <class EP, class = void> struct HasRow4 { static constexpr bool value = false; };
+template <class EP> struct HasRow4<EP, std::void_t<decltype(&EP::row4_ok)>> { static constexpr bool value = true; };
 template <class EP, class = void> struct LaneIsRow { static constexpr bool value = false; };
 template <class EP> struct LaneIsRow<EP, std::void_t<decltype(EP::kLaneIsRow)>> { static constexpr bool value = EP::kLaneIsRow; };
 
@@ -402,6 +406,17 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
         const int quad = warp & 3;
         float* tile = epi_stage + (warp - kEpiWarp0) * (32 * 33);
         const bool split = n_splits > 1;
+        // Row segments straight from the accumulator registers (see HasRow4) - only for outputs one column tile wide (the NLayer forward and
+        // its split partials: rows of <= 512 bytes, so the 16-byte pieces of a warp's store fill whole lines between them).  Measured on the
+        // 2 880-wide input gradient the lane-per-row stores (16 bytes at an 11.5 KB stride) are SLOWER than the staged, line-wide ones:
+        // 55.9 -> 71.3 us at mini-batch 8 192; on the forward 49.7 -> 49.0 us.
+        bool direct_rows = false;
+        if constexpr (!LaneIsRow<EP>::value) {
+            if ((N & 3) == 0 && tiles_n == 1) {
+                if (split) direct_rows = (reinterpret_cast<uintptr_t>(partials) & 15) == 0;
+                else if constexpr (HasRow4<EP>::value) direct_rows = ep.row4_ok();
+            }
+        }
         int j = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
             const TileCoord c = decode_tile(t, tiles_m, tiles_n, K, k_per_split);
@@ -455,6 +470,22 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
                             }
                         }
                         __syncwarp();
+                    } else if (direct_rows) {
+                        // lane = row: its 32 registers are 128 contiguous bytes of the output row (or of the split's partial row)
+                        const int gr = c.i0 + quad * 32 + lane;
+                        if (gr < M) {
+                            float* prow = split ? partials + ((size_t)c.z * M + gr) * N : nullptr;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int gj = c.j0 + c0 + 4 * i;
+                                if (gj < N) {   // (N is a multiple of 4 here: a group of four columns is valid as a whole)
+                                    const float4 a4 = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                                                  __uint_as_float(v[4 * i + 3]));
+                                    if (split) *reinterpret_cast<float4*>(prow + gj) = a4;
+                                    else if constexpr (HasRow4<EP>::value) ep.row4(gr, gj, a4);
+                                }
+                            }
+                        }
                     } else {
                         // 32 x 32 block: lane = row in registers -> shared (padded) -> lane = column, so that every warp-wide access
                         // of the epilogue (stores, bias / previous-activation loads) covers 128 contiguous bytes
