@@ -411,17 +411,10 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
         // 2 880-wide input gradient the lane-per-row stores (16 bytes at an 11.5 KB stride) are SLOWER than the staged, line-wide ones:
         // 55.9 -> 71.3 us at mini-batch 8 192; on the forward 49.7 -> 49.0 us.
         bool direct_rows = false;
-        // Wider outputs with the same protocol: the 32 x 32 block still goes through shared memory, but as 16-byte pieces - eight STS.128
-        // into an XOR-swizzled [row][8 x float4] image (conflict-free per quarter warp), eight LDS.128 back with eight lanes per row, eight
-        // 16-byte stores that each write four full 128-byte row segments: ~40 instructions per block instead of ~130, line-wide stores kept.
-        bool staged16 = false;
         if constexpr (!LaneIsRow<EP>::value) {
-            if ((N & 3) == 0) {
-                bool vec_ok = false;
-                if (split) vec_ok = (reinterpret_cast<uintptr_t>(partials) & 15) == 0;
-                else if constexpr (HasRow4<EP>::value) vec_ok = ep.row4_ok();
-                direct_rows = vec_ok && tiles_n == 1;
-                staged16 = vec_ok && tiles_n != 1;
+            if ((N & 3) == 0 && tiles_n == 1) {
+                if (split) direct_rows = (reinterpret_cast<uintptr_t>(partials) & 15) == 0;
+                else if constexpr (HasRow4<EP>::value) direct_rows = ep.row4_ok();
             }
         }
         int j = 0;
@@ -493,28 +486,6 @@ tc_gemm_kernel(int M, int N, int K, int k_per_split, int tiles_m, int tiles_n, i
                                 }
                             }
                         }
-                    } else if (staged16) {
-                        float4* tile4 = reinterpret_cast<float4*>(tile);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            tile4[lane * 8 + (i ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                                                             __uint_as_float(v[4 * i + 3]));
-                        __syncwarp();
-                        const int sub = lane >> 3, piece = lane & 7;          // pass p: row p * 4 + sub of the block, columns 4 * piece .. + 3
-                        const int gj = c.j0 + c0 + 4 * piece;
-                        const int gr0 = c.i0 + quad * 32 + sub;
-                        if (gj < N) {   // (N is a multiple of 4 here: a group of four columns is valid as a whole)
-#pragma unroll
-                            for (int p = 0; p < 8; ++p) {
-                                const int r = p * 4 + sub, gr = gr0 + p * 4;
-                                const float4 a4 = tile4[r * 8 + (piece ^ (r & 7))];
-                                if (gr < M) {
-                                    if (split) *reinterpret_cast<float4*>(partials + ((size_t)c.z * M + gr) * N + gj) = a4;
-                                    else if constexpr (HasRow4<EP>::value) ep.row4(gr, gj, a4);
-                                }
-                            }
-                        }
-                        __syncwarp();
                     } else {
                         // 32 x 32 block: lane = row in registers -> shared (padded) -> lane = column, so that every warp-wide access
                         // of the epilogue (stores, bias / previous-activation loads) covers 128 contiguous bytes
