@@ -225,6 +225,52 @@ def compute_fraction(net, key: str, batch: int, us: float, real: str, pk: dict) 
     return {"tflops": tf, "compute_pipe": pipe, "compute_peak_tflops": peak, "frac_of_compute_peak": (tf / peak) if peak else None}
 
 
+def pool_roofline(dl, ctx, peak_gbs: float) -> dict:
+    """The bandwidth kernels of the path measured as bandwidth kernels: PLayer max 2x2 forward / backward (layers.cuh, pool2x2_*) on
+    CIFAR-deep's first pooling layer at mini-batch 1024 (32 x 32 x 32 float per sample: 201 MB of algorithmic traffic per launch - input,
+    output and int32 index map), CUDA events around 24 launches over three buffer sets in rotation (604 MB: nothing is served from L2)."""
+    import ctypes as C
+    from deeplearning_b200 import _capi
+    lib = ctx.lib
+    B, c, h, w = 1024, 32, 32, 32
+    spec = dl.PLayer((c, h, w), (2, 2), dl.PoolTypeId.MAX)
+    n_in, n_out = B * c * h * w, B * c * (h // 2) * (w // 2)
+    ptrs = []
+
+    def alloc(nbytes):
+        p = C.c_void_p()
+        _capi.check(lib.dlb_malloc(ctx.h, nbytes, C.byref(p)))
+        ptrs.append(p)
+        return p
+    try:
+        x_host = np.random.default_rng(3).random(n_in, dtype=np.float32)
+        sets = []
+        for _ in range(3):
+            x, y, m, dx = alloc(n_in * 4), alloc(n_out * 4), alloc(n_out * 4), alloc(n_in * 4)
+            _capi.check(lib.dlb_memcpy_h2d(ctx.h, x, x_host.ctypes.data, x_host.nbytes))
+            sets.append((x, y, m, dx))
+        out = {"workload": "PLayer max 2x2 on {32,32,32} float, mini-batch 1024 (CIFAR-deep layer 1)", "algorithmic_bytes": n_in * 4 + n_out * 8,
+               "peak": peak_gbs, "unit": "GB/s"}
+        for name, call in (("forward", lambda b: lib.dlb_pool_forward_f32(ctx.h, C.byref(spec), B, b[0], b[1], b[2])),
+                           ("backward", lambda b: lib.dlb_pool_backward_f32(ctx.h, C.byref(spec), B, b[1], b[2], b[3]))):
+            for b in sets:
+                _capi.check(call(b))
+            ctx.synchronize()
+            e0, e1 = dl.Event(ctx), dl.Event(ctx)
+            e0.record()
+            for r in range(24):
+                _capi.check(call(sets[r % 3]))
+            e1.record()
+            ctx.synchronize()
+            us = 1e3 * e0.elapsed_ms(e1) / 24
+            gbs = out["algorithmic_bytes"] / us / 1e3
+            out[name] = {"us_per_launch": us, "achieved": gbs, "frac": gbs / peak_gbs}
+        return out
+    finally:
+        for p in ptrs:
+            lib.dlb_free(ctx.h, p)
+
+
 CIFAR_FLOP_PER_SAMPLE = 119_946_240      # SURVEY.md section 8(d), config 3
 CIFAR_BYTES_PER_SAMPLE_F32 = 1_826_370
 
@@ -624,6 +670,10 @@ def main():
         line["cpu_baseline"]["one_thread"] = {"value": r1["value"], "unit": "samples/s", "cores": 1, "sample": r1["sample"]}
         if pk:
             line["measured_peaks"] = {k: pk[k] for k in ("tf32_tcgen05_cta1_m128_n256_tflops", "tf32_3x_equivalent_fp32_tflops", "ffma2_tflops", "dfma_tflops", "dmma_m8n8k4_tflops") if k in pk}
+        try:
+            line["pool_roofline"] = pool_roofline(dl, ctx, hbm_peak()[0])
+        except Exception as exc:  # noqa: BLE001
+            line["pool_roofline"] = {"error": str(exc)[:200]}
     if world > 1:
         same_after = ranks_identical()
         # per-kernel table of this rank at N > 1 (instrumented pass on every rank at once: the exchange kernel waits for its peers)
